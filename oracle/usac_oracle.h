@@ -1,0 +1,110 @@
+/*
+ * usac_oracle.h - C ABI of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY. This library is a CPU restatement of the hypothesize-and-verify path of the reference
+ * (MathsionYang/Ransac, `usac/`). It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it. The product (ransac_b200/) never links, imports or
+ * falls back to it.
+ *
+ * Parity status: the homography and Sampson scoring functions are pinned by the 46 known-answer vectors recovered
+ * from the reference's shipped datasets/results (tests/golden/scoring_kat.npz). Everything else (line/essential
+ * scoring, solvers, samplers, SPRT, termination) is "parity unpinned" by the reference's own artefacts - the
+ * reference cannot be compiled here (needs OpenCV-contrib/Eigen/nanoflann) - and is anchored on (a) identities
+ * (solver output annihilates its sample, det F = 0 ...), (b) OpenCV primitives called through Python cv2 4.13
+ * (tests/golden/make_cv_golden.py) and (c) the glibc random() stream of this container's libc.
+ *
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ */
+#ifndef USAC_ORACLE_H
+#define USAC_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enums mirror usac/model.hpp:10-13 */
+enum { ORC_EST_LINE2D = 1, ORC_EST_HOMOGRAPHY = 2, ORC_EST_FUNDAMENTAL = 3, ORC_EST_ESSENTIAL = 4 };
+enum { ORC_SAMPLER_UNIFORM = 1, ORC_SAMPLER_PROGRESSIVE_NAPSAC = 2, ORC_SAMPLER_NAPSAC = 3, ORC_SAMPLER_PROSAC = 4 };
+enum { ORC_NEIGH_NONE = 0, ORC_NEIGH_KNN = 1, ORC_NEIGH_GRID = 2 };
+/* random source of the samplers */
+enum { ORC_RNG_GLIBC = 0 /* reference stream: glibc random(), uniform_sampler.hpp:42-54 */,
+       ORC_RNG_PHILOX = 1 /* counter based, keyed by (seed, hypothesis id) */,
+       ORC_RNG_TABLE = 2 /* caller supplied K x m index table */ };
+
+/* ---- RNG streams ---- */
+typedef struct orc_glibc_rand orc_glibc_rand;
+orc_glibc_rand* orc_glibc_rand_new(unsigned seed);             /* srandom(seed) */
+void orc_glibc_rand_free(orc_glibc_rand*);
+int32_t orc_glibc_rand_next(orc_glibc_rand*);                   /* random() */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* ---- scoring (usac/quality/quality.hpp:60-101 over Estimator::GetError) ---- */
+/* per-point error, float32, one rounding per operator, no FMA */
+void orc_errors(int estimator, const float* points, int n, const float* model, float* err_out);
+/* count/sum exactly as Quality::getNumberInliers; inliers_out may be NULL; thr==0 is not special here.
+ * flagged_out (may be NULL) = number of points with |err-thr| <= band_rel*thr. */
+void orc_score(int estimator, const float* points, int n, const float* model, float thr, int* count_out,
+               float* sum_out, int* inliers_out, double band_rel, int* flagged_out);
+/* cv::Mat::inv() of a 3x3 CV_32F (OpenCV core, closed-form cofactor path): returns 0 when det==0 (all zeros) */
+int orc_inv3x3(const float* m, float* out);
+
+/* ---- minimal solvers: returns number of models written to models_out (<= 3 models x 9 floats; line: 3 floats) ---- */
+int orc_solve_minimal(int estimator, const float* points, const int* sample, float* models_out);
+/* pieces exposed for unit tests */
+int orc_solve_cubic(const double c[4], double roots[3]);       /* c0 x^3 + c1 x^2 + c2 x + c3, cv::solveCubic order */
+int orc_fundamental_is_valid(const float* points, const float* F, const int* sample);
+int orc_null_space(double* A, int rows, double* basis_out);    /* A rows x 9 row-major, destroyed; basis (9-rows) x 9 */
+
+/* ---- samplers ---- */
+typedef struct orc_sampler orc_sampler;
+orc_sampler* orc_sampler_new(int kind, int rng, int n, int m, uint64_t seed);
+void orc_sampler_free(orc_sampler*);
+/* neighbourhood structures for NAPSAC */
+void orc_sampler_set_knn(orc_sampler*, const int* neighbors, int k);
+void orc_sampler_set_grid(orc_sampler*, const float* points, int cell_size);
+void orc_sampler_set_termination_length(orc_sampler*, unsigned len);   /* PROSAC coupling */
+unsigned orc_sampler_largest_sample_size(orc_sampler*);
+const unsigned* orc_sampler_growth_function(orc_sampler*);
+/* generate the sample of hypothesis `hyp_id` (sequential samplers ignore hyp_id and advance their state) */
+void orc_sampler_generate(orc_sampler*, uint64_t hyp_id, int* sample_out);
+void orc_philox_unique(uint64_t seed, uint64_t hyp_id, uint32_t stream, int n, int m, int* out);
+
+/* ---- termination ---- */
+unsigned orc_standard_termination(unsigned inliers, unsigned n, int m, float confidence, unsigned max_iterations);
+
+/* ---- grid neighbours (usac/utils/nearest_neighbors.cpp:160-201) as CSR: cell id per point, members sorted ---- */
+void orc_grid_cells(const float* points, int n, int cell_size, int* cell_of_point, int* members, int* cell_start,
+                    int* ncells_out);
+
+/* ---- full robust fit (usac/ransac/ransac.cpp:14-238, main loop :58-139; no final polish) ---- */
+typedef struct {
+    int estimator, sampler, rng;
+    float threshold, confidence;
+    unsigned max_iterations;
+    int sprt;                 /* 0/1 */
+    int batch;                /* 0 = reference-sequential; K>0 = batched(K) semantics (state frozen within a round) */
+    int neighbors, knn, cell_size;
+    uint64_t seed;
+    const int* sample_table;  /* rng==ORC_RNG_TABLE: K_total x m */
+    unsigned sample_table_rows;
+    const int* knn_table;     /* neighbors==KNN: n x knn */
+} orc_config;
+
+typedef struct {
+    float model[9];
+    int inliers;
+    float score;
+    unsigned iterations;      /* value of `iters` when the loop ended */
+    unsigned samples_drawn;
+    long long best_hyp;       /* sample index that produced the best model, -1 if none */
+    int best_model_idx;       /* which root of that sample */
+    unsigned long long evals; /* GetError calls executed */
+    unsigned models_scored;
+} orc_result;
+
+int orc_ransac(const orc_config* cfg, const float* points, int n, orc_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
