@@ -1,0 +1,439 @@
+// pipeline.cuh - the kernels around the scoring kernel for one round of K samples per problem:
+//   sample_kernel  -> solve_kernel -> prepare_kernel -> score_kernel -> reduce_kernel -> [all-gather] -> select_kernel
+// One host sync per round (the FitState records are copied back after select_kernel).
+#pragma once
+#include "strict_math.cuh"
+
+struct RoundArgs {
+    const ProblemDesc* prob;
+    const int* active;           // slot -> problem id
+    FitState* state;             // per problem
+    const float* aos;
+    int est, K, S, m, mstride;   // samples per round, models per sample, sample size, K*S
+    // sampler
+    int sampler, rng, neighbors;
+    uint64_t seed;
+    const int* table; unsigned table_rows;     // USAC_RNG_TABLE (problem 0)
+    const unsigned* growth;                    // PROSAC growth functions (ProblemDesc::growth_off)
+    const int* knn; const int* cell_of_point; const int* members; const int* rank_in_cell; const int* cell_start;
+    unsigned* cursors;                         // NAPSAC use counters
+    int* seeds;                                // [slot][K] NAPSAC seed points of the round
+    // buffers, all [slot][...]
+    int* samples;                // [K][m]
+    float* models_raw;           // [K][S][9]
+    int* nmodels;                // [K]
+    int* offsets;                // [K]  exclusive prefix sum of nmodels
+    float* recs;                 // [K*S][USAC_REC_STRIDE]
+    int* mvalid;                 // [1]
+    int* part_cnt; float* part_sum; int nchunks;   // [nchunks][K*S]
+    uint2* sample_scores;        // [K] per-sample best (cnt | midx<<30, sum bits); with nranks>1: [nranks][ceil(K/nranks)]
+    // fit parameters
+    float thr, confidence;
+    unsigned max_iterations;
+    const unsigned* term_tables; // standard termination bound by inlier count (ProblemDesc::term_off)
+    int rank, nranks;
+    // SPRT (sprt.cuh)
+    int sprt;
+    const int* pool;             // shuffled point pools (ProblemDesc::pool_off)
+    struct SprtModelResult* sprt_res;   // [slot][K*S]
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Guard-band constants of the fast scoring path (see score.cuh). u = 2^-24. All bounds are deliberately loose
+// (worst-case linear error accumulation); a looser band only sends a few more points through the strict path.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void make_record(int est, const float* model, float thr, const ProblemDesc& pd, float* rec) {
+    const float u = 5.9604645e-8f;
+#pragma unroll
+    for (int i = 0; i < USAC_REC_STRIDE; i++) rec[i] = 0.f;
+    const int w = est == USAC_EST_LINE2D ? 3 : 9;
+    for (int i = 0; i < w; i++) rec[i] = model[i];
+    rec[REC_THR] = thr;
+    const float* f = model;
+    if (est == USAC_EST_HOMOGRAPHY) {
+        cv_inv3x3(model, rec + REC_HINV);
+        const float* g = rec + REC_HINV;
+        const float T = 2.f * thr;
+        const float bx1 = fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2]);
+        const float by1 = fabsf(f[3]) * pd.mx1 + fabsf(f[4]) * pd.my1 + fabsf(f[5]);
+        const float bz1 = fabsf(f[6]) * pd.mx1 + fabsf(f[7]) * pd.my1 + fabsf(f[8]);
+        const float bx2 = fabsf(g[0]) * pd.mx2 + fabsf(g[1]) * pd.my2 + fabsf(g[2]);
+        const float by2 = fabsf(g[3]) * pd.mx2 + fabsf(g[4]) * pd.my2 + fabsf(g[5]);
+        const float bz2 = fabsf(g[6]) * pd.mx2 + fabsf(g[7]) * pd.my2 + fabsf(g[8]);
+        const float e1 = fmaxf(pd.mx1, pd.my1) + 2.f * T, e2 = fmaxf(pd.mx2, pd.my2) + 2.f * T;   // |estimate| near the threshold
+        const float k = 1.4142136f * 8.f * u;
+        const float c0 = k * (e1 + e2) + 8.f * u * T;
+        const float C = k * (bz2 * (fmaxf(bx1, by1) + e2 * bz1) + bz1 * (fmaxf(bx2, by2) + e1 * bz2));
+        // |t| <= c0 + C|r|, and |r| <= (1 + r^2)/2
+        rec[REC_BAND] = c0 + 0.5f * C;
+        rec[REC_BAND + 1] = 0.5f * C;
+    } else if (est == USAC_EST_FUNDAMENTAL) {
+        const float ba = fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2]);
+        const float bb = fabsf(f[3]) * pd.mx1 + fabsf(f[4]) * pd.my1 + fabsf(f[5]);
+        const float bc = fabsf(f[0]) * pd.mx2 + fabsf(f[3]) * pd.my2 + fabsf(f[6]);
+        const float bd = fabsf(f[1]) * pd.mx2 + fabsf(f[4]) * pd.my2 + fabsf(f[7]);
+        const float bn = pd.mx2 * ba + pd.my2 * bb + fabsf(f[6]) * pd.mx1 + fabsf(f[7]) * pd.my1 + fabsf(f[8]);
+        const float dn = 18.f * u * bn, dabcd = 5.f * u * (ba + bb + bc + bd);
+        const float eta = 1e-3f * thr;
+        const float gq = 1.5f * sqrtf(thr) * dn + thr * dabcd;
+        rec[REC_BAND] = eta + 16.f * u * thr;                 // * den
+        rec[REC_BAND + 1] = gq * gq / eta + dn * dn;          // + const
+    } else if (est == USAC_EST_ESSENTIAL) {
+        const float T = 2.f * thr;
+        const float bl1 = fabsf(f[0]) * pd.mx2 + fabsf(f[3]) * pd.my2 + fabsf(f[6]);
+        const float bl2 = fabsf(f[1]) * pd.mx2 + fabsf(f[4]) * pd.my2 + fabsf(f[7]);
+        const float bl3 = fabsf(f[2]) * pd.mx2 + fabsf(f[5]) * pd.my2 + fabsf(f[8]);
+        const float bt1 = fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2]);
+        const float bt2 = fabsf(f[3]) * pd.mx1 + fabsf(f[4]) * pd.my1 + fabsf(f[5]);
+        const float bt3 = fabsf(f[6]) * pd.mx1 + fabsf(f[7]) * pd.my1 + fabsf(f[8]);
+        const float ba1 = pd.mx1 * bl1 + pd.my1 * bl2 + bl3, bb1 = pd.mx2 * bt1 + pd.my2 * bt2 + bt3;
+        rec[REC_BAND] = 10.f * u * ba1 + 10.f * u * T * (bl1 + bl2);       // * 1/|l12|
+        rec[REC_BAND + 1] = 10.f * u * bb1 + 10.f * u * T * (bt1 + bt2);   // * 1/|t12|
+        rec[REC_BAND + 2] = 32.f * u * T;
+    } else {
+        rec[REC_BAND] = 5.f * u * (fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2])) + 2.f * u * thr;
+    }
+}
+
+// records for host-supplied models (usac_gpu_score): one thread per model, no compaction
+__global__ void prepare_models_kernel(int est, const float* __restrict__ models, int M, int model_stride, float thr,
+                                      const ProblemDesc* prob, int problem, float* __restrict__ recs) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    float rec[USAC_REC_STRIDE];
+    make_record(est, models + (size_t)q * model_stride, thr, prob[problem], rec);
+    float4* dst = reinterpret_cast<float4*>(recs + (size_t)q * USAC_REC_STRIDE);
+#pragma unroll
+    for (int i = 0; i < USAC_REC_STRIDE / 4; i++) dst[i] = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Samplers (uniform_sampler.hpp, prosac_sampler.hpp, napsac_sampler.hpp). One thread per sample of the round.
+// ---------------------------------------------------------------------------------------------------------------
+
+// PROSAC: subset size after the call with hypothesis counter t (prosac_sampler.hpp:147-156): min{n >= m : g[n-1] >= t}
+__device__ __forceinline__ unsigned prosac_subset(const unsigned* __restrict__ g, unsigned n_points, unsigned m, unsigned t) {
+    unsigned lo = m, hi = n_points;          // answer in [m, n_points]
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (g[mid - 1] >= t) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// NAPSAC seed points of the round (napsac_sampler.hpp:77, 103-108)
+__global__ void napsac_seed_kernel(const RoundArgs a) {
+    const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.K) return;
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const uint64_t hyp = (uint64_t)a.state[pid].samples_drawn + j;
+    int p = 0;
+    if (a.neighbors == USAC_NEIGH_KNN) {
+        philox_unique(a.seed, hyp, 4, pd.n, 1, &p);
+    } else {
+        int tries = 0;
+        for (; tries < pd.n; tries++) {
+            philox_unique(a.seed, hyp, 16 + (uint32_t)tries, pd.n, 1, &p);
+            const int c = a.cell_of_point[pd.grid_off + p];
+            const int cnt = a.cell_start[pd.cell_start_off + c + 1] - a.cell_start[pd.cell_start_off + c] - 1;
+            if (cnt >= a.m) break;
+        }
+        if (tries == pd.n) p = -1;           // no usable neighbourhood anywhere: uniform fallback for this sample
+    }
+    a.seeds[(size_t)slot * a.K + j] = p;
+}
+
+__global__ void napsac_commit_kernel(const RoundArgs a) {
+    const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.K) return;
+    const int pid = a.active[slot];
+    const int p = a.seeds[(size_t)slot * a.K + j];
+    if (p >= 0) atomicAdd(&a.cursors[a.prob[pid].cursor_off + p], (unsigned)(a.m - 1));
+}
+
+__global__ void sample_kernel(const RoundArgs a) {
+    const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.K) return;
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    FitState& st = a.state[pid];
+    const uint64_t hyp = (uint64_t)st.samples_drawn + j;
+    int s[8];
+    const int m = a.m, n = pd.n;
+    if (a.rng == USAC_RNG_TABLE && pid == 0 && hyp < a.table_rows) {
+        for (int i = 0; i < m; i++) s[i] = a.table[hyp * m + i];
+    } else if (a.sampler == USAC_SAMPLER_PROSAC) {
+        // prosac_sampler.hpp:117-172 replayed in closed form. Sequential rule for the call with counter t and subset
+        // size n_prev: n_prev > L -> draw m from [0, L] and leave (t, n) alone; else n = n_prev + (t > g[n_prev-1]),
+        // draw m-1 from [0, n-2] plus point n-1, t++. While the sampler stays in PROSAC mode t_j = t0 + j and
+        // n_j = max(n0, F(t_j)), F(t) = min{n : g[n-1] >= t}; once n_prev exceeds L everything freezes.
+        const unsigned* g = a.growth + pd.growth_off;
+        const unsigned t0 = st.prosac_t, n0 = st.prosac_n, L = st.prosac_term_len;
+        auto n_before = [&](int jj) -> unsigned { return jj == 0 ? n0 : max(n0, prosac_subset(g, n, m, t0 + jj - 1)); };
+        unsigned n_prev = n_before(j);
+        const bool term_mode = n_prev > L;
+        unsigned t_next, n_next;
+        if (term_mode) {
+            int lo = 0, hi = j;                                   // first call of the round in termination mode
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (n_before(mid) > L) hi = mid; else lo = mid + 1; }
+            n_prev = n_before(lo);
+            philox_unique(a.seed, hyp, 2, (int)min(L + 1, (unsigned)n), m, s);          // closed range [0, L], clipped to the data
+            t_next = t0 + lo; n_next = n_prev;
+        } else {
+            const unsigned nn = max(n0, prosac_subset(g, n, m, t0 + j));
+            philox_unique(a.seed, hyp, 3, (int)nn - 1, m - 1, s);                       // closed range [0, nn-2]
+            s[m - 1] = (int)nn - 1;
+            t_next = t0 + j + 1; n_next = nn;
+        }
+        if (j == a.K - 1) { st.prosac_t_next = t_next; st.prosac_n_next = n_next; st.prosac_largest_next = max(st.prosac_largest, n_next); }
+    } else if (a.sampler == USAC_SAMPLER_NAPSAC) {
+        const int* seeds = a.seeds + (size_t)slot * a.K;
+        const int p = seeds[j];
+        if (p < 0) {
+            philox_unique(a.seed, hyp, 0, n, m, s);
+        } else {
+            unsigned c = a.cursors[pd.cursor_off + p];
+            for (int i = 0; i < j; i++) c += (seeds[i] == p) ? (unsigned)(m - 1) : 0u;   // earlier uses within this round
+            s[0] = p;
+            if (a.neighbors == USAC_NEIGH_KNN) {
+                const int* row = a.knn + pd.knn_off + (size_t)pd.knn * p;
+                for (int i = 1; i < m; i++) s[i] = row[pd.knn - 1 - (int)((c + i - 1) % (unsigned)pd.knn)];   // farthest first, cyclic
+            } else {
+                const int cell = a.cell_of_point[pd.grid_off + p];
+                const int cs = a.cell_start[pd.cell_start_off + cell];
+                const int cnt = a.cell_start[pd.cell_start_off + cell + 1] - cs - 1;
+                const int rk = a.rank_in_cell[pd.grid_off + p];
+                for (int i = 1; i < m; i++) {
+                    const int pos = (int)((c + i - 1) % (unsigned)cnt);
+                    s[i] = a.members[pd.grid_off + cs + pos + (pos >= rk ? 1 : 0)];       // other cell members, ascending
+                }
+            }
+        }
+    } else {
+        philox_unique(a.seed, hyp, 0, n, m, s);
+    }
+    int* dst = a.samples + ((size_t)slot * a.K + j) * m;
+    for (int i = 0; i < m; i++) dst[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Minimal solvers: one thread per sample (Estimator::EstimateModel, estimator.hpp:19)
+// ---------------------------------------------------------------------------------------------------------------
+template <int EST>
+__global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
+    const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.K) return;
+    int* nm = a.nmodels + (size_t)slot * a.K + j;
+    if (a.nranks > 1 && (j % a.nranks) != a.rank) { *nm = 0; return; }     // another rank's hypothesis
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+    int s[8];
+    const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
+    for (int i = 0; i < a.m; i++) s[i] = src[i];
+    float out[27];
+    const int k = solve_minimal<EST>(pts, s, out);
+    float* dst = a.models_raw + ((size_t)slot * a.K + j) * a.S * 9;
+    for (int i = 0; i < k * 9; i++) dst[i] = out[i];
+    *nm = k;
+}
+
+// standalone Estimator API (usac_gpu_estimate)
+template <int EST>
+__global__ void __launch_bounds__(64) estimate_kernel(const float* __restrict__ pts, const int* __restrict__ samples, int K, int m, int S,
+                                                     float* __restrict__ models, int* __restrict__ nmodels) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    int s[8];
+    for (int i = 0; i < m; i++) s[i] = samples[(size_t)j * m + i];
+    float out[27];
+    for (int i = 0; i < 27; i++) out[i] = 0.f;
+    const int k = solve_minimal<EST>(pts, s, out);
+    for (int i = 0; i < S * 9; i++) models[(size_t)j * S * 9 + i] = out[i];
+    nmodels[j] = k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prepare: compact the valid models of the round in (sample, root) order and build their scoring records
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* sm /* >= 33 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? sm[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        sm[lane] = w;
+    }
+    __syncthreads();
+    const int before = (warp > 0 ? sm[warp - 1] : 0) + x - v;
+    *total = sm[nw - 1];
+    __syncthreads();
+    return before;
+}
+
+__global__ void __launch_bounds__(256) prepare_kernel(const RoundArgs a) {
+    __shared__ int sm[33];
+    const int slot = blockIdx.x;
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const int per = (a.K + blockDim.x - 1) / blockDim.x;
+    const int j0 = threadIdx.x * per, j1 = min(j0 + per, a.K);
+    const int* nm = a.nmodels + (size_t)slot * a.K;
+    int local = 0;
+    for (int j = j0; j < j1; j++) local += nm[j];
+    int total;
+    int off = block_exclusive_scan(local, &total, sm);
+    float rec[USAC_REC_STRIDE];
+    for (int j = j0; j < j1; j++) {
+        a.offsets[(size_t)slot * a.K + j] = off;
+        const int k = nm[j];
+        for (int i = 0; i < k; i++) {
+            make_record(a.est, a.models_raw + (((size_t)slot * a.K + j) * a.S + i) * 9, a.thr, pd, rec);
+            float4* dst = reinterpret_cast<float4*>(a.recs + ((size_t)slot * a.mstride + off + i) * USAC_REC_STRIDE);
+#pragma unroll
+            for (int w = 0; w < USAC_REC_STRIDE / 4; w++) dst[w] = make_float4(rec[4 * w], rec[4 * w + 1], rec[4 * w + 2], rec[4 * w + 3]);
+        }
+        off += k;
+    }
+    if (threadIdx.x == 0) a.mvalid[slot] = total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reduce: per-sample best score (sum the chunk partials in fixed order -> deterministic), packed for the exchange
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool score_bigger(int ca, float sa, int cb, float sb) {   // Score::bigger, quality.hpp:22-26
+    return ca > cb || (ca == cb && sa > sb);
+}
+
+__global__ void reduce_kernel(const RoundArgs a) {
+    const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.K) return;
+    if (a.nranks > 1 && (j % a.nranks) != a.rank) return;
+    const int k = a.nmodels[(size_t)slot * a.K + j];
+    const int off = a.offsets[(size_t)slot * a.K + j];
+    int bc = -1, bi = 0;
+    float bs = 0.f;
+    for (int i = 0; i < k; i++) {
+        int c = 0;
+        float s = 0.f;
+        for (int ch = 0; ch < a.nchunks; ch++) {
+            const size_t o = ((size_t)slot * a.nchunks + ch) * a.mstride + off + i;
+            c += a.part_cnt[o];
+            s += a.part_sum[o];
+        }
+        if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
+    }
+    if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }                       // no model: midx 3 marks "nothing to compare"
+    const int per_rank = (a.K + a.nranks - 1) / a.nranks;
+    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + j / a.nranks) : ((size_t)slot * a.K + j);
+    a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// select: best-update and adaptive termination with the reference's sequential semantics (ransac.cpp:58-139):
+// the prefix best over the samples of the round, the first sample t at which iters reaches max_iters, the result
+// as of that sample. One CTA per problem.
+// ---------------------------------------------------------------------------------------------------------------
+struct SelKey { unsigned long long key; int j; };
+__device__ __forceinline__ SelKey sel_max(SelKey a, SelKey b) { return (b.key > a.key) ? b : a; }   // ties keep the earlier
+
+__global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const uint2* __restrict__ scores_all) {
+    __shared__ unsigned long long s_key[256];
+    __shared__ int s_j[256];
+    __shared__ int s_stop[256];
+    __shared__ int s_T;
+    const int slot = blockIdx.x;
+    const int pid = a.active[slot];
+    FitState& st = a.state[pid];
+    const ProblemDesc pd = a.prob[pid];
+    const unsigned* table = a.term_tables + pd.term_off;
+    const int K = a.K, R = a.nranks;
+    const int per_rank = (K + R - 1) / R;
+    const uint2* sc = scores_all;
+    auto load = [&](int j) -> uint2 {
+        return (R > 1) ? sc[((size_t)(j % R) * gridDim.x + slot) * per_rank + j / R] : sc[(size_t)slot * K + j];
+    };
+    const unsigned long long carry_key = score_key(st.best_cnt, st.best_sum);
+    const unsigned iters0 = st.iters, carry_max = st.max_iters;
+
+    const int per = (K + blockDim.x - 1) / blockDim.x;
+    const int j0 = threadIdx.x * per, j1 = min(j0 + per, K);
+    SelKey mine = {0ull, -1};
+    for (int j = j0; j < j1; j++) {
+        const uint2 v = load(j);
+        if ((v.x >> 30) == 3u) continue;
+        SelKey c = {score_key((int)(v.x & 0x3fffffffu), __uint_as_float(v.y)), j};
+        mine = sel_max(mine, c);
+    }
+    s_key[threadIdx.x] = mine.key; s_j[threadIdx.x] = mine.j;
+    __syncthreads();
+    // exclusive prefix over threads (256 entries: serial scan by each thread is cheap and branch-free enough)
+    SelKey run = {carry_key, -1};
+    for (int t = 0; t < (int)threadIdx.x; t++) { SelKey c = {s_key[t], s_j[t]}; if (c.j >= 0) run = sel_max(run, c); }
+    // walk own samples with the running prefix best; find the first sample at which the loop condition fails
+    int stop = K;           // K = no stop in my range
+    SelKey at_stop = run;
+    for (int j = j0; j < j1; j++) {
+        const uint2 v = load(j);
+        if ((v.x >> 30) != 3u) { SelKey c = {score_key((int)(v.x & 0x3fffffffu), __uint_as_float(v.y)), j}; run = sel_max(run, c); }
+        const unsigned mi = (run.j < 0) ? carry_max : table[(unsigned)(run.key >> 32)];
+        if (iters0 + (unsigned)j + 1u >= mi) { stop = j; at_stop = run; break; }
+    }
+    s_stop[threadIdx.x] = stop;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int T = K;
+        for (int t = 0; t < (int)blockDim.x; t++) T = min(T, s_stop[t]);
+        s_T = T;
+    }
+    __syncthreads();
+    const int T = s_T;
+    // the owner of T (or the last thread when the round did not terminate) publishes the result
+    const bool owner = (T < K) ? (stop == T) : (threadIdx.x == blockDim.x - 1);
+    if (owner) {
+        const SelKey best = (T < K) ? at_stop : run;
+        if (best.j >= 0) {
+            const uint2 v = load(best.j);
+            st.best_cnt = (int)(v.x & 0x3fffffffu);
+            st.best_sum = __uint_as_float(v.y);
+            st.best_hyp = (long long)st.samples_drawn + best.j;
+            st.best_midx = (int)(v.x >> 30);
+            st.max_iters = table[(unsigned)st.best_cnt];
+        }
+        st.iters = iters0 + (unsigned)min(T + 1, K);
+        st.done = (T < K) || !(st.iters < st.max_iters);
+        st.samples_drawn += (unsigned)K;
+        st.rounds += 1;
+    }
+}
+
+// Round epilogue, one thread per problem: the winning model is re-derived from its sample (the solvers are
+// deterministic), so no model has to travel between ranks; sampler state of the round is committed.
+template <int EST>
+__global__ void winner_kernel(const RoundArgs a, int slots) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= slots) return;
+    const int pid = a.active[slot];
+    FitState& st = a.state[pid];
+    const ProblemDesc pd = a.prob[pid];
+    const long long first = (long long)st.samples_drawn - a.K;       // select_kernel already advanced samples_drawn
+    if (st.best_hyp >= first) {
+        const int j = (int)(st.best_hyp - first);
+        int s[8];
+        const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
+        for (int i = 0; i < a.m; i++) s[i] = src[i];
+        float out[27];
+        const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+        const int k = solve_minimal<EST>(pts, s, out);
+        const int w = EST == USAC_EST_LINE2D ? 3 : 9;
+        if (st.best_midx < k) for (int i = 0; i < w; i++) st.best_model[i] = out[9 * st.best_midx + i];
+    }
+    st.evals += (unsigned long long)a.mvalid[slot] * (unsigned long long)pd.n;
+    st.prosac_t = st.prosac_t_next; st.prosac_n = st.prosac_n_next; st.prosac_largest = st.prosac_largest_next;
+}

@@ -1,0 +1,916 @@
+// usac_gpu.cu - context, host orchestration and the C ABI of libusac_gpu.so (see include/usac_gpu.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (ransac_b200/build.py)
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "essential.cuh"
+#include "pipeline.cuh"
+#include "score.cuh"
+#include "sprt.cuh"
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct usac_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    std::string err;
+    void set_error(const char* what, const char* why) { err = std::string(what) + ": " + why; }
+
+    // data
+    int est = 0, P = 0;
+    std::vector<ProblemDesc> h_prob;
+    long long total_points = 0, total_pairs = 0;
+    DevBuf<float> d_aos, d_pairs;
+    DevBuf<ProblemDesc> d_prob;
+    DevBuf<long long> d_pair_offs;
+    DevBuf<FitState> d_state;
+    FitState* h_state = nullptr; size_t h_state_cap = 0;     // pinned
+    DevBuf<int> d_active;
+    int* h_active = nullptr; size_t h_active_cap = 0;        // pinned
+    // side structures
+    DevBuf<int> d_knn, d_cell_of_point, d_members, d_rank, d_cell_start, d_pool;
+    DevBuf<unsigned> d_cursors, d_growth, d_term;
+    std::vector<int> h_pool_set;   // problems with an uploaded SPRT pool
+    // round buffers
+    DevBuf<int> d_samples, d_nmodels, d_offsets, d_mvalid, d_part_cnt, d_seeds, d_table;
+    DevBuf<float> d_models_raw, d_recs, d_part_sum;
+    DevBuf<uint2> d_scores, d_scores_all;
+    DevBuf<SprtModelResult> d_sprt_res;
+    // scoring API buffers
+    DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
+    DevBuf<int> d_q_cnt, d_q_ids;
+    // exchange
+    usac_allgather_fn allgather = nullptr;
+    void* allgather_user = nullptr;
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    // timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
+    size_t score_events_used = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_total_ms = 0, last_score_ms = 0;
+    int last_launches = 0, last_score_launches = 0;
+
+    std::pair<cudaEvent_t, cudaEvent_t>& next_score_event() {
+        if (score_events_used == score_events.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            score_events.push_back({a, b});
+        }
+        return score_events[score_events_used++];
+    }
+};
+
+static std::string g_create_error;
+
+static int fail(usac_gpu_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" int usac_gpu_create(usac_gpu_ctx** out, int device) {
+    if (!out) return USAC_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libusac_gpu has no CPU fallback)";
+        return USAC_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return USAC_ERR_ARG; }
+    usac_gpu_ctx* c = new usac_gpu_ctx;
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return USAC_ERR_CUDA;
+    }
+    if (c->prop.major < 10) {
+        g_create_error = "libusac_gpu is built for sm_100a only; device is sm_" + std::to_string(c->prop.major * 10 + c->prop.minor);
+        delete c;
+        return USAC_ERR_CUDA;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return USAC_ERR_CUDA;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return USAC_OK;
+}
+
+extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && c->nccl_lib) {
+        typedef int (*destroy_fn)(void*);
+        destroy_fn f = (destroy_fn)dlsym(c->nccl_lib, "ncclCommDestroy");
+        if (f) f(c->nccl_comm);
+    }
+    c->d_aos.release(); c->d_pairs.release(); c->d_prob.release(); c->d_pair_offs.release(); c->d_state.release(); c->d_active.release();
+    c->d_knn.release(); c->d_cell_of_point.release(); c->d_members.release(); c->d_rank.release(); c->d_cell_start.release();
+    c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
+    c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
+    c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release();
+    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release();
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_active) cudaFreeHost(c->h_active);
+    for (auto& pr : c->score_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* usac_gpu_last_error(const usac_gpu_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int usac_gpu_device_info(const usac_gpu_ctx* c, int info[4]) {
+    if (!c || !info) return USAC_ERR_ARG;
+    info[0] = c->prop.multiProcessorCount;
+    info[1] = c->prop.clockRate;
+    info[2] = c->prop.major * 10 + c->prop.minor;
+    info[3] = c->prop.l2CacheSize;
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// data upload: AoS copy + device-side re-layout into point pairs + per-column max |coordinate|
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void layout_kernel(const float* __restrict__ aos, float* __restrict__ pairs, ProblemDesc* prob, int P, int dim,
+                              const long long* __restrict__ pair_offs, long long total_pairs) {
+    const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= total_pairs) return;
+    int lo = 0, hi = P - 1;                       // problem owning global pair gp
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pair_offs[mid] <= gp) lo = mid; else hi = mid - 1; }
+    ProblemDesc& pd = prob[lo];
+    const int j = (int)(gp - pd.pair_off);
+    const int i0 = 2 * j, i1 = 2 * j + 1;
+    const float nanv = __int_as_float(0x7fc00000);
+    if (dim == 4) {
+        const float4 a = reinterpret_cast<const float4*>(aos)[pd.aos_off + i0];
+        const float4 b = (i1 < pd.n) ? reinterpret_cast<const float4*>(aos)[pd.aos_off + i1] : make_float4(nanv, nanv, nanv, nanv);
+        float4* dst = reinterpret_cast<float4*>(pairs) + 2 * gp;
+        dst[0] = make_float4(a.x, b.x, a.y, b.y);
+        dst[1] = make_float4(a.z, b.z, a.w, b.w);
+        float m1 = fabsf(a.x), m2 = fabsf(a.y), m3 = fabsf(a.z), m4 = fabsf(a.w);
+        if (i1 < pd.n) { m1 = fmaxf(m1, fabsf(b.x)); m2 = fmaxf(m2, fabsf(b.y)); m3 = fmaxf(m3, fabsf(b.z)); m4 = fmaxf(m4, fabsf(b.w)); }
+        atomicMax(reinterpret_cast<unsigned*>(&pd.mx1), __float_as_uint(m1));
+        atomicMax(reinterpret_cast<unsigned*>(&pd.my1), __float_as_uint(m2));
+        atomicMax(reinterpret_cast<unsigned*>(&pd.mx2), __float_as_uint(m3));
+        atomicMax(reinterpret_cast<unsigned*>(&pd.my2), __float_as_uint(m4));
+    } else {
+        const float2 a = reinterpret_cast<const float2*>(aos)[pd.aos_off + i0];
+        const float2 b = (i1 < pd.n) ? reinterpret_cast<const float2*>(aos)[pd.aos_off + i1] : make_float2(nanv, nanv);
+        reinterpret_cast<float4*>(pairs)[gp] = make_float4(a.x, b.x, a.y, b.y);
+        float m1 = fabsf(a.x), m2 = fabsf(a.y);
+        if (i1 < pd.n) { m1 = fmaxf(m1, fabsf(b.x)); m2 = fmaxf(m2, fabsf(b.y)); }
+        atomicMax(reinterpret_cast<unsigned*>(&pd.mx1), __float_as_uint(m1));
+        atomicMax(reinterpret_cast<unsigned*>(&pd.my1), __float_as_uint(m2));
+    }
+}
+
+extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* points, const int* n_per_problem, int P) {
+    if (!c || !points || !n_per_problem || P <= 0) return fail(c, USAC_ERR_ARG, "set_points: bad arguments");
+    if (estimator < USAC_EST_LINE2D || estimator > USAC_EST_ESSENTIAL) return fail(c, USAC_ERR_ARG, "set_points: unknown estimator");
+    cudaSetDevice(c->device);
+    const int dim = usac_point_dim(estimator);
+    c->est = estimator; c->P = P;
+    c->h_prob.assign(P, ProblemDesc());
+    std::vector<long long> pair_offs(P);
+    long long aos = 0, pairs = 0;
+    for (int p = 0; p < P; p++) {
+        const int n = n_per_problem[p];
+        if (n < usac_sample_size(estimator)) return fail(c, USAC_ERR_ARG, "set_points: a problem has fewer points than the minimal sample");
+        ProblemDesc& d = c->h_prob[p];
+        memset(&d, 0, sizeof(d));
+        d.n = n; d.n_pairs = (n + 1) / 2; d.aos_off = aos; d.pair_off = pairs;
+        d.growth_off = d.term_off = d.pool_off = d.knn_off = d.grid_off = d.cell_start_off = d.cursor_off = -1;
+        pair_offs[p] = pairs;
+        aos += n; pairs += d.n_pairs;
+    }
+    c->total_points = aos; c->total_pairs = pairs;
+    c->h_pool_set.assign(P, 0);
+    const size_t pair_floats = (dim == 4) ? 8 : 4;
+    CUDA_TRY(c, c->d_aos.ensure((size_t)aos * dim));
+    CUDA_TRY(c, c->d_pairs.ensure((size_t)pairs * pair_floats));
+    CUDA_TRY(c, c->d_prob.ensure(P));
+    CUDA_TRY(c, c->d_pair_offs.ensure(P));
+    CUDA_TRY(c, c->d_state.ensure(P));
+    CUDA_TRY(c, c->d_active.ensure(P));
+    if (c->h_state_cap < (size_t)P) {
+        if (c->h_state) cudaFreeHost(c->h_state);
+        CUDA_TRY(c, cudaMallocHost(&c->h_state, sizeof(FitState) * P));
+        c->h_state_cap = P;
+    }
+    if (c->h_active_cap < (size_t)P) {
+        if (c->h_active) cudaFreeHost(c->h_active);
+        CUDA_TRY(c, cudaMallocHost(&c->h_active, sizeof(int) * P));
+        c->h_active_cap = P;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_aos.p, points, (size_t)aos * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), sizeof(ProblemDesc) * P, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_pair_offs.p, pair_offs.data(), sizeof(long long) * P, cudaMemcpyHostToDevice, c->stream));
+    const int threads = 256;
+    layout_kernel<<<(unsigned)((pairs + threads - 1) / threads), threads, 0, c->stream>>>(c->d_aos.p, c->d_pairs.p, c->d_prob.p, P, dim,
+                                                                                          c->d_pair_offs.p, pairs);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // pair_offs / h_prob staging are stack/heap temporaries
+    return USAC_OK;
+}
+
+// push host-side descriptor fields that the host owns (offsets) without clobbering the device-computed maxima
+static int push_desc(usac_gpu_ctx* c) {
+    std::vector<ProblemDesc> cur(c->P);
+    CUDA_TRY(c, cudaMemcpyAsync(cur.data(), c->d_prob.p, sizeof(ProblemDesc) * c->P, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < c->P; p++) {
+        ProblemDesc& h = c->h_prob[p];
+        h.mx1 = cur[p].mx1; h.my1 = cur[p].my1; h.mx2 = cur[p].mx2; h.my2 = cur[p].my2;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), sizeof(ProblemDesc) * c->P, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return USAC_OK;
+}
+
+// grow a device array of per-problem segments: returns the offset of a new segment of `count` elements
+template <class T>
+static cudaError_t append_segment(DevBuf<T>& buf, size_t& used, const T* host, size_t count, long long* off_out, cudaStream_t s) {
+    if (used + count > buf.cap) {
+        DevBuf<T> nb;
+        cudaError_t e = nb.ensure(std::max((used + count) * 2, (size_t)1024));
+        if (e != cudaSuccess) return e;
+        if (used) cudaMemcpyAsync(nb.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        buf.release();
+        buf = nb;
+    }
+    cudaError_t e = host ? cudaMemcpyAsync(buf.p + used, host, count * sizeof(T), cudaMemcpyHostToDevice, s)
+                         : cudaMemsetAsync(buf.p + used, 0, count * sizeof(T), s);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(s);
+    *off_out = (long long)used;
+    used += count;
+    return e;
+}
+
+struct SideUsed { size_t knn = 0, grid = 0, cell_start = 0, cursors = 0, pool = 0; };
+static std::map<usac_gpu_ctx*, SideUsed> g_side;   // bookkeeping of appended segments per context
+
+extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const int* neighbors, int k) {
+    if (!c || problem < 0 || problem >= c->P || !neighbors || k < 1) return fail(c, USAC_ERR_ARG, "set_neighbors_knn: bad arguments");
+    cudaSetDevice(c->device);
+    SideUsed& u = g_side[c];
+    ProblemDesc& d = c->h_prob[problem];
+    CUDA_TRY(c, append_segment(c->d_knn, u.knn, neighbors, (size_t)d.n * k, &d.knn_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)d.n, &d.cursor_off, c->stream));
+    d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
+    return push_desc(c);
+}
+
+extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cell_size) {
+    if (!c || problem < 0 || problem >= c->P || cell_size <= 0) return fail(c, USAC_ERR_ARG, "set_neighbors_grid: bad arguments");
+    if (usac_point_dim(c->est) != 4) return fail(c, USAC_ERR_ARG, "set_neighbors_grid: needs correspondences (nearest_neighbors.cpp:172 reads 4 columns)");
+    cudaSetDevice(c->device);
+    ProblemDesc& d = c->h_prob[problem];
+    const int n = d.n;
+    // nearest_neighbors.cpp:160-201: cell = (int(x1/c), int(y1/c), int(x2/c), int(y2/c)); a point's neighbours are the other
+    // members of its cell in ascending index order. Stored as CSR (sorted by cell key, then index) + rank of each point.
+    std::vector<float> pts((size_t)n * 4);
+    CUDA_TRY(c, cudaMemcpyAsync(pts.data(), c->d_aos.p + (size_t)d.aos_off * 4, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    typedef std::tuple<int, int, int, int, int> Key;
+    std::vector<Key> keys(n);
+    for (int i = 0; i < n; i++) {
+        const float* p = &pts[4 * (size_t)i];
+        keys[i] = Key((int)(p[0] / cell_size), (int)(p[1] / cell_size), (int)(p[2] / cell_size), (int)(p[3] / cell_size), i);
+    }
+    std::sort(keys.begin(), keys.end());
+    std::vector<int> cell(n), members(n), rank(n), cell_start;
+    int ncell = -1;
+    for (int q = 0; q < n; q++) {
+        const bool first = q == 0 || std::get<0>(keys[q]) != std::get<0>(keys[q - 1]) || std::get<1>(keys[q]) != std::get<1>(keys[q - 1]) ||
+                           std::get<2>(keys[q]) != std::get<2>(keys[q - 1]) || std::get<3>(keys[q]) != std::get<3>(keys[q - 1]);
+        if (first) { ncell++; cell_start.push_back(q); }
+        const int idx = std::get<4>(keys[q]);
+        members[q] = idx; cell[idx] = ncell; rank[idx] = q - cell_start.back();
+    }
+    cell_start.push_back(n);
+    cell_start.resize(n + 1, n);
+    SideUsed& u = g_side[c];
+    size_t g0 = u.grid, g1 = u.grid, g2 = u.grid;
+    long long o0, o1, o2;
+    CUDA_TRY(c, append_segment(c->d_cell_of_point, g0, cell.data(), (size_t)n, &o0, c->stream));
+    CUDA_TRY(c, append_segment(c->d_members, g1, members.data(), (size_t)n, &o1, c->stream));
+    CUDA_TRY(c, append_segment(c->d_rank, g2, rank.data(), (size_t)n, &o2, c->stream));
+    u.grid = g0;
+    d.grid_off = o0;
+    CUDA_TRY(c, append_segment(c->d_cell_start, u.cell_start, cell_start.data(), (size_t)n + 1, &d.cell_start_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)n, &d.cursor_off, c->stream));
+    d.neigh_type = USAC_NEIGH_GRID;
+    return push_desc(c);
+}
+
+extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* pool) {
+    if (!c || problem < 0 || problem >= c->P || !pool) return fail(c, USAC_ERR_ARG, "set_sprt_pool: bad arguments");
+    cudaSetDevice(c->device);
+    SideUsed& u = g_side[c];
+    ProblemDesc& d = c->h_prob[problem];
+    CUDA_TRY(c, append_segment(c->d_pool, u.pool, pool, (size_t)d.n, &d.pool_off, c->stream));
+    c->h_pool_set[problem] = 1;
+    return push_desc(c);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------------------------
+static void launch_score(usac_gpu_ctx* c, const ScoreArgs& a, int slots, int mblocks) {
+    dim3 grid(mblocks, a.nchunks, slots);
+    auto& ev = c->next_score_event();
+    cudaEventRecord(ev.first, c->stream);
+    switch (c->est) {
+        case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+        case USAC_EST_HOMOGRAPHY: score_kernel<USAC_EST_HOMOGRAPHY><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+        case USAC_EST_FUNDAMENTAL: score_kernel<USAC_EST_FUNDAMENTAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+        default: score_kernel<USAC_EST_ESSENTIAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+    }
+    cudaEventRecord(ev.second, c->stream);
+    c->last_launches++;
+    c->last_score_launches++;
+}
+
+static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_pairs, int* chunk_pairs, int* nchunks) {
+    const long long target = 8LL * c->prop.multiProcessorCount;
+    long long want = (target + (long long)slots * mblocks - 1) / ((long long)slots * mblocks);
+    const int max_chunks = std::max(1, max_pairs / (4 * USAC_TILE_PAIRS));
+    int nc = (int)std::min<long long>(std::max<long long>(want, 1), max_chunks);
+    int cp = (max_pairs + nc - 1) / nc;
+    cp = ((cp + USAC_TILE_PAIRS - 1) / USAC_TILE_PAIRS) * USAC_TILE_PAIRS;
+    nc = (max_pairs + cp - 1) / cp;
+    *chunk_pairs = cp;
+    *nchunks = std::max(nc, 1);
+}
+
+static void collect_timing(usac_gpu_ctx* c) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_total_ms = ms;
+    float s = 0;
+    for (size_t i = 0; i < c->score_events_used; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->score_events[i].first, c->score_events[i].second);
+        s += t;
+    }
+    c->last_score_ms = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Quality API
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void final_reduce_kernel(const int* __restrict__ part_cnt, const float* __restrict__ part_sum, int M, int mstride, int nchunks,
+                                    int* __restrict__ cnt, float* __restrict__ sum) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    int cc = 0;
+    float s = 0.f;
+    for (int ch = 0; ch < nchunks; ch++) { cc += part_cnt[(size_t)ch * mstride + q]; s += part_sum[(size_t)ch * mstride + q]; }
+    cnt[q] = cc;
+    sum[q] = s;
+}
+
+extern "C" int usac_gpu_score(usac_gpu_ctx* c, int problem, const float* models, int M, float threshold, int* inliers_out, float* sumerr_out) {
+    if (!c || problem < 0 || problem >= c->P || !models || M < 0 || !(threshold > 0.f)) return fail(c, USAC_ERR_ARG, "score: bad arguments");
+    if (M == 0) return USAC_OK;
+    cudaSetDevice(c->device);
+    const int w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    CUDA_TRY(c, c->d_q_models.ensure((size_t)M * w));
+    CUDA_TRY(c, c->d_q_recs.ensure((size_t)M * USAC_REC_STRIDE));
+    const ProblemDesc& d = c->h_prob[problem];
+    const int mblocks = (M + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS;
+    int chunk_pairs, nchunks;
+    plan_chunks(c, 1, mblocks, d.n_pairs, &chunk_pairs, &nchunks);
+    CUDA_TRY(c, c->d_part_cnt.ensure((size_t)nchunks * M));
+    CUDA_TRY(c, c->d_part_sum.ensure((size_t)nchunks * M));
+    CUDA_TRY(c, c->d_q_cnt.ensure(M));
+    CUDA_TRY(c, c->d_q_sum.ensure(M));
+    c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
+    cudaEventRecord(c->ev0, c->stream);
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, models, sizeof(float) * w * M, cudaMemcpyHostToDevice, c->stream));
+    c->h_active[0] = problem;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    prepare_models_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(c->est, c->d_q_models.p, M, w, threshold, c->d_prob.p, problem, c->d_q_recs.p);
+    c->last_launches++;
+    ScoreArgs a;
+    a.pairs = c->d_pairs.p; a.aos = c->d_aos.p; a.prob = c->d_prob.p; a.active = c->d_active.p; a.recs = c->d_q_recs.p; a.mvalid = nullptr;
+    a.M = M; a.mstride = M; a.chunk_pairs = chunk_pairs; a.nchunks = nchunks; a.part_cnt = c->d_part_cnt.p; a.part_sum = c->d_part_sum.p;
+    launch_score(c, a, 1, mblocks);
+    final_reduce_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(c->d_part_cnt.p, c->d_part_sum.p, M, M, nchunks, c->d_q_cnt.p, c->d_q_sum.p);
+    c->last_launches++;
+    if (inliers_out) CUDA_TRY(c, cudaMemcpyAsync(inliers_out, c->d_q_cnt.p, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream));
+    if (sumerr_out) CUDA_TRY(c, cudaMemcpyAsync(sumerr_out, c->d_q_sum.p, sizeof(float) * M, cudaMemcpyDeviceToHost, c->stream));
+    cudaEventRecord(c->ev1, c->stream);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    collect_timing(c);
+    return USAC_OK;
+}
+
+static int upload_one_record(usac_gpu_ctx* c, int problem, const float* model, float thr) {
+    const int w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    CUDA_TRY(c, c->d_q_models.ensure(9));
+    CUDA_TRY(c, c->d_q_recs.ensure(USAC_REC_STRIDE));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, model, sizeof(float) * w, cudaMemcpyHostToDevice, c->stream));
+    prepare_models_kernel<<<1, 32, 0, c->stream>>>(c->est, c->d_q_models.p, 1, w, thr, c->d_prob.p, problem, c->d_q_recs.p);
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_errors(usac_gpu_ctx* c, int problem, const float* model, float* err_out) {
+    if (!c || problem < 0 || problem >= c->P || !model || !err_out) return fail(c, USAC_ERR_ARG, "errors: bad arguments");
+    cudaSetDevice(c->device);
+    const ProblemDesc& d = c->h_prob[problem];
+    const int dim = usac_point_dim(c->est);
+    int rc = upload_one_record(c, problem, model, 1.f);
+    if (rc) return rc;
+    CUDA_TRY(c, c->d_q_err.ensure(d.n));
+    const float* aos = c->d_aos.p + (size_t)d.aos_off * dim;
+    const int g = (d.n + 255) / 256;
+    switch (c->est) {
+        case USAC_EST_LINE2D: errors_kernel<USAC_EST_LINE2D><<<g, 256, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, c->d_q_err.p); break;
+        case USAC_EST_HOMOGRAPHY: errors_kernel<USAC_EST_HOMOGRAPHY><<<g, 256, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, c->d_q_err.p); break;
+        case USAC_EST_FUNDAMENTAL: errors_kernel<USAC_EST_FUNDAMENTAL><<<g, 256, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, c->d_q_err.p); break;
+        default: errors_kernel<USAC_EST_ESSENTIAL><<<g, 256, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, c->d_q_err.p); break;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(err_out, c->d_q_err.p, sizeof(float) * d.n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_get_inliers(usac_gpu_ctx* c, int problem, const float* model, float threshold, int* ids_out, int* n_out) {
+    if (!c || problem < 0 || problem >= c->P || !model || !ids_out || !n_out || !(threshold > 0.f)) return fail(c, USAC_ERR_ARG, "get_inliers: bad arguments");
+    cudaSetDevice(c->device);
+    const ProblemDesc& d = c->h_prob[problem];
+    const int dim = usac_point_dim(c->est);
+    int rc = upload_one_record(c, problem, model, threshold);
+    if (rc) return rc;
+    CUDA_TRY(c, c->d_q_ids.ensure((size_t)d.n + 1));
+    const float* aos = c->d_aos.p + (size_t)d.aos_off * dim;
+    int* cnt = c->d_q_ids.p + d.n;
+    switch (c->est) {
+        case USAC_EST_LINE2D: inliers_kernel<USAC_EST_LINE2D><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, threshold, c->d_q_ids.p, cnt); break;
+        case USAC_EST_HOMOGRAPHY: inliers_kernel<USAC_EST_HOMOGRAPHY><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, threshold, c->d_q_ids.p, cnt); break;
+        case USAC_EST_FUNDAMENTAL: inliers_kernel<USAC_EST_FUNDAMENTAL><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, threshold, c->d_q_ids.p, cnt); break;
+        default: inliers_kernel<USAC_EST_ESSENTIAL><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, threshold, c->d_q_ids.p, cnt); break;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(n_out, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (*n_out > 0) CUDA_TRY(c, cudaMemcpyAsync(ids_out, c->d_q_ids.p, sizeof(int) * (*n_out), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side tables: StandardTerminationCriteria (standard_termination_criteria.hpp:52-62) and the PROSAC growth
+// function (prosac_sampler.hpp:62-114). Host libm on purpose: the bound is a function of the inlier count only, so a
+// table indexed by the count makes the device decision bit-identical to the host plugin's.
+// ------------------------------------------------------------------------------------------------------------------
+static void standard_termination_table(unsigned n, int m, float confidence, unsigned max_iterations, std::vector<unsigned>& out) {
+    out.resize((size_t)n + 1);
+    const float log_1_p = (float)logf(1 - confidence);
+    for (unsigned inl = 0; inl <= n; inl++) {
+        float inl_ratio = (float)inl / n;
+        float inl_prob = inl_ratio * inl_ratio;
+        int k = m;
+        while (k > 2) { inl_prob *= inl_ratio; k--; }
+        out[inl] = (inl_prob < 0.0005f) ? max_iterations : (unsigned)(log_1_p / logf(1 - inl_prob));
+    }
+}
+
+static void prosac_growth(unsigned n, unsigned m, std::vector<unsigned>& g) {
+    g.resize(n);
+    double T_n = 200000;
+    for (unsigned i = 0; i < m; ++i) T_n *= (double)(m - i) / (n - i);
+    unsigned T_n_prime = 1;
+    for (unsigned i = 0; i < n; ++i) {
+        if (i + 1 <= m) { g[i] = T_n_prime; continue; }
+        double Tn_plus1 = (double)(i + 1) * T_n / (i + 1 - m);
+        g[i] = T_n_prime + (unsigned)ceil(Tn_plus1 - T_n);
+        T_n = Tn_plus1;
+        T_n_prime = g[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sampler / Estimator APIs
+// ------------------------------------------------------------------------------------------------------------------
+static int ensure_round_buffers(usac_gpu_ctx* c, int slots, int K, int nchunks, int nranks) {
+    const int S = usac_models_per_sample(c->est), m = usac_sample_size(c->est);
+    const size_t sk = (size_t)slots * K;
+    CUDA_TRY(c, c->d_samples.ensure(sk * m));
+    CUDA_TRY(c, c->d_nmodels.ensure(sk));
+    CUDA_TRY(c, c->d_offsets.ensure(sk));
+    CUDA_TRY(c, c->d_mvalid.ensure(slots));
+    CUDA_TRY(c, c->d_models_raw.ensure(sk * S * 9));
+    CUDA_TRY(c, c->d_recs.ensure(sk * S * USAC_REC_STRIDE));
+    CUDA_TRY(c, c->d_part_cnt.ensure(sk * S * nchunks));
+    CUDA_TRY(c, c->d_part_sum.ensure(sk * S * nchunks));
+    CUDA_TRY(c, c->d_seeds.ensure(sk));
+    const size_t per_rank = (K + nranks - 1) / nranks;
+    CUDA_TRY(c, c->d_scores.ensure(std::max(sk, (size_t)slots * per_rank)));
+    CUDA_TRY(c, c->d_scores_all.ensure((size_t)slots * per_rank * nranks));
+    CUDA_TRY(c, c->d_sprt_res.ensure(sk * S));
+    return USAC_OK;
+}
+
+static int setup_sampler_side(usac_gpu_ctx* c, const usac_sampler_cfg& s) {
+    if (s.sampler == USAC_SAMPLER_PROSAC) {
+        std::vector<unsigned> all, g;
+        for (int p = 0; p < c->P; p++) {
+            prosac_growth((unsigned)c->h_prob[p].n, (unsigned)usac_sample_size(c->est), g);
+            c->h_prob[p].growth_off = (long long)all.size();
+            all.insert(all.end(), g.begin(), g.end());
+        }
+        CUDA_TRY(c, c->d_growth.ensure(all.size()));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_growth.p, all.data(), sizeof(unsigned) * all.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    if (s.sampler == USAC_SAMPLER_NAPSAC) {
+        for (int p = 0; p < c->P; p++) {
+            const ProblemDesc& d = c->h_prob[p];
+            if (s.neighbors == USAC_NEIGH_KNN ? d.knn_off < 0 : d.grid_off < 0) return fail(c, USAC_ERR_STATE, "NAPSAC: neighbourhood of a problem was not set");
+            CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off, 0, sizeof(unsigned) * d.n, c->stream));
+        }
+    }
+    return USAC_OK;
+}
+
+static void fill_round_args(usac_gpu_ctx* c, RoundArgs& a, const usac_sampler_cfg& s, int K) {
+    memset(&a, 0, sizeof(a));
+    a.prob = c->d_prob.p; a.active = c->d_active.p; a.state = c->d_state.p; a.aos = c->d_aos.p;
+    a.est = c->est; a.K = K; a.S = usac_models_per_sample(c->est); a.m = usac_sample_size(c->est); a.mstride = K * a.S;
+    a.sampler = s.sampler; a.rng = s.rng; a.neighbors = s.neighbors; a.seed = s.seed;
+    a.growth = c->d_growth.p; a.knn = c->d_knn.p; a.cell_of_point = c->d_cell_of_point.p; a.members = c->d_members.p;
+    a.rank_in_cell = c->d_rank.p; a.cell_start = c->d_cell_start.p; a.cursors = c->d_cursors.p; a.seeds = c->d_seeds.p;
+    a.samples = c->d_samples.p; a.models_raw = c->d_models_raw.p; a.nmodels = c->d_nmodels.p; a.offsets = c->d_offsets.p;
+    a.recs = c->d_recs.p; a.mvalid = c->d_mvalid.p; a.part_cnt = c->d_part_cnt.p; a.part_sum = c->d_part_sum.p;
+    a.sample_scores = c->d_scores.p; a.term_tables = c->d_term.p; a.table = c->d_table.p;
+    a.rank = 0; a.nranks = 1; a.nchunks = 1;
+}
+
+static void launch_sampler(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+    dim3 g((a.K + 127) / 128, slots);
+    if (a.sampler == USAC_SAMPLER_NAPSAC) { napsac_seed_kernel<<<g, 128, 0, c->stream>>>(a); c->last_launches++; }
+    sample_kernel<<<g, 128, 0, c->stream>>>(a);
+    c->last_launches++;
+    if (a.sampler == USAC_SAMPLER_NAPSAC) { napsac_commit_kernel<<<g, 128, 0, c->stream>>>(a); c->last_launches++; }
+}
+
+static void init_state(FitState& s, const ProblemDesc& d, int est, unsigned max_iterations, uint64_t first_hyp) {
+    memset(&s, 0, sizeof(s));
+    s.best_hyp = -1;
+    s.max_iters = max_iterations;
+    s.samples_drawn = (unsigned)first_hyp;
+    s.prosac_t = s.prosac_t_next = 1;
+    s.prosac_n = s.prosac_n_next = s.prosac_largest = s.prosac_largest_next = (unsigned)usac_sample_size(est);
+    s.prosac_term_len = (unsigned)d.n;
+    sprt_init_state(s, est);
+}
+
+extern "C" int usac_gpu_sample(usac_gpu_ctx* c, int problem, const usac_sampler_cfg* cfg, uint64_t first_hyp, int K, int* samples_out) {
+    if (!c || !cfg || problem < 0 || problem >= c->P || K <= 0 || !samples_out) return fail(c, USAC_ERR_ARG, "sample: bad arguments");
+    if (cfg->rng == USAC_RNG_TABLE) return fail(c, USAC_ERR_ARG, "sample: table replay has nothing to generate");
+    cudaSetDevice(c->device);
+    int rc = ensure_round_buffers(c, 1, K, 1, 1);
+    if (rc) return rc;
+    rc = setup_sampler_side(c, *cfg);
+    if (rc) return rc;
+    rc = push_desc(c);
+    if (rc) return rc;
+    FitState s;
+    init_state(s, c->h_prob[problem], c->est, 0, first_hyp);
+    if (cfg->sampler == USAC_SAMPLER_PROSAC) {
+        if (cfg->prosac_termination_length) s.prosac_term_len = cfg->prosac_termination_length;
+        if (cfg->prosac_hyp_count) {
+            // subset size implied by the counter: the state a sequential sampler would be in before call t
+            std::vector<unsigned> g;
+            prosac_growth((unsigned)c->h_prob[problem].n, (unsigned)usac_sample_size(c->est), g);
+            unsigned n = (unsigned)usac_sample_size(c->est);
+            for (unsigned t = 1; t < cfg->prosac_hyp_count; t++) if (t > g[n - 1] && n < (unsigned)c->h_prob[problem].n) n++;
+            s.prosac_t = cfg->prosac_hyp_count; s.prosac_n = n;
+        }
+    }
+    c->h_state[problem] = s;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p + problem, c->h_state + problem, sizeof(FitState), cudaMemcpyHostToDevice, c->stream));
+    c->h_active[0] = problem;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RoundArgs a;
+    fill_round_args(c, a, *cfg, K);
+    c->last_launches = 0;
+    launch_sampler(c, a, 1);
+    CUDA_TRY(c, cudaMemcpyAsync(samples_out, c->d_samples.p, sizeof(int) * K * a.m, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_estimate(usac_gpu_ctx* c, int problem, const int* samples, int K, float* models_out, int* nmodels_out) {
+    if (!c || problem < 0 || problem >= c->P || !samples || K <= 0 || !models_out || !nmodels_out) return fail(c, USAC_ERR_ARG, "estimate: bad arguments");
+    cudaSetDevice(c->device);
+    const int S = usac_models_per_sample(c->est), m = usac_sample_size(c->est), dim = usac_point_dim(c->est);
+    const ProblemDesc& d = c->h_prob[problem];
+    for (size_t i = 0; i < (size_t)K * m; i++)
+        if (samples[i] < 0 || samples[i] >= d.n) return fail(c, USAC_ERR_ARG, "estimate: sample index out of range");
+    CUDA_TRY(c, c->d_samples.ensure((size_t)K * m));
+    CUDA_TRY(c, c->d_models_raw.ensure((size_t)K * S * 9));
+    CUDA_TRY(c, c->d_nmodels.ensure(K));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_samples.p, samples, sizeof(int) * K * m, cudaMemcpyHostToDevice, c->stream));
+    const float* aos = c->d_aos.p + (size_t)d.aos_off * dim;
+    const int g = (K + 63) / 64;
+    switch (c->est) {
+        case USAC_EST_LINE2D: estimate_kernel<USAC_EST_LINE2D><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
+        case USAC_EST_HOMOGRAPHY: estimate_kernel<USAC_EST_HOMOGRAPHY><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
+        case USAC_EST_FUNDAMENTAL: estimate_kernel<USAC_EST_FUNDAMENTAL><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
+        default: estimate_kernel<USAC_EST_ESSENTIAL><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(models_out, c->d_models_raw.p, sizeof(float) * K * S * 9, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(nmodels_out, c->d_nmodels.p, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused fit
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int usac_gpu_set_allgather(usac_gpu_ctx* c, usac_allgather_fn fn, void* user) {
+    if (!c) return USAC_ERR_ARG;
+    c->allgather = fn; c->allgather_user = user;
+    return USAC_OK;
+}
+
+template <int EST>
+static void launch_round_est(usac_gpu_ctx* c, const RoundArgs& a, int slots, bool sprt) {
+    dim3 gs((a.K + 63) / 64, slots);
+    solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    c->last_launches++;
+}
+template <int EST>
+static void launch_winner_est(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+    winner_kernel<EST><<<(slots + 31) / 32, 32, 0, c->stream>>>(a, slots);
+    c->last_launches++;
+}
+
+extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results) {
+    if (!c || !cfg || !results) return fail(c, USAC_ERR_ARG, "fit: bad arguments");
+    if (c->P <= 0) return fail(c, USAC_ERR_STATE, "fit: no points uploaded");
+    if (!(cfg->threshold > 0.f) || cfg->max_iterations == 0) return fail(c, USAC_ERR_ARG, "fit: threshold and max_iterations must be positive");
+    const int nranks = std::max(cfg->nranks, 1), rank = cfg->rank;
+    if (rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "fit: rank out of range");
+    if (nranks > 1 && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_nccl_init or usac_gpu_set_allgather");
+    if (cfg->sampler.rng == USAC_RNG_TABLE && (!cfg->sample_table || cfg->sample_table_rows == 0)) return fail(c, USAC_ERR_ARG, "fit: empty sample table");
+    if (cfg->sprt && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT with hypothesis sharding is not supported");
+    cudaSetDevice(c->device);
+    const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est);
+    int max_n = 0;
+    for (int p = 0; p < P; p++) max_n = std::max(max_n, c->h_prob[p].n);
+    if (cfg->sprt) for (int p = 0; p < P; p++) if (!c->h_pool_set[p]) return fail(c, USAC_ERR_STATE, "fit: SPRT needs usac_gpu_set_sprt_pool for every problem");
+
+    int K = cfg->round_size;
+    if (K <= 0) K = max_n >= 100000 ? 2048 : 512;
+    K = (int)std::min<unsigned>((unsigned)K, std::max(cfg->max_iterations, 1u));
+    if (nranks > 1) K = ((K + nranks - 1) / nranks) * nranks;
+
+    // termination tables (cached by n) and sampler side data
+    {
+        std::map<int, long long> by_n;
+        std::vector<unsigned> all, t;
+        for (int p = 0; p < P; p++) {
+            const int n = c->h_prob[p].n;
+            auto it = by_n.find(n);
+            if (it == by_n.end()) {
+                standard_termination_table((unsigned)n, m, cfg->confidence, cfg->max_iterations, t);
+                it = by_n.insert({n, (long long)all.size()}).first;
+                all.insert(all.end(), t.begin(), t.end());
+            }
+            c->h_prob[p].term_off = it->second;
+        }
+        CUDA_TRY(c, c->d_term.ensure(all.size()));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_term.p, all.data(), sizeof(unsigned) * all.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    int rc = setup_sampler_side(c, cfg->sampler);
+    if (rc) return rc;
+    rc = push_desc(c);
+    if (rc) return rc;
+    if (cfg->sampler.rng == USAC_RNG_TABLE) {
+        CUDA_TRY(c, c->d_table.ensure((size_t)cfg->sample_table_rows * m));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_table.p, cfg->sample_table, sizeof(int) * (size_t)cfg->sample_table_rows * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int p = 0; p < P; p++) init_state(c->h_state[p], c->h_prob[p], c->est, cfg->max_iterations, 0);
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof(FitState) * P, cudaMemcpyHostToDevice, c->stream));
+
+    std::vector<int> active(P);
+    for (int p = 0; p < P; p++) active[p] = p;
+    c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
+    cudaEventRecord(c->ev0, c->stream);
+
+    while (!active.empty()) {
+        const int slots = (int)active.size();
+        int max_pairs = 0;
+        for (int p : active) max_pairs = std::max(max_pairs, c->h_prob[p].n_pairs);
+        const int mblocks = (K * S + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS;
+        int chunk_pairs, nchunks;
+        plan_chunks(c, slots, std::max(1, mblocks / nranks), max_pairs, &chunk_pairs, &nchunks);
+        rc = ensure_round_buffers(c, slots, K, nchunks, nranks);
+        if (rc) return rc;
+        memcpy(c->h_active, active.data(), sizeof(int) * slots);
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int) * slots, cudaMemcpyHostToDevice, c->stream));
+
+        RoundArgs a;
+        fill_round_args(c, a, cfg->sampler, K);
+        a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
+        a.table_rows = cfg->sample_table_rows; a.rank = rank; a.nranks = nranks; a.nchunks = nchunks;
+        a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
+
+        launch_sampler(c, a, slots);
+        switch (c->est) {
+            case USAC_EST_LINE2D: launch_round_est<USAC_EST_LINE2D>(c, a, slots, cfg->sprt); break;
+            case USAC_EST_HOMOGRAPHY: launch_round_est<USAC_EST_HOMOGRAPHY>(c, a, slots, cfg->sprt); break;
+            case USAC_EST_FUNDAMENTAL: launch_round_est<USAC_EST_FUNDAMENTAL>(c, a, slots, cfg->sprt); break;
+            default: launch_round_est<USAC_EST_ESSENTIAL>(c, a, slots, cfg->sprt); break;
+        }
+        prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
+        c->last_launches++;
+        if (cfg->sprt) {
+            launch_sprt(c->est, a, slots, c->stream);
+            c->last_launches += 2;
+        } else {
+            ScoreArgs sa;
+            sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
+            sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
+            sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
+            launch_score(c, sa, slots, mblocks);
+            dim3 gr((K + 127) / 128, slots);
+            reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
+            c->last_launches++;
+            const uint2* scores = c->d_scores.p;
+            if (nranks > 1) {
+                const size_t bytes = (size_t)slots * (K / nranks) * sizeof(uint2);
+                int grc = c->allgather(c->allgather_user, c->d_scores.p, c->d_scores_all.p, bytes, (void*)c->stream);
+                if (grc) return fail(c, USAC_ERR_NCCL, "fit: all-gather failed");
+                scores = c->d_scores_all.p;
+            }
+            select_kernel<<<slots, 256, 0, c->stream>>>(a, scores);
+            c->last_launches++;
+        }
+        switch (c->est) {
+            case USAC_EST_LINE2D: launch_winner_est<USAC_EST_LINE2D>(c, a, slots); break;
+            case USAC_EST_HOMOGRAPHY: launch_winner_est<USAC_EST_HOMOGRAPHY>(c, a, slots); break;
+            case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
+            default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState) * P, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the one host sync of the round
+        CUDA_TRY(c, cudaGetLastError());
+        std::vector<int> next;
+        for (int p : active) if (!c->h_state[p].done) next.push_back(p);
+        active.swap(next);
+    }
+    cudaEventRecord(c->ev1, c->stream);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    const int w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    for (int p = 0; p < P; p++) {
+        const FitState& s = c->h_state[p];
+        usac_fit_result& r = results[p];
+        memset(&r, 0, sizeof(r));
+        for (int i = 0; i < w; i++) r.model[i] = s.best_model[i];
+        r.inliers = s.best_cnt; r.score = s.best_sum; r.iterations = s.iters; r.samples_drawn = s.samples_drawn;
+        r.best_hyp = s.best_hyp; r.best_model_idx = s.best_midx; r.rounds = s.rounds; r.evals = s.evals;
+    }
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NCCL binding (dlopen: libusac_gpu.so itself has no link-time dependency on NCCL)
+// ------------------------------------------------------------------------------------------------------------------
+struct NcclUniqueId { char internal[128]; };
+typedef int (*nccl_get_id_fn)(NcclUniqueId*);
+typedef int (*nccl_init_rank_fn)(void**, int, NcclUniqueId, int);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+
+static void* open_nccl() {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return h;
+}
+
+extern "C" int usac_gpu_nccl_unique_id(char id_out[128]) {
+    void* h = open_nccl();
+    if (!h) { g_create_error = "libnccl.so.2 not found"; return USAC_ERR_NCCL; }
+    nccl_get_id_fn f = (nccl_get_id_fn)dlsym(h, "ncclGetUniqueId");
+    if (!f) return USAC_ERR_NCCL;
+    NcclUniqueId id;
+    if (f(&id) != 0) return USAC_ERR_NCCL;
+    memcpy(id_out, id.internal, 128);
+    return USAC_OK;
+}
+
+static int nccl_allgather_hook(void* user, const void* d_send, void* d_recv, size_t bytes, void* stream) {
+    usac_gpu_ctx* c = (usac_gpu_ctx*)user;
+    nccl_allgather_fn f = (nccl_allgather_fn)dlsym(c->nccl_lib, "ncclAllGather");
+    if (!f) return 1;
+    return f(d_send, d_recv, bytes, /*ncclUint8*/ 1, c->nccl_comm, (cudaStream_t)stream);
+}
+
+extern "C" int usac_gpu_nccl_init(usac_gpu_ctx* c, const char id[128], int rank, int nranks) {
+    if (!c || !id || rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "nccl_init: bad arguments");
+    cudaSetDevice(c->device);
+    c->nccl_lib = open_nccl();
+    if (!c->nccl_lib) return fail(c, USAC_ERR_NCCL, "libnccl.so.2 not found");
+    nccl_init_rank_fn f = (nccl_init_rank_fn)dlsym(c->nccl_lib, "ncclCommInitRank");
+    if (!f) return fail(c, USAC_ERR_NCCL, "ncclCommInitRank not found");
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    if (f(&c->nccl_comm, nranks, uid, rank) != 0) return fail(c, USAC_ERR_NCCL, "ncclCommInitRank failed");
+    c->allgather = nccl_allgather_hook;
+    c->allgather_user = c;
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int usac_gpu_last_timing(const usac_gpu_ctx* c, float* total_ms, float* score_kernel_ms, int* launches, int* score_launches) {
+    if (!c) return USAC_ERR_ARG;
+    if (total_ms) *total_ms = c->last_total_ms;
+    if (score_kernel_ms) *score_kernel_ms = c->last_score_ms;
+    if (launches) *launches = c->last_launches;
+    if (score_launches) *score_launches = c->last_score_launches;
+    return USAC_OK;
+}
+
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 1.0f + threadIdx.x * 1e-3f + i;
+    const float b = 0.999f, cc = 1e-3f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], b, cc);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int usac_gpu_measure_fp32_peak(usac_gpu_ctx* c, double* tflops_out) {
+    if (!c || !tflops_out) return USAC_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int ctas = c->prop.multiProcessorCount * 8, iters = 1 << 14;
+    DevBuf<float> out;
+    CUDA_TRY(c, out.ensure((size_t)ctas * 256));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(c->ev0, c->stream);
+        fp32_peak_kernel<<<ctas, 256, 0, c->stream>>>(out.p, iters);
+        cudaEventRecord(c->ev1, c->stream);
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        const double fl = 2.0 * 8 * iters * 256.0 * ctas;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    out.release();
+    *tflops_out = best;
+    return USAC_OK;
+}

@@ -1,0 +1,263 @@
+"""GPU parity tests (run on the B200 box with -m gpu). Everything goes through the C ABI (ransac_b200.api is a ctypes
+shim); the CPU oracle is the checker. Integer results (sample indices, inlier counts, iteration counts) must be
+bit-exact; models produced by the device solvers must be bit-identical to the oracle's; error sums within 1e-4."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from ransac_b200 import generator as gen
+
+pytestmark = pytest.mark.gpu
+
+EST = {"line2d": O.EST_LINE2D, "homography": O.EST_HOMOGRAPHY, "fundamental": O.EST_FUNDAMENTAL, "essential": O.EST_ESSENTIAL}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ransac_b200 import GpuContext
+    c = GpuContext(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def models_for(est, pts, mask, count, seed):
+    """A mix of all-inlier, contaminated and ground-truth-adjacent models, produced by the oracle's solvers."""
+    g = np.random.default_rng(seed)
+    m = O.SAMPLE_SIZE[est]
+    out = []
+    inl = np.where(mask)[0]
+    while len(out) < count:
+        if len(out) % 3 == 0:
+            s = g.choice(inl, m, replace=False)
+        else:
+            s = g.choice(len(pts), m, replace=False)
+        for mod in O.solve_minimal(est, pts, s.astype(np.int32)):
+            out.append(mod)
+    return np.stack(out[:count])
+
+
+def check_scores(ctx, est, pts, models, thr):
+    cnt, s = ctx.score(models, thr)
+    flagged_total = 0
+    for i, mod in enumerate(models):
+        c_ref, s_ref, flagged = O.score(est, pts, mod, thr)
+        flagged_total += flagged
+        assert cnt[i] == c_ref, (i, cnt[i], c_ref, flagged)          # bit-exact, even inside the 1e-6 band
+        assert abs(s[i] - s_ref) <= 1e-4 * max(abs(s_ref), 1e-3), (i, s[i], s_ref)
+    return flagged_total
+
+
+def test_scoring_known_answers(ctx, golden_dir):
+    kat = np.load(os.path.join(golden_dir, "scoring_kat.npz"))
+    offs = kat["offsets"]
+    for i, name in enumerate(kat["names"]):
+        pts = kat["points"][offs[i]:offs[i + 1]]
+        model, thr, exp = kat["models"][i], float(kat["threshold"][i]), int(kat["expected"][i])
+        if kat["kind"][i] == 0:
+            ctx.set_points(O.EST_HOMOGRAPHY, pts)
+            inv, _ = O.inv3x3(model)
+            cnt, _ = ctx.score(np.stack([model.ravel(), inv.ravel()]), thr)
+            assert max(cnt) == exp, name
+        else:
+            ctx.set_points(O.EST_FUNDAMENTAL, pts)
+            cnt, _ = ctx.score(model.ravel()[None], thr)
+            assert cnt[0] == exp, name
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_score_matches_oracle(ctx, cfg):
+    pts, gt, mask = gen.make(cfg)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr = gen.CONFIGS[cfg]["threshold"]
+    models = models_for(est, pts, mask, 300, cfg)
+    models = np.concatenate([models, gt.reshape(1, -1)])
+    ctx.set_points(est, pts)
+    check_scores(ctx, est, pts, models, thr)
+    check_scores(ctx, est, pts, models[:40], thr * 10)               # LO thresholds (10x), quality.hpp:62-64
+
+
+def test_score_essential_metric(ctx):
+    pts, E, mask = gen.essential(n=5000)
+    g = np.random.default_rng(4)
+    models = [E.ravel()]
+    for _ in range(100):                                             # perturbed essential matrices
+        models.append((E + g.normal(0, 10 ** g.uniform(-4, -1), (3, 3)).astype(np.float32)).ravel())
+    models = np.stack(models).astype(np.float32)
+    ctx.set_points(O.EST_ESSENTIAL, pts)
+    check_scores(ctx, O.EST_ESSENTIAL, pts, models, 2.5e-3)
+
+
+def test_score_odd_and_tiny_sizes(ctx):
+    for n in (4, 5, 255, 256, 257, 513, 1001):
+        pts, H, mask = gen.homography(n=max(n, 40), seed=n)
+        pts = pts[:n]
+        ctx.set_points(O.EST_HOMOGRAPHY, pts)
+        models = np.stack([H.ravel(), (H * np.float32(1.001)).ravel() / np.float32(1.001 * H[2, 2])])
+        check_scores(ctx, O.EST_HOMOGRAPHY, pts, models.astype(np.float32), 2.0)
+
+
+def test_degenerate_models_do_not_count(ctx):
+    pts, H, _ = gen.homography(n=1000, seed=3)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    bad = np.array([[1, 2, 3, 2, 4, 6, 1, 0, 1],            # singular: cv::invert gives zeros -> NaN errors
+                    [0, 0, 0, 0, 0, 0, 0, 0, 0],
+                    [np.nan] * 9,
+                    [1e30, 0, 0, 0, 1e30, 0, 0, 0, 1]], np.float32)
+    cnt, s = ctx.score(bad, 2.0)
+    for i, mod in enumerate(bad):
+        assert cnt[i] == O.score(O.EST_HOMOGRAPHY, pts, mod, 2.0)[0]
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_errors_and_inliers_bit_exact(ctx, cfg):
+    pts, gt, mask = gen.make(cfg, n=3001) if cfg != 1 else gen.make(cfg)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr = gen.CONFIGS[cfg]["threshold"]
+    ctx.set_points(est, pts)
+    for mod in models_for(est, pts, mask, 5, 7):
+        e_gpu, e_ref = ctx.errors(mod), O.errors(est, pts, mod)
+        assert np.array_equal(bits(e_gpu), bits(e_ref))
+        ids = ctx.get_inliers(mod, thr)
+        assert np.array_equal(ids, O.score(est, pts, mod, thr, want_inliers=True)[3])
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_solvers_bit_identical_to_oracle(ctx, cfg):
+    pts, gt, mask = gen.make(cfg)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    m = O.SAMPLE_SIZE[est]
+    g = np.random.default_rng(cfg)
+    inl = np.where(mask)[0]
+    samples = np.stack([g.choice(inl, m, replace=False) if i % 2 else g.choice(len(pts), m, replace=False) for i in range(600)]).astype(np.int32)
+    samples[0, :] = samples[0, 0]                                    # degenerate: one point repeated
+    ctx.set_points(est, pts)
+    models, nm = ctx.estimate(samples)
+    w = 3 if est == O.EST_LINE2D else 9
+    total = 0
+    for j, s in enumerate(samples):
+        ref = O.solve_minimal(est, pts, s)
+        assert nm[j] == len(ref), (j, nm[j], len(ref))
+        for i in range(nm[j]):
+            assert np.array_equal(bits(models[j, i, :w]), bits(ref[i])), (j, i, models[j, i], ref[i])
+            total += 1
+    assert total > 100
+
+
+def test_philox_sampler_matches_oracle(ctx):
+    pts, _, _ = gen.homography(n=4000)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    got = ctx.sample(3000, seed=99, first_hyp=17)
+    ref = np.stack([O.philox_unique(99, 17 + j, 0, 4000, 4) for j in range(3000)])
+    assert np.array_equal(got, ref)
+
+
+def test_prosac_sampler_matches_oracle(ctx):
+    from ransac_b200.api import SAMPLER_PROSAC
+    pts, _, _ = gen.fundamental(n=2000)
+    ctx.set_points(O.EST_FUNDAMENTAL, pts)
+    s = O.Sampler(O.SAMPLER_PROSAC, O.RNG_PHILOX, 2000, 7, 5)
+    ref = s.table(2500)
+    got = ctx.sample(2500, sampler=SAMPLER_PROSAC, seed=5)
+    assert np.array_equal(got, ref)
+    # frozen termination length: the oracle switches to [0, L] once its pool outgrows L
+    s2 = O.Sampler(O.SAMPLER_PROSAC, O.RNG_PHILOX, 2000, 7, 5)
+    s2.set_termination_length(30)
+    ref2 = s2.table(1500)
+    got2 = ctx.sample(1500, sampler=SAMPLER_PROSAC, seed=5, prosac_termination_length=30)
+    assert np.array_equal(got2, ref2)
+
+
+def test_napsac_sampler_matches_oracle(ctx):
+    from ransac_b200.api import NEIGH_GRID, NEIGH_KNN, SAMPLER_NAPSAC
+    pts, _, _ = gen.homography(n=5000, clustered=True, seed=12)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    ctx.set_neighbors_grid(0, 100)
+    ref = O.Sampler(O.SAMPLER_NAPSAC, O.RNG_PHILOX, 5000, 4, 8, points=pts, cell_size=100).table(4000)
+    got = ctx.sample(4000, sampler=SAMPLER_NAPSAC, seed=8, neighbors=NEIGH_GRID)
+    assert np.array_equal(got, ref)
+    g = np.random.default_rng(1)
+    table = np.stack([g.choice(5000, 6, replace=False) for _ in range(5000)]).astype(np.int32)
+    ctx.set_neighbors_knn(0, table)
+    ref = O.Sampler(O.SAMPLER_NAPSAC, O.RNG_PHILOX, 5000, 4, 8, knn_table=table).table(4000)
+    got = ctx.sample(4000, sampler=SAMPLER_NAPSAC, seed=8, neighbors=NEIGH_KNN)
+    assert np.array_equal(got, ref)
+
+
+def assert_fit_equal(r, ref, est):
+    for key in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+        assert r[key] == ref[key], (key, r[key], ref[key])
+    assert np.array_equal(bits(r["model"]), bits(ref["model"]))
+    assert abs(r["score"] - ref["score"]) <= 1e-4 * max(ref["score"], 1e-3)
+
+
+@pytest.mark.parametrize("cfg,round_size", [(1, 64), (1, 0), (2, 0), (2, 100), (3, 0)])
+def test_fit_matches_oracle(ctx, cfg, round_size):
+    pts, gt, mask = gen.make(cfg)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    max_it = 10000 if cfg != 3 else 3000
+    ctx.set_points(est, pts)
+    for seed in (1, 2, 3):
+        r = ctx.fit(thr, conf, max_it, seed=seed, round_size=round_size)[0]
+        ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=max_it, seed=seed)
+        assert_fit_equal(r, ref, est)
+
+
+def test_fit_replays_reference_random_stream(ctx):
+    """Sample table = the reference's UniformSampler over glibc random() (uniform_sampler.hpp:42-54), seed 1."""
+    from ransac_b200.api import RNG_TABLE
+    pts, _, _ = gen.homography(n=4000)
+    table = O.Sampler(O.SAMPLER_UNIFORM, O.RNG_GLIBC, 4000, 4, 1).table(10000)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    r = ctx.fit(2.0, 0.95, 10000, rng=RNG_TABLE, sample_table=table)[0]
+    ref = O.ransac(pts, O.EST_HOMOGRAPHY, rng=O.RNG_GLIBC, threshold=2.0, confidence=0.95, seed=1)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+
+
+def test_fit_batched_ragged_problems(ctx):
+    sizes = [4000, 1500, 2333, 800, 4000, 64, 3100]
+    sets = [gen.homography(n=n, seed=100 + i) for i, n in enumerate(sizes)]
+    pts = np.concatenate([s[0] for s in sets])
+    ctx.set_points(O.EST_HOMOGRAPHY, pts, sizes)
+    res = ctx.fit(2.0, 0.95, 10000, seed=11)
+    for (p, _, _), r in zip(sets, res):
+        ref = O.ransac(p, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=2.0, confidence=0.95, seed=11)
+        assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+
+
+def test_fit_napsac_matches_oracle(ctx):
+    from ransac_b200.api import NEIGH_GRID, SAMPLER_NAPSAC
+    pts, _, mask = gen.homography(n=20000, inlier_ratio=0.1, clustered=True, seed=31)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    ctx.set_neighbors_grid(0, 50)
+    r = ctx.fit(2.0, 0.95, 2000, sampler=SAMPLER_NAPSAC, neighbors=NEIGH_GRID, seed=4, round_size=256)[0]
+    ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_GRID, cell_size=50,
+                   threshold=2.0, confidence=0.95, max_iterations=2000, seed=4)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+
+
+def test_full_size_properties_1m(ctx):
+    """BASELINE config 5 size: counts of a few models against the oracle, chunked partial sums, and the invariants
+    count(thr_a) <= count(thr_b) for thr_a < thr_b and count == len(get_inliers)."""
+    pts, H, mask = gen.make(5)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    inl = np.where(mask)[0]
+    g = np.random.default_rng(0)
+    models = [H.ravel()] + [O.solve_minimal(O.EST_HOMOGRAPHY, pts, g.choice(inl, 4, replace=False).astype(np.int32))[0] for _ in range(6)]
+    models = np.stack(models)
+    c2, s2 = ctx.score(models, 2.0)
+    c4, _ = ctx.score(models, 4.0)
+    assert (c2 <= c4).all()
+    for i in (0, 3):
+        c_ref, s_ref, _ = O.score(O.EST_HOMOGRAPHY, pts, models[i], 2.0)
+        assert c2[i] == c_ref and abs(s2[i] - s_ref) <= 1e-4 * s_ref
+    assert len(ctx.get_inliers(models[0], 2.0)) == c2[0]
+    many = np.repeat(models, 40, axis=0)                              # 280 models: several CTAs along x, many chunks
+    cm, _ = ctx.score(many, 2.0)
+    assert np.array_equal(cm, np.repeat(c2, 40))
