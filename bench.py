@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py - hypothesis x point evaluations per second and ms per robust fit of the USAC hypothesize-and-verify path.
+
+Workload (BASELINE.json configs[1]): homography, 4-point normalized DLT, inlier count + error sum (MSAC derivable),
+uniform sampler, N = 4000 correspondences, 30 % inliers, threshold 2 px, confidence 0.95, max 10 000 iterations.
+One such fit is ~1.5 M evaluations (a few microseconds of B200 time), so a "step" is a BATCH of independent image
+pairs of that size - the reference's own batched use (Tests::getStatisticalResults loops fits, test/tests.h:148-150) -
+all run to their own adaptive termination through usac_gpu_fit (sample -> solve -> score -> best-update -> terminate).
+
+  value : useful evaluations/s with the point sets resident in HBM. "Useful" = the evaluations the sequential loop of
+          ransac.cpp:58-139 executes for the same sample stream (speculative tail of the last round is NOT counted).
+  e2e   : the same with HOST buffers: every step copies the step's point sets host->device (pinned memory) through
+          usac_gpu_set_points, fits, and reads the results (model, inliers, score, iterations) back.
+  roofline : the scoring kernel, FP32 bound (BASELINE.json: "the roofline is FP32 FMA throughput plus HBM point
+          streaming"); algorithmic 42 flop per homography evaluation.
+  cpu_baseline / --impl reference : the CPU oracle (a restatement - the reference needs OpenCV-contrib/Eigen/nanoflann
+          and cannot be compiled here) on the box's host cores, on a bounded sample of the same problems.
+
+Multi-GPU: one process per GPU (torchrun); independent image pairs shard across ranks with no data-path collective
+(weak scaling: every rank owns --problems pairs). `--workload c5` instead shards the HYPOTHESES of one 1M-point fit
+across the ranks with one NCCL all-gather per round (BASELINE.json configs[4]).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_EVAL = {"homography": 42, "fundamental": 33, "essential": 44, "line2d": 4}
+THR, CONF, MAX_IT, N_POINTS, INLIER_RATIO = 2.0, 0.95, 10000, 4000, 0.3
+METRIC = "hypothesis x point evaluations/s (useful, whole job); ms per robust fit in config"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def make_problems(count, first_seed):
+    from ransac_b200 import generator as gen
+    return [gen.homography(n=N_POINTS, inlier_ratio=INLIER_RATIO, seed=first_seed + i)[0] for i in range(count)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML): SM clock + throttle reasons during the timed region
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:   # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_fits(problems, seeds, threads):
+    """-> (evals, seconds, iterations list) of oracle fits (reference-sequential semantics) over `problems`."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    O.lib()
+
+    def one(args):
+        p, s = args
+        return O.ransac(p, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=s)
+    t0 = time.perf_counter()
+    if threads == 1:
+        rs = [one(a) for a in zip(problems, seeds)]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            rs = list(ex.map(one, zip(problems, seeds)))
+    dt = time.perf_counter() - t0
+    return sum(r["evals"] for r in rs), dt, rs
+
+
+def cpu_baseline(budget_s=12.0):
+    """Bounded sample: as many C2 problems as fit ~budget_s of wall time on all host cores (the reference itself is
+    single-threaded; the per-core figure is reported next to it)."""
+    cores = os.cpu_count() or 1
+    probe = make_problems(2, 5000)
+    e1, t1, _ = cpu_fits(probe, [1, 1], 1)
+    per_fit = t1 / 2
+    count = int(max(cores, min(4096, budget_s / per_fit * cores * 0.8)))
+    problems = make_problems(count, 1000)
+    evals, dt, rs = cpu_fits(problems, [1] * count, cores)
+    return {"value": evals / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": f"{count} of the C2 image pairs (first seeds of the GPU batch), oracle/libusac_oracle.so -O2 -ffp-contract=off, "
+                      f"{cores} threads over independent fits; single thread: {e1 / t1:.3e} evals/s",
+            "ms_per_fit": dt / count * 1e3, "single_thread_value": e1 / t1}
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores, args.ref_problems)
+    problems = make_problems(per_step, 1000)
+    seeds = [1] * per_step
+    for _ in range(args.warmup):
+        cpu_fits(problems[:cores], seeds[:cores], cores)
+    evals = 0
+    t = 0.0
+    for _ in range(args.steps):
+        e, dt, _ = cpu_fits(problems, seeds, cores)
+        evals += e
+        t += dt
+    v = evals / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(per_step), "ms_per_fit": t / args.steps / per_step * 1e3},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} C2 image pairs per step, CPU oracle (restated reference; the reference needs "
+                                       "OpenCV-contrib/Eigen/nanoflann and does not compile here), all host threads over independent fits"},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(problems):
+    return (f"C2 homography 4-pt normalized DLT, uniform sampler, N={N_POINTS}, {int(INLIER_RATIO * 100)}% inliers, thr {THR}, "
+            f"conf {CONF}, max_iter {MAX_IT}; step = {problems} independent image pairs per GPU, each run to adaptive termination")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from ransac_b200 import GpuContext, capi
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.problems
+    problems = make_problems(B, 1000 + rank * B)
+    host = torch.empty((B * N_POINTS, 4), dtype=torch.float32).pin_memory()
+    host.numpy()[:] = np.concatenate(problems)
+    sizes = [N_POINTS] * B
+
+    ctx = GpuContext(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    info = ctx.device_info()
+    fit_kw = dict(threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=1, round_size=args.round_size)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        """K steps bracketed by barrier+synchronize, CUDA events on the launching stream -> (ms, per-step stats)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stats = []
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                stats.append(step_fn())
+            ev1.record(stream)
+        barrier()
+        return ev0.elapsed_time(ev1), stats
+
+    def step_resident():
+        res = ctx.fit(**fit_kw)
+        t = ctx.last_timing()
+        return (sum(r["useful_evals"] for r in res), sum(r["evals"] for r in res), t["launches"], t["score_launches"], t["score_ms"],
+                sum(r["iterations"] for r in res), max(r["rounds"] for r in res))
+
+    def step_e2e():
+        ctx.set_points(capi.EST_HOMOGRAPHY, host, sizes)
+        return step_resident()
+
+    # ---- device-resident arm ----
+    ctx.set_points(capi.EST_HOMOGRAPHY, host, sizes)
+    timed(step_resident, args.warmup)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, stats = timed(step_resident, args.steps)
+    clk = clocks.stop()
+    useful = sum(s[0] for s in stats)
+    executed = sum(s[1] for s in stats)
+    launches = sum(s[2] for s in stats)
+    score_launches = sum(s[3] for s in stats)
+    score_ms = sum(s[4] for s in stats)
+    iters = sum(s[5] for s in stats)
+    # ---- end-to-end arm (host buffers) ----
+    timed(step_e2e, 1)
+    ms_e2e, stats_e2e = timed(step_e2e, args.steps)
+    useful_e2e = sum(s[0] for s in stats_e2e)
+    d2h_step = sum(s[6] for s in stats_e2e) / args.steps * B * 168      # one FitState record per problem and round
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([useful, useful_e2e, executed, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_all, ms_e2e_all = t.tolist()
+    useful_all, useful_e2e_all, executed_all, launches_all = cnt.tolist()
+
+    if rank == 0:
+        fp32_peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12       # TFLOP/s at the max SM clock
+        measured_ffma = ctx.measure_fp32_peak()
+        flops_launch = FLOPS_PER_EVAL["homography"] * executed / max(score_launches, 1)
+        ach = flops_launch / (score_ms / max(score_launches, 1) * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:   # noqa: BLE001
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes_launch = (16.0 * N_POINTS * B + 128.0 * executed / N_POINTS) / 1.0       # every point once per pass + the model records
+        roofline = {"bound": "fp32", "kernel": "score_kernel<HOMOGRAPHY>", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak, "traffic": None,
+                    "peak_source": "2*128 lanes*SMs*max SM clock from the device (no FP32 figure in MEASURED_PEAKS.json); "
+                                   f"register-resident FFMA loop measured in this run: {measured_ffma:.1f} TFLOP/s",
+                    "flops_per_eval": 42, "evals_per_launch": executed / max(score_launches, 1),
+                    "avg_launch_ms": score_ms / max(score_launches, 1), "score_share_of_step": score_ms / ms,
+                    "hbm": {"algorithmic_bytes_per_launch": alg_bytes_launch,
+                            "achieved_gbs": alg_bytes_launch / (score_ms / max(score_launches, 1) * 1e-3) / 1e9,
+                            "peak_gbs": hbm_peak, "peak_source": "measured" if peaks else "fallback"}}
+        line = {"metric": METRIC, "value": useful_all / (ms_all * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(B), "problems_per_gpu": B, "round_size": args.round_size,
+                           "l2": f"inputs larger than L2: {B * N_POINTS * 32 / 1e6:.0f} MB of points per GPU (AoS + pair layout) vs 126 MB",
+                           "ms_per_fit": ms_all / args.steps / B, "avg_iterations_per_fit": iters / (args.steps * B),
+                           "evals_executed_per_s": executed_all / (ms_all * 1e-3), "useful_fraction": useful / max(executed, 1)},
+                "clocks": clk, "gpu_launches": int(launches_all),
+                "e2e": {"value": useful_e2e_all / (ms_e2e_all * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": B * N_POINTS * 16,
+                        "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e_all / args.steps, "ms_per_fit": ms_e2e_all / args.steps / B},
+                "roofline": roofline}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        if args.latency:
+            line["config"]["single_fit_latency_ms"] = single_fit_latency(ctx, problems[0], timed)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def single_fit_latency(ctx, pts, timed):
+    """ms per robust fit when ONE image pair is fitted alone (launch/sync latency bound), median of 20."""
+    from ransac_b200 import capi
+    ctx.set_points(capi.EST_HOMOGRAPHY, pts)
+    vals = []
+    for i in range(23):
+        ms, _ = timed(lambda: ctx.fit(threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=1), 1)
+        if i >= 3:
+            vals.append(ms)
+    return float(np.median(vals))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--problems", type=int, default=2368, help="image pairs per GPU and step (2368 = 16 x 148 SMs)")
+    ap.add_argument("--ref-problems", type=int, default=256, help="image pairs per step of the CPU reference arm")
+    ap.add_argument("--round-size", type=int, default=128, help="samples per round and problem")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

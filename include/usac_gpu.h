@@ -38,6 +38,9 @@ void usac_gpu_destroy(usac_gpu_ctx* ctx);
 const char* usac_gpu_last_error(const usac_gpu_ctx* ctx);   /* ctx may be NULL: error of the failed create */
 /* {sm_count, sm_clock_khz, cc_major*10+cc_minor, l2_bytes} of the bound device */
 int usac_gpu_device_info(const usac_gpu_ctx* ctx, int info[4]);
+/* Run every later call on the caller's CUDA stream (a cudaStream_t passed as void*; the caller keeps ownership) instead
+ * of the handle's own non-blocking stream - lets a host time several calls with its own events on that stream. */
+int usac_gpu_set_stream(usac_gpu_ctx* ctx, void* cuda_stream);
 
 /* ---- data: replaces `Ransac::Ransac(Model*, cv::InputArray points)` (ransac.hpp:41-55) + initEstimator (init.cpp:3) */
 /* One call uploads `num_problems` independent point sets (image pairs) of one estimator type; problem p owns rows
@@ -100,7 +103,9 @@ typedef struct {
     long long best_hyp;          /* sample id of the best model, -1 if none */
     int best_model_idx;
     unsigned rounds;
-    unsigned long long evals;    /* hypothesis x point evaluations executed on this GPU */
+    unsigned long long evals;    /* hypothesis x point evaluations executed on this GPU (whole rounds) */
+    unsigned long long useful_evals; /* the part of `evals` the sequential loop of ransac.cpp:58-139 would also have
+                                        executed: models of the samples up to the one that ended the loop */
 } usac_fit_result;
 
 int usac_gpu_fit(usac_gpu_ctx* ctx, const usac_fit_cfg* cfg, usac_fit_result* results /* [num_problems] */);

@@ -54,6 +54,10 @@ class GpuContext:
         self._check(self.L.usac_gpu_device_info(self.h, C.byref(info)), "device_info")
         return {"sm_count": info[0], "sm_clock_khz": info[1], "cc": info[2], "l2_bytes": info[3]}
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream); the caller keeps it alive."""
+        self._check(self.L.usac_gpu_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")
+
     # ---- data ----
     def set_points(self, est, points, n_per_problem=None):
         """points: [sum(n), dim] float32 host array (numpy or CPU torch tensor); n_per_problem: list of row counts."""
@@ -138,7 +142,7 @@ class GpuContext:
         w = 3 if self.est == EST_LINE2D else 9
         return [{"model": np.array(r.model[:w], np.float32), "inliers": r.inliers, "score": r.score, "iterations": r.iterations,
                  "samples_drawn": r.samples_drawn, "best_hyp": r.best_hyp, "best_model_idx": r.best_model_idx, "rounds": r.rounds,
-                 "evals": r.evals} for r in res]
+                 "evals": r.evals, "useful_evals": r.useful_evals} for r in res]
 
     def last_timing(self):
         t, s = C.c_float(), C.c_float()

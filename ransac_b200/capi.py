@@ -34,7 +34,7 @@ class FitCfg(C.Structure):
 class FitResult(C.Structure):
     _fields_ = [("model", C.c_float * 9), ("inliers", C.c_int), ("score", C.c_float), ("iterations", C.c_uint),
                 ("samples_drawn", C.c_uint), ("best_hyp", C.c_longlong), ("best_model_idx", C.c_int), ("rounds", C.c_uint),
-                ("evals", C.c_ulonglong)]
+                ("evals", C.c_ulonglong), ("useful_evals", C.c_ulonglong)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -65,6 +65,7 @@ def load():
     L.usac_gpu_last_error.argtypes = [vp]
     L.usac_gpu_last_error.restype = C.c_char_p
     L.usac_gpu_device_info.argtypes = [vp, C.POINTER(C.c_int * 4)]
+    L.usac_gpu_set_stream.argtypes = [vp, vp]
     L.usac_gpu_set_points.argtypes = [vp, C.c_int, vp, ip, C.c_int]
     L.usac_gpu_set_neighbors_grid.argtypes = [vp, C.c_int, C.c_int]
     L.usac_gpu_set_neighbors_knn.argtypes = [vp, C.c_int, ip, C.c_int]

@@ -43,7 +43,7 @@ struct FitState {
     int best_midx;
     unsigned iters, max_iters, samples_drawn, rounds;
     int done;
-    unsigned long long evals;
+    unsigned long long evals, useful_evals;
     // PROSAC sampler state (prosac_sampler.hpp:19-31)
     unsigned prosac_t, prosac_n, prosac_largest, prosac_term_len;
     unsigned prosac_t_next, prosac_n_next, prosac_largest_next;   // written by the sampler, committed at round end

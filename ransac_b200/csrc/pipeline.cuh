@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
     __shared__ int s_j[256];
     __shared__ int s_stop[256];
     __shared__ int s_T;
+    __shared__ unsigned s_useful;
     const int slot = blockIdx.x;
     const int pid = a.active[slot];
     FitState& st = a.state[pid];
@@ -391,9 +392,17 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
         int T = K;
         for (int t = 0; t < (int)blockDim.x; t++) T = min(T, s_stop[t]);
         s_T = T;
+        s_useful = 0;
     }
     __syncthreads();
     const int T = s_T;
+    {   // models this rank scored for samples 0..T: what the sequential loop would have evaluated too
+        unsigned u = 0;
+        const int* nmod = a.nmodels + (size_t)slot * K;
+        for (int j = j0; j < j1 && j <= T; j++) u += (unsigned)nmod[j];
+        if (u) atomicAdd(&s_useful, u);
+    }
+    __syncthreads();
     // the owner of T (or the last thread when the round did not terminate) publishes the result
     const bool owner = (T < K) ? (stop == T) : (threadIdx.x == blockDim.x - 1);
     if (owner) {
@@ -410,6 +419,7 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
         st.done = (T < K) || !(st.iters < st.max_iters);
         st.samples_drawn += (unsigned)K;
         st.rounds += 1;
+        st.useful_evals += (unsigned long long)s_useful * (unsigned long long)pd.n;
     }
 }
 

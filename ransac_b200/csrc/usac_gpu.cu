@@ -37,6 +37,7 @@ struct DevBuf {
 struct usac_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     cudaDeviceProp prop;
     std::string err;
     void set_error(const char* what, const char* why) { err = std::string(what) + ": " + why; }
@@ -146,8 +147,18 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     if (c->h_active) cudaFreeHost(c->h_active);
     for (auto& pr : c->score_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+extern "C" int usac_gpu_set_stream(usac_gpu_ctx* c, void* cuda_stream) {
+    if (!c) return USAC_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return USAC_OK;
 }
 
 extern "C" const char* usac_gpu_last_error(const usac_gpu_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -815,6 +826,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         for (int i = 0; i < w; i++) r.model[i] = s.best_model[i];
         r.inliers = s.best_cnt; r.score = s.best_sum; r.iterations = s.iters; r.samples_drawn = s.samples_drawn;
         r.best_hyp = s.best_hyp; r.best_model_idx = s.best_midx; r.rounds = s.rounds; r.evals = s.evals;
+        r.useful_evals = s.useful_evals;
     }
     return USAC_OK;
 }
