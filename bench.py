@@ -208,10 +208,10 @@ def run_native(args):
         return ev0.elapsed_time(ev1), stats
 
     def step_resident():
-        res = ctx.fit(**fit_kw)
+        res = ctx.fit_records(**fit_kw)
         t = ctx.last_timing()
-        return (sum(r["useful_evals"] for r in res), sum(r["evals"] for r in res), t["launches"], t["score_launches"], t["score_ms"],
-                sum(r["iterations"] for r in res), max(r["rounds"] for r in res))
+        return (int(res["useful_evals"].sum()), int(res["evals"].sum()), t["launches"], t["score_launches"], t["score_ms"],
+                int(res["iterations"].sum()), int(res["rounds"].max()))
 
     def step_e2e():
         ctx.set_points(capi.EST_HOMOGRAPHY, host, sizes)
@@ -234,7 +234,8 @@ def run_native(args):
     timed(step_e2e, 1)
     ms_e2e, stats_e2e = timed(step_e2e, args.steps)
     useful_e2e = sum(s[0] for s in stats_e2e)
-    d2h_step = sum(s[6] for s in stats_e2e) / args.steps * B * 168      # one FitState record per problem and round
+    # results: one 168-byte FitState record per problem at the end + one `done` int per still-active problem per round
+    d2h_step = B * 168 + sum(s[6] for s in stats_e2e) / args.steps * B * 4   # (upper bound: every problem active in every round)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([useful, useful_e2e, executed, launches], dtype=torch.float64, device="cuda")

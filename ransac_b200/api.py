@@ -126,8 +126,10 @@ class GpuContext:
         return models, nm
 
     # ---- fused fit ----
-    def fit(self, threshold, confidence=0.95, max_iterations=10000, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, seed=1, sprt=False,
-            round_size=0, neighbors=NEIGH_NONE, sample_table=None, rank=0, nranks=1):
+    def fit_records(self, threshold, confidence=0.95, max_iterations=10000, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, seed=1,
+                    sprt=False, round_size=0, neighbors=NEIGH_NONE, sample_table=None, rank=0, nranks=1):
+        """One robust fit per uploaded problem; returns a numpy record array laid out as usac_fit_result (no per-problem
+        Python work: this is what a batched caller uses)."""
         cfg = capi.FitCfg()
         cfg.sampler = capi.SamplerCfg(sampler, rng, seed, neighbors, 0, 0)
         cfg.threshold, cfg.confidence, cfg.max_iterations = threshold, confidence, max_iterations
@@ -139,10 +141,16 @@ class GpuContext:
         P = len(self.n)
         res = (capi.FitResult * P)()
         self._check(self.L.usac_gpu_fit(self.h, C.byref(cfg), res), "fit")
+        return np.frombuffer(res, dtype=np.dtype(capi.FitResult), count=P)
+
+    def fit(self, *args, **kw):
+        """fit_records as a list of dicts (model as float32 array of 9, or 3 for lines)."""
+        rec = self.fit_records(*args, **kw)
         w = 3 if self.est == EST_LINE2D else 9
-        return [{"model": np.array(r.model[:w], np.float32), "inliers": r.inliers, "score": r.score, "iterations": r.iterations,
-                 "samples_drawn": r.samples_drawn, "best_hyp": r.best_hyp, "best_model_idx": r.best_model_idx, "rounds": r.rounds,
-                 "evals": r.evals, "useful_evals": r.useful_evals} for r in res]
+        return [{"model": np.array(r["model"][:w], np.float32), "inliers": int(r["inliers"]), "score": float(r["score"]),
+                 "iterations": int(r["iterations"]), "samples_drawn": int(r["samples_drawn"]), "best_hyp": int(r["best_hyp"]),
+                 "best_model_idx": int(r["best_model_idx"]), "rounds": int(r["rounds"]), "evals": int(r["evals"]),
+                 "useful_evals": int(r["useful_evals"])} for r in rec]
 
     def last_timing(self):
         t, s = C.c_float(), C.c_float()

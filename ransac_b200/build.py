@@ -15,20 +15,22 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "usac_gpu.h")]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants, e.g. build(defines=["USAC_PPI=1"], out="libusac_gpu_ppi1.so") (tools/ only)."""
     srcs = sources()
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
-        return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB, os.path.join(CSRC, "usac_gpu.cu")]
+    lib = os.path.join(HERE, out) if out else LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(s) <= os.path.getmtime(lib) for s in srcs):
+        return lib
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-o", lib, os.path.join(CSRC, "usac_gpu.cu")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = res.stdout
-    with open(os.path.join(HERE, "build.log"), "w") as fh:
+    with open(os.path.join(HERE, "build.log" if not out else out + ".log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + log)
     if verbose or res.returncode:
         print(log)
     if res.returncode:
         raise RuntimeError("nvcc failed, see ransac_b200/build.log")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libusac_gpu.so")
+LIB_PATH = os.environ.get("USAC_GPU_LIB", os.path.join(_HERE, "libusac_gpu.so"))   # env override: tuning variants only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "usac_gpu.h")
 
 EST_LINE2D, EST_HOMOGRAPHY, EST_FUNDAMENTAL, EST_ESSENTIAL = 1, 2, 3, 4

@@ -9,6 +9,12 @@
 #define USAC_TILE_PAIRS 128         // point pairs per shared-memory tile (256 points)
 #define USAC_STAGES 4               // bulk-copy pipeline depth of the scoring kernel
 #define USAC_SCORE_THREADS 128      // models per scoring CTA
+#ifndef USAC_SCORE_MIN_CTAS
+#define USAC_SCORE_MIN_CTAS 8        // resident scoring CTAs per SM (8 -> <= 64 registers per thread)
+#endif
+#ifndef USAC_PPI
+#define USAC_PPI 2                  // point pairs per trip of the scoring loop (independent instruction streams)
+#endif
 
 // Prepared-model record (one per valid model, written by prepare_kernel, read by the scoring kernels):
 //   [0..8]   model, row-major (line: a b c in [0..2])

@@ -36,6 +36,7 @@ struct RoundArgs {
     int sprt;
     const int* pool;             // shuffled point pools (ProblemDesc::pool_off)
     struct SprtModelResult* sprt_res;   // [slot][K*S]
+    int* done_out;               // [slot] FitState::done after the round (the only thing the host reads per round)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -53,20 +54,24 @@ __device__ __forceinline__ void make_record(int est, const float* model, float t
     if (est == USAC_EST_HOMOGRAPHY) {
         cv_inv3x3(model, rec + REC_HINV);
         const float* g = rec + REC_HINV;
-        const float T = 2.f * thr;
+        // |fl32 reference value of 2*err  -  fast value| <= c0 + K1 |1/nz| + K2 |1/mz| for every point that either
+        // arithmetic puts at or below the threshold (first order in u, derivation in DESIGN.md section 4.2):
+        //   projections: reference 3u*A, fast (FMA) 2u*A, A = |h_i1 x| + |h_i2 y| + |h_i3| <= b*;
+        //   quotient: reference u, fast 4u (product, rcp.approx 2^-23, product);  norm: reference 2u, fast 3u.
+        // c0 is folded into the first term with |1/nz| >= 1/bz1.
+        const float T2 = 2.f * thr;
         const float bx1 = fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2]);
         const float by1 = fabsf(f[3]) * pd.mx1 + fabsf(f[4]) * pd.my1 + fabsf(f[5]);
         const float bz1 = fabsf(f[6]) * pd.mx1 + fabsf(f[7]) * pd.my1 + fabsf(f[8]);
         const float bx2 = fabsf(g[0]) * pd.mx2 + fabsf(g[1]) * pd.my2 + fabsf(g[2]);
         const float by2 = fabsf(g[3]) * pd.mx2 + fabsf(g[4]) * pd.my2 + fabsf(g[5]);
         const float bz2 = fabsf(g[6]) * pd.mx2 + fabsf(g[7]) * pd.my2 + fabsf(g[8]);
-        const float e1 = fmaxf(pd.mx1, pd.my1) + 2.f * T, e2 = fmaxf(pd.mx2, pd.my2) + 2.f * T;   // |estimate| near the threshold
-        const float k = 1.4142136f * 8.f * u;
-        const float c0 = k * (e1 + e2) + 8.f * u * T;
-        const float C = k * (bz2 * (fmaxf(bx1, by1) + e2 * bz1) + bz1 * (fmaxf(bx2, by2) + e1 * bz2));
-        // |t| <= c0 + C|r|, and |r| <= (1 + r^2)/2
-        rec[REC_BAND] = c0 + 0.5f * C;
-        rec[REC_BAND + 1] = 0.5f * C;
+        const float g8 = 8.f * u;
+        const float K1 = g8 * ((bx1 + by1) + (pd.mx2 + pd.my2 + 2.1f * T2) * bz1);
+        const float K2 = g8 * ((bx2 + by2) + (pd.mx1 + pd.my1 + 2.1f * T2) * bz2);
+        const float c0 = g8 * (pd.mx1 + pd.my1 + pd.mx2 + pd.my2 + 4.2f * T2) + 16.f * u * T2;
+        rec[REC_BAND] = 1.001f * (K1 + c0 * bz1);
+        rec[REC_BAND + 1] = 1.001f * K2;
     } else if (est == USAC_EST_FUNDAMENTAL) {
         const float ba = fabsf(f[0]) * pd.mx1 + fabsf(f[1]) * pd.my1 + fabsf(f[2]);
         const float bb = fabsf(f[3]) * pd.mx1 + fabsf(f[4]) * pd.my1 + fabsf(f[5]);
@@ -435,15 +440,21 @@ __global__ void winner_kernel(const RoundArgs a, int slots) {
     const long long first = (long long)st.samples_drawn - a.K;       // select_kernel already advanced samples_drawn
     if (st.best_hyp >= first) {
         const int j = (int)(st.best_hyp - first);
-        int s[8];
-        const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
-        for (int i = 0; i < a.m; i++) s[i] = src[i];
-        float out[27];
-        const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
-        const int k = solve_minimal<EST>(pts, s, out);
         const int w = EST == USAC_EST_LINE2D ? 3 : 9;
-        if (st.best_midx < k) for (int i = 0; i < w; i++) st.best_model[i] = out[9 * st.best_midx + i];
+        if (a.nranks == 1 || (j % a.nranks) == a.rank) {            // this rank solved the sample: the model is in HBM
+            const float* src = a.models_raw + (((size_t)slot * a.K + j) * a.S + st.best_midx) * 9;
+            for (int i = 0; i < w; i++) st.best_model[i] = src[i];
+        } else {                                                    // another rank's sample: re-derive (deterministic solver)
+            int s[8];
+            const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
+            for (int i = 0; i < a.m; i++) s[i] = src[i];
+            float out[27];
+            const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+            const int k = solve_minimal<EST>(pts, s, out);
+            if (st.best_midx < k) for (int i = 0; i < w; i++) st.best_model[i] = out[9 * st.best_midx + i];
+        }
     }
+    if (a.done_out) a.done_out[slot] = st.done;
     st.evals += (unsigned long long)a.mvalid[slot] * (unsigned long long)pd.n;
     st.prosac_t = st.prosac_t_next; st.prosac_n = st.prosac_n_next; st.prosac_largest = st.prosac_largest_next;
 }

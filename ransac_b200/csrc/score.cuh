@@ -20,7 +20,7 @@
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float2 dup(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 dup(float x) { return make_float2(x, x); }   // folds into the scalar-broadcast operand form of FFMA2
 
 // ---- mbarrier / bulk-copy helpers (PTX ISA 8.x, sm_90+) ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,31 +51,35 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 }
 
 // ---- per-estimator fast evaluators --------------------------------------------------------------------------------
-// eval(): given one pair of points returns, per lane, `t` (< 0 <=> inlier by the fast path), `bnd` (guard band for
-// |t|) and `e` (the value accumulated into the error sum for an inlier, in the units of finish()).
+// eval(): given one pair of points returns, per lane,
+//   t   : decision value, t < 0 <=> inlier by the fast path (homography/essential: 2*err - 2*thr, fundamental:
+//         n^2 - thr*den, line: err - thr);
+//   s   : guard band (>= 0): the fast decision is trusted only when |t| > s, otherwise the point is re-evaluated with
+//         the reference's exact arithmetic (strict_em);
+//   w   : (fundamental only) 1/den, so that min(t,0)*w = err - thr.
+// The kernel accumulates em = min(t, 0) [* w] (NaN-safe: fminf drops a NaN) and counts its sign bits; finish() turns
+// (sum of em, count) into the reference's error sum of the inliers.
 
 template <int EST> struct FastModel;
 
 template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
-    // rows 0,1 negated so that dx = x2 - nx/nz is a single FFMA2
-    float2 a11, a12, a13, a21, a22, a23, h31, h32, h33;
-    float2 b11, b12, b13, b21, b22, b23, g31, g32, g33;
-    float2 negT, c0, c1;
+    // rows 0,1 negated so that dx = x2 - nx/nz is a single FFMA2; scalars are broadcast by the FFMA2 operand form
+    float a11, a12, a13, a21, a22, a23, h31, h32, h33;
+    float b11, b12, b13, b21, b22, b23, g31, g32, g33;
+    float negT, k1, k2;
     __device__ __forceinline__ void load(const float* r) {
-        a11 = dup(-r[0]); a12 = dup(-r[1]); a13 = dup(-r[2]); a21 = dup(-r[3]); a22 = dup(-r[4]); a23 = dup(-r[5]);
-        h31 = dup(r[6]); h32 = dup(r[7]); h33 = dup(r[8]);
-        b11 = dup(-r[9]); b12 = dup(-r[10]); b13 = dup(-r[11]); b21 = dup(-r[12]); b22 = dup(-r[13]); b23 = dup(-r[14]);
-        g31 = dup(r[15]); g32 = dup(r[16]); g33 = dup(r[17]);
-        negT = dup(-2.f * r[REC_THR]); c0 = dup(r[REC_BAND]); c1 = dup(r[REC_BAND + 1]);
+        a11 = -r[0]; a12 = -r[1]; a13 = -r[2]; a21 = -r[3]; a22 = -r[4]; a23 = -r[5]; h31 = r[6]; h32 = r[7]; h33 = r[8];
+        b11 = -r[9]; b12 = -r[10]; b13 = -r[11]; b21 = -r[12]; b22 = -r[13]; b23 = -r[14]; g31 = r[15]; g32 = r[16]; g33 = r[17];
+        negT = -2.f * r[REC_THR]; k1 = r[REC_BAND]; k2 = r[REC_BAND + 1];
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& bnd, float2& e) const {
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
-        const float2 nz = __ffma2_rn(h31, X1, __ffma2_rn(h32, Y1, h33));
-        const float2 nx = __ffma2_rn(a11, X1, __ffma2_rn(a12, Y1, a13));   // -(h11 x1 + h12 y1 + h13)
-        const float2 ny = __ffma2_rn(a21, X1, __ffma2_rn(a22, Y1, a23));
-        const float2 mz = __ffma2_rn(g31, X2, __ffma2_rn(g32, Y2, g33));
-        const float2 mx = __ffma2_rn(b11, X2, __ffma2_rn(b12, Y2, b13));
-        const float2 my = __ffma2_rn(b21, X2, __ffma2_rn(b22, Y2, b23));
+        const float2 nz = __ffma2_rn(dup(h31), X1, __ffma2_rn(dup(h32), Y1, dup(h33)));
+        const float2 nx = __ffma2_rn(dup(a11), X1, __ffma2_rn(dup(a12), Y1, dup(a13)));   // -(h11 x1 + h12 y1 + h13)
+        const float2 ny = __ffma2_rn(dup(a21), X1, __ffma2_rn(dup(a22), Y1, dup(a23)));
+        const float2 mz = __ffma2_rn(dup(g31), X2, __ffma2_rn(dup(g32), Y2, dup(g33)));
+        const float2 mx = __ffma2_rn(dup(b11), X2, __ffma2_rn(dup(b12), Y2, dup(b13)));
+        const float2 my = __ffma2_rn(dup(b21), X2, __ffma2_rn(dup(b22), Y2, dup(b23)));
         const float2 q = __fmul2_rn(nz, mz);
         const float2 r = make_float2(fast_rcp(q.x), fast_rcp(q.y));        // one reciprocal serves both projections
         const float2 r1 = __fmul2_rn(r, mz), r2 = __fmul2_rn(r, nz);       // 1/nz, 1/mz
@@ -84,102 +88,102 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
         const float2 sa = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
         const float2 sb = __ffma2_rn(ey, ey, __fmul2_rn(ex, ex));
         const float2 d1 = make_float2(fast_sqrt(sa.x), fast_sqrt(sa.y)), d2 = make_float2(fast_sqrt(sb.x), fast_sqrt(sb.y));
-        e = __fadd2_rn(d1, d2);                                             // 2 * error
-        t = __fadd2_rn(e, negT);
-        bnd = __ffma2_rn(c1, __fmul2_rn(r, r), c0);
+        t = __fadd2_rn(__fadd2_rn(d1, dup(negT)), d2);                     // 2*err - 2*thr
+        const float2 p1 = __fmul2_rn(dup(k1), r1), p2 = __fmul2_rn(dup(k2), r2);
+        s = make_float2(fabsf(p1.x) + fabsf(p2.x), fabsf(p1.y) + fabsf(p2.y));
+        w = t;
     }
-    static __device__ __forceinline__ float finish(float sum) { return 0.5f * sum; }
-    static __device__ __forceinline__ float strict_to_e(float err) { return 2.f * err; }
+    static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
+    static __device__ __forceinline__ float strict_to_em(float err, float thr) { return 2.f * err - 2.f * thr; }
 };
 
 template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
-    float2 f11, f12, f13, f21, f22, f23, f31, f32, f33, negthr, b1, b0;
+    float f11, f12, f13, f21, f22, f23, f31, f32, f33, negthr, b1, b0;
     __device__ __forceinline__ void load(const float* r) {
-        f11 = dup(r[0]); f12 = dup(r[1]); f13 = dup(r[2]); f21 = dup(r[3]); f22 = dup(r[4]); f23 = dup(r[5]);
-        f31 = dup(r[6]); f32 = dup(r[7]); f33 = dup(r[8]);
-        negthr = dup(-r[REC_THR]); b1 = dup(r[REC_BAND]); b0 = dup(r[REC_BAND + 1]);
+        f11 = r[0]; f12 = r[1]; f13 = r[2]; f21 = r[3]; f22 = r[4]; f23 = r[5]; f31 = r[6]; f32 = r[7]; f33 = r[8];
+        negthr = -r[REC_THR]; b1 = r[REC_BAND]; b0 = r[REC_BAND + 1];
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& bnd, float2& e) const {
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
-        const float2 a = __ffma2_rn(f11, X1, __ffma2_rn(f12, Y1, f13));
-        const float2 b = __ffma2_rn(f21, X1, __ffma2_rn(f22, Y1, f23));
-        const float2 c = __ffma2_rn(f11, X2, __ffma2_rn(f21, Y2, f31));
-        const float2 d = __ffma2_rn(f12, X2, __ffma2_rn(f22, Y2, f32));
-        const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, __ffma2_rn(f31, X1, __ffma2_rn(f32, Y1, f33))));
+        const float2 a = __ffma2_rn(dup(f11), X1, __ffma2_rn(dup(f12), Y1, dup(f13)));
+        const float2 b = __ffma2_rn(dup(f21), X1, __ffma2_rn(dup(f22), Y1, dup(f23)));
+        const float2 c = __ffma2_rn(dup(f11), X2, __ffma2_rn(dup(f21), Y2, dup(f31)));
+        const float2 d = __ffma2_rn(dup(f12), X2, __ffma2_rn(dup(f22), Y2, dup(f32)));
+        const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, __ffma2_rn(dup(f31), X1, __ffma2_rn(dup(f32), Y1, dup(f33)))));
         const float2 n2 = __fmul2_rn(n, n);
         const float2 den = __ffma2_rn(d, d, __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a))));
-        t = __ffma2_rn(negthr, den, n2);          // n^2 - thr*den  (< 0 <=> n^2/den < thr, no division)
-        bnd = __ffma2_rn(b1, den, b0);
-        e = make_float2(n2.x * fast_rcp(den.x), n2.y * fast_rcp(den.y));   // only the error sum needs the quotient
+        t = __ffma2_rn(dup(negthr), den, n2);     // n^2 - thr*den  (< 0 <=> n^2/den < thr, no division)
+        s = __ffma2_rn(dup(b1), den, dup(b0));
+        w = make_float2(fast_rcp(den.x), fast_rcp(den.y));                 // only the error sum needs the quotient
     }
-    static __device__ __forceinline__ float finish(float sum) { return sum; }
-    static __device__ __forceinline__ float strict_to_e(float err) { return err; }
+    static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return sum_em + (float)cnt * thr; }
+    static __device__ __forceinline__ float strict_to_em(float err, float thr) { return err - thr; }
 };
 
 template <> struct FastModel<USAC_EST_ESSENTIAL> {
-    float2 e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0;
+    float e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0;
     __device__ __forceinline__ void load(const float* r) {
-        e11 = dup(r[0]); e12 = dup(r[1]); e13 = dup(r[2]); e21 = dup(r[3]); e22 = dup(r[4]); e23 = dup(r[5]);
-        e31 = dup(r[6]); e32 = dup(r[7]); e33 = dup(r[8]);
-        negT = dup(-2.f * r[REC_THR]); ka = dup(r[REC_BAND]); kb = dup(r[REC_BAND + 1]); k0 = dup(r[REC_BAND + 2]);
+        e11 = r[0]; e12 = r[1]; e13 = r[2]; e21 = r[3]; e22 = r[4]; e23 = r[5]; e31 = r[6]; e32 = r[7]; e33 = r[8];
+        negT = -2.f * r[REC_THR]; ka = r[REC_BAND]; kb = r[REC_BAND + 1]; k0 = r[REC_BAND + 2];
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& bnd, float2& e) const {
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
-        const float2 l1 = __ffma2_rn(e11, X2, __ffma2_rn(e21, Y2, e31));
-        const float2 l2 = __ffma2_rn(e12, X2, __ffma2_rn(e22, Y2, e32));
-        const float2 l3 = __ffma2_rn(e13, X2, __ffma2_rn(e23, Y2, e33));
-        const float2 t1 = __ffma2_rn(e11, X1, __ffma2_rn(e12, Y1, e13));
-        const float2 t2 = __ffma2_rn(e21, X1, __ffma2_rn(e22, Y1, e23));
-        const float2 t3 = __ffma2_rn(e31, X1, __ffma2_rn(e32, Y1, e33));
+        const float2 l1 = __ffma2_rn(dup(e11), X2, __ffma2_rn(dup(e21), Y2, dup(e31)));
+        const float2 l2 = __ffma2_rn(dup(e12), X2, __ffma2_rn(dup(e22), Y2, dup(e32)));
+        const float2 l3 = __ffma2_rn(dup(e13), X2, __ffma2_rn(dup(e23), Y2, dup(e33)));
+        const float2 t1 = __ffma2_rn(dup(e11), X1, __ffma2_rn(dup(e12), Y1, dup(e13)));
+        const float2 t2 = __ffma2_rn(dup(e21), X1, __ffma2_rn(dup(e22), Y1, dup(e23)));
+        const float2 t3 = __ffma2_rn(dup(e31), X1, __ffma2_rn(dup(e32), Y1, dup(e33)));
         const float2 a1 = __ffma2_rn(l1, X1, __ffma2_rn(l2, Y1, l3));
         const float2 b1 = __ffma2_rn(t1, X2, __ffma2_rn(t2, Y2, t3));
         const float2 a2 = __ffma2_rn(l2, l2, __fmul2_rn(l1, l1));
         const float2 b2 = __ffma2_rn(t2, t2, __fmul2_rn(t1, t1));
         const float2 ra = make_float2(fast_rsqrt(a2.x), fast_rsqrt(a2.y)), rb = make_float2(fast_rsqrt(b2.x), fast_rsqrt(b2.y));
-        const float2 aa = make_float2(fabsf(a1.x), fabsf(a1.y)), bb = make_float2(fabsf(b1.x), fabsf(b1.y));
-        e = __ffma2_rn(aa, ra, __fmul2_rn(bb, rb));     // 2 * error
-        t = __fadd2_rn(e, negT);
-        bnd = __ffma2_rn(ka, ra, __ffma2_rn(kb, rb, k0));
+        const float2 pa = __fmul2_rn(a1, ra), pb = __fmul2_rn(b1, rb);
+        t = make_float2((fabsf(pa.x) + negT) + fabsf(pb.x), (fabsf(pa.y) + negT) + fabsf(pb.y));   // 2*err - 2*thr
+        s = __ffma2_rn(dup(ka), ra, __ffma2_rn(dup(kb), rb, dup(k0)));
+        w = t;
     }
-    static __device__ __forceinline__ float finish(float sum) { return 0.5f * sum; }
-    static __device__ __forceinline__ float strict_to_e(float err) { return 2.f * err; }
+    static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
+    static __device__ __forceinline__ float strict_to_em(float err, float thr) { return 2.f * err - 2.f * thr; }
 };
 
 template <> struct FastModel<USAC_EST_LINE2D> {
-    float2 a, b, c, negthr, band;
-    __device__ __forceinline__ void load(const float* r) {
-        a = dup(r[0]); b = dup(r[1]); c = dup(r[2]); negthr = dup(-r[REC_THR]); band = dup(r[REC_BAND]);
-    }
+    float a, b, c, negthr, band;
+    __device__ __forceinline__ void load(const float* r) { a = r[0]; b = r[1]; c = r[2]; negthr = -r[REC_THR]; band = r[REC_BAND]; }
     // line pairs are [xa xb ya yb]: one float4 per pair (B unused)
-    __device__ __forceinline__ void eval(const float4 A, const float4, float2& t, float2& bnd, float2& e) const {
+    __device__ __forceinline__ void eval(const float4 A, const float4, float2& t, float2& s, float2& w) const {
         const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w);
-        const float2 v = __ffma2_rn(a, X, __ffma2_rn(b, Y, c));
-        e = make_float2(fabsf(v.x), fabsf(v.y));
-        t = __fadd2_rn(e, negthr);
-        bnd = band;
+        const float2 v = __ffma2_rn(dup(a), X, __ffma2_rn(dup(b), Y, dup(c)));
+        t = make_float2(fabsf(v.x) + negthr, fabsf(v.y) + negthr);
+        s = dup(band);
+        w = t;
     }
-    static __device__ __forceinline__ float finish(float sum) { return sum; }
-    static __device__ __forceinline__ float strict_to_e(float err) { return err; }
+    static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return sum_em + (float)cnt * thr; }
+    static __device__ __forceinline__ float strict_to_em(float err, float thr) { return err - thr; }
 };
 
 struct ScoreArgs {
     const float* pairs;          // pair-interleaved points of all problems
     const float* aos;            // original AoS points (strict re-evaluation reads these)
     const ProblemDesc* prob;
-    const int* active;           // blockIdx.z -> problem id (NULL: identity)
+    const int* active;           // slot -> problem id (NULL: identity)
     const float* recs;           // [slot][mstride][USAC_REC_STRIDE]
     const int* mvalid;           // [slot] models to score (NULL: M for all)
     int M, mstride;              // models per problem (upper bound) and record/partial stride
-    int chunk_pairs, nchunks;    // point pairs per CTA along y
+    int chunk_pairs, nchunks;    // point pairs per work item along the point axis
+    int mblocks, slots;          // work items = slots x nchunks x mblocks (model block fastest: neighbours share points)
     int* part_cnt;               // [slot][nchunks][mstride]
     float* part_sum;
 };
 
-// Slow path of one lane: the reference's exact arithmetic for point `idx` of the problem.
+// Slow path of one lane: the reference's exact arithmetic for point `idx` of the problem. Returns the lane's `em`
+// contribution: negative (its sign bit is the inlier flag) for an inlier, +0 otherwise. Pure, so the hot loop keeps
+// everything in registers.
 template <int EST>
-__device__ __noinline__ void strict_fix(const float* __restrict__ rec, const float* __restrict__ aos, int idx, int n, float thr,
-                                        bool& in, float& e) {
-    if (idx >= n) { in = false; e = 0.f; return; }
+__device__ __noinline__ float strict_em(const float* __restrict__ rec, const float* __restrict__ aos, int idx, int n) {
+    if (idx >= n) return 0.f;
+    const float thr = rec[REC_THR];
     float err;
     if (EST == USAC_EST_LINE2D) {
         const float2 p = reinterpret_cast<const float2*>(aos)[idx];
@@ -188,98 +192,151 @@ __device__ __noinline__ void strict_fix(const float* __restrict__ rec, const flo
         const float4 p = reinterpret_cast<const float4*>(aos)[idx];
         err = strict_error<EST>(rec, p.x, p.y, p.z, p.w);
     }
-    in = err < thr;
-    e = FastModel<EST>::strict_to_e(err);
+    // err < thr  =>  strict_to_em < 0 exactly (2*err and 2*thr are exact, the difference of distinct floats is non-zero)
+    return (err < thr) ? FastModel<EST>::strict_to_em(err, thr) : 0.f;
 }
 
+// Persistent kernel: a CTA loops over work items (slot, point chunk, model block). The points of an item are streamed
+// through a USAC_STAGES-deep ring of shared-memory tiles filled by 1-D bulk async copies (completion on `full` mbarriers).
+// There is no CTA-wide barrier inside an item: the last warp to finish a tile (counted with a shared-memory atomic)
+// re-arms the stage and issues the copy of the tile USAC_STAGES ahead.
 template <int EST>
-__global__ void __launch_bounds__(USAC_SCORE_THREADS) score_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a) {
     constexpr int PAIR_FLOATS = (EST == USAC_EST_LINE2D) ? 4 : 8;
-    constexpr int TILE_BYTES = USAC_TILE_PAIRS * PAIR_FLOATS * 4;
+    constexpr int NWARPS = USAC_SCORE_THREADS / 32;
     __shared__ __align__(128) float tile[USAC_STAGES][USAC_TILE_PAIRS * PAIR_FLOATS];
     __shared__ __align__(8) uint64_t full[USAC_STAGES];
-
-    const int slot = blockIdx.z;
-    const int M = a.mvalid ? a.mvalid[slot] : a.M;
-    if ((int)(blockIdx.x * USAC_SCORE_THREADS) >= M) return;        // uniform per CTA
-    const ProblemDesc pd = a.prob[a.active ? a.active[slot] : slot];
-    const int m = blockIdx.x * USAC_SCORE_THREADS + threadIdx.x;
-    const bool live = m < M;
-    const float* rec = a.recs + ((size_t)slot * a.mstride + (live ? m : 0)) * USAC_REC_STRIDE;
-
-    const int pair_begin = blockIdx.y * a.chunk_pairs;
-    const int pair_end = min(pair_begin + a.chunk_pairs, pd.n_pairs);
-    const int npairs = pair_end - pair_begin;
-    if (npairs <= 0) {                                              // ragged batch: this problem is shorter than the chunk grid
-        if (live) {
-            const size_t o = ((size_t)slot * a.nchunks + blockIdx.y) * a.mstride + m;
-            a.part_cnt[o] = 0;
-            a.part_sum[o] = 0.f;
-        }
-        return;
-    }
-    const int ntiles = (npairs + USAC_TILE_PAIRS - 1) / USAC_TILE_PAIRS;
-    const float* src = a.pairs + ((size_t)pd.pair_off + pair_begin) * PAIR_FLOATS;
+    __shared__ int done[USAC_STAGES];
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < USAC_STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < USAC_STAGES; s++) { mbar_init(&full[s], 1); done[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < USAC_STAGES && s < ntiles; s++) {
-            const int np = min(USAC_TILE_PAIRS, npairs - s * USAC_TILE_PAIRS);
-            const uint32_t bytes = np * PAIR_FLOATS * 4;
-            mbar_expect_tx(&full[s], bytes);
-            bulk_copy_g2s(tile[s], src + (size_t)s * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
+
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)a.slots * a.nchunks * a.mblocks;
+    uint32_t g = 0;                                                  // tiles consumed so far by this CTA (uniform)
+
+    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+        const int mblock = (int)(item % a.mblocks);
+        const long long rest = item / a.mblocks;
+        const int chunk = (int)(rest % a.nchunks), slot = (int)(rest / a.nchunks);
+        const int M = a.mvalid ? a.mvalid[slot] : a.M;
+        if (mblock * USAC_SCORE_THREADS >= M) continue;              // uniform per CTA
+        const ProblemDesc pd = a.prob[a.active ? a.active[slot] : slot];
+        const int m = mblock * USAC_SCORE_THREADS + threadIdx.x;
+        const bool live = m < M;
+        const float* rec = a.recs + ((size_t)slot * a.mstride + (live ? m : 0)) * USAC_REC_STRIDE;
+        const size_t out = ((size_t)slot * a.nchunks + chunk) * a.mstride + m;
+
+        const int pair_begin = chunk * a.chunk_pairs;
+        const int npairs = min(pair_begin + a.chunk_pairs, pd.n_pairs) - pair_begin;
+        if (npairs <= 0) {                                           // ragged batch: this problem is shorter than the chunk grid
+            if (live) { a.part_cnt[out] = 0; a.part_sum[out] = 0.f; }
+            continue;
         }
-    }
+        const int ntiles = (npairs + USAC_TILE_PAIRS - 1) / USAC_TILE_PAIRS;
+        const float* src = a.pairs + ((size_t)pd.pair_off + pair_begin) * PAIR_FLOATS;
 
-    FastModel<EST> fm;
-    fm.load(rec);
-    const float thr = rec[REC_THR];
-    const float* aos = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
-    int cnt = 0;
-    float2 sum = make_float2(0.f, 0.f);
-
-    for (int tI = 0; tI < ntiles; tI++) {
-        const int s = tI % USAC_STAGES;
-        const uint32_t parity = (tI / USAC_STAGES) & 1;
-        mbar_wait(&full[s], parity);
-        const int np = min(USAC_TILE_PAIRS, npairs - tI * USAC_TILE_PAIRS);
-        const float4* tp = reinterpret_cast<const float4*>(tile[s]);
-#pragma unroll 2
-        for (int j = 0; j < np; j++) {
-            float4 A, B;
-            if (EST == USAC_EST_LINE2D) { A = tp[j]; B = A; }
-            else { A = tp[2 * j]; B = tp[2 * j + 1]; }
-            float2 t, bnd, e;
-            fm.eval(A, B, t, bnd, e);
-            bool inx = t.x < 0.f, iny = t.y < 0.f;
-            // "not clearly decided" (also catches NaN): re-evaluate with the reference's arithmetic
-            if (!(fabsf(t.x) > bnd.x) || !(fabsf(t.y) > bnd.y)) {
-                const int idx = 2 * (pair_begin + tI * USAC_TILE_PAIRS + j);
-                if (!(fabsf(t.x) > bnd.x)) strict_fix<EST>(rec, aos, idx, pd.n, thr, inx, e.x);
-                if (!(fabsf(t.y) > bnd.y)) strict_fix<EST>(rec, aos, idx + 1, pd.n, thr, iny, e.y);
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < USAC_STAGES && k < ntiles; k++) {
+                const int s = (g + k) % USAC_STAGES;
+                const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - k * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_copy_g2s(tile[s], src + (size_t)k * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
             }
-            cnt += (int)inx + (int)iny;
-            sum = __fadd2_rn(sum, make_float2(inx ? e.x : 0.f, iny ? e.y : 0.f));
         }
-        __syncthreads();                                   // every warp is done with stage s
-        if (threadIdx.x == 0 && tI + USAC_STAGES < ntiles) {
-            const int nt = tI + USAC_STAGES;
-            const int np2 = min(USAC_TILE_PAIRS, npairs - nt * USAC_TILE_PAIRS);
-            const uint32_t bytes = np2 * PAIR_FLOATS * 4;
-            mbar_expect_tx(&full[s], bytes);
-            bulk_copy_g2s(tile[s], src + (size_t)nt * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
+
+        FastModel<EST> fm;
+        fm.load(rec);
+        const float* aos = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+        unsigned cnt = 0;
+        float2 sum[USAC_PPI];
+#pragma unroll
+        for (int q = 0; q < USAC_PPI; q++) sum[q] = make_float2(0.f, 0.f);
+
+        for (int k = 0; k < ntiles; k++) {
+            const int s = (g + k) % USAC_STAGES;
+            mbar_wait(&full[s], ((g + k) / USAC_STAGES) & 1);
+            const int np = min(USAC_TILE_PAIRS, npairs - k * USAC_TILE_PAIRS);
+            const float4* tp = reinterpret_cast<const float4*>(tile[s]);
+            const int idx0 = 2 * (pair_begin + k * USAC_TILE_PAIRS);
+            // Hot loop with a warp-uniform exit: USAC_PPI pairs (2*USAC_PPI points) per trip, evaluated as independent
+            // instruction streams. When any lane of the warp cannot decide one of them from the fast value the whole
+            // warp leaves the loop, these pairs are redone one by one - undecided lanes re-evaluate with the reference's
+            // arithmetic (a real function call, kept out of the loop body so that it does not clobber the loop's uniform
+            // registers) - and the loop resumes behind them.
+            auto load_pair = [&](int j, float4& A, float4& B) {
+                if (EST == USAC_EST_LINE2D) { A = tp[j]; B = A; }
+                else { A = tp[2 * j]; B = tp[2 * j + 1]; }
+            };
+            int j = 0;
+            while (j < np) {
+#pragma unroll 1
+                for (; j + USAC_PPI <= np; j += USAC_PPI) {
+                    float2 em[USAC_PPI];
+                    bool unsure = false;
+#pragma unroll
+                    for (int q = 0; q < USAC_PPI; q++) {
+                        float4 A, B;
+                        load_pair(j + q, A, B);
+                        float2 t, sb, w;
+                        fm.eval(A, B, t, sb, w);
+                        em[q] = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
+                        if (EST == USAC_EST_FUNDAMENTAL) em[q] = __fmul2_rn(em[q], w);
+                        unsure = unsure || !(fabsf(t.x) > sb.x) || !(fabsf(t.y) > sb.y);   // also catches NaN
+                    }
+                    if (__any_sync(0xffffffffu, unsure)) break;
+#pragma unroll
+                    for (int q = 0; q < USAC_PPI; q++) {
+                        cnt += (__float_as_uint(em[q].x) >> 31) + (__float_as_uint(em[q].y) >> 31);
+                        sum[q] = __fadd2_rn(sum[q], em[q]);
+                    }
+                }
+                const int jend = min(j + USAC_PPI, np);
+#pragma unroll 1
+                for (; j < jend; j++) {
+                    float4 A, B;
+                    load_pair(j, A, B);
+                    float2 t, sb, w;
+                    fm.eval(A, B, t, sb, w);
+                    float2 e1 = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
+                    if (EST == USAC_EST_FUNDAMENTAL) e1 = __fmul2_rn(e1, w);
+                    if (!(fabsf(t.x) > sb.x)) e1.x = strict_em<EST>(rec, aos, idx0 + 2 * j, pd.n);
+                    if (!(fabsf(t.y) > sb.y)) e1.y = strict_em<EST>(rec, aos, idx0 + 2 * j + 1, pd.n);
+                    cnt += (__float_as_uint(e1.x) >> 31) + (__float_as_uint(e1.y) >> 31);
+                    sum[0] = __fadd2_rn(sum[0], e1);
+                }
+            }
+            // release the stage: the last warp to get here re-arms it and fetches the tile USAC_STAGES ahead
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done[s], 1) == NWARPS - 1) {
+                    done[s] = 0;
+                    if (k + USAC_STAGES < ntiles) {
+                        __threadfence_block();
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        const int nk = k + USAC_STAGES;
+                        const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - nk * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
+                        mbar_expect_tx(&full[s], bytes);
+                        bulk_copy_g2s(tile[s], src + (size_t)nk * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
+                    }
+                }
+            }
         }
-    }
-    if (live) {
-        const size_t o = ((size_t)slot * a.nchunks + blockIdx.y) * a.mstride + m;
-        a.part_cnt[o] = cnt;
-        a.part_sum[o] = FastModel<EST>::finish(sum.x + sum.y);
+        g += (uint32_t)ntiles;
+        if (live) {
+            a.part_cnt[out] = (int)cnt;
+            float tot = 0.f;
+#pragma unroll
+            for (int q = 0; q < USAC_PPI; q++) tot += sum[q].x + sum[q].y;
+            a.part_sum[out] = FastModel<EST>::finish(tot, (int)cnt, rec[REC_THR]);
+        }
+        __syncthreads();                                             // every warp left the item: its stages may be refilled
     }
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -51,8 +52,9 @@ struct usac_gpu_ctx {
     DevBuf<long long> d_pair_offs;
     DevBuf<FitState> d_state;
     FitState* h_state = nullptr; size_t h_state_cap = 0;     // pinned
-    DevBuf<int> d_active;
+    DevBuf<int> d_active, d_done;
     int* h_active = nullptr; size_t h_active_cap = 0;        // pinned
+    int* h_done = nullptr;                                   // pinned, same capacity as h_active
     // side structures
     DevBuf<int> d_knn, d_cell_of_point, d_members, d_rank, d_cell_start, d_pool;
     DevBuf<unsigned> d_cursors, d_growth, d_term;
@@ -145,6 +147,8 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
+    if (c->h_done) cudaFreeHost(c->h_done);
+    c->d_done.release();
     for (auto& pr : c->score_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -236,6 +240,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     CUDA_TRY(c, c->d_pair_offs.ensure(P));
     CUDA_TRY(c, c->d_state.ensure(P));
     CUDA_TRY(c, c->d_active.ensure(P));
+    CUDA_TRY(c, c->d_done.ensure(P));
     if (c->h_state_cap < (size_t)P) {
         if (c->h_state) cudaFreeHost(c->h_state);
         CUDA_TRY(c, cudaMallocHost(&c->h_state, sizeof(FitState) * P));
@@ -244,6 +249,8 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     if (c->h_active_cap < (size_t)P) {
         if (c->h_active) cudaFreeHost(c->h_active);
         CUDA_TRY(c, cudaMallocHost(&c->h_active, sizeof(int) * P));
+        if (c->h_done) cudaFreeHost(c->h_done);
+        CUDA_TRY(c, cudaMallocHost(&c->h_done, sizeof(int) * P));
         c->h_active_cap = P;
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->d_aos.p, points, (size_t)aos * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -362,8 +369,10 @@ extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* p
 // ------------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------------------------
-static void launch_score(usac_gpu_ctx* c, const ScoreArgs& a, int slots, int mblocks) {
-    dim3 grid(mblocks, a.nchunks, slots);
+static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
+    a.mblocks = mblocks; a.slots = slots;
+    const long long items = (long long)slots * a.nchunks * mblocks;
+    const unsigned grid = (unsigned)std::min<long long>(items, (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS);
     auto& ev = c->next_score_event();
     cudaEventRecord(ev.first, c->stream);
     switch (c->est) {
@@ -377,13 +386,16 @@ static void launch_score(usac_gpu_ctx* c, const ScoreArgs& a, int slots, int mbl
     c->last_score_launches++;
 }
 
+// Work items of the persistent scoring kernel = slots x mblocks x nchunks; all items cost about the same, so aim at a
+// whole number (>= 2) of items per resident CTA when the model axis alone does not fill the machine.
 static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_pairs, int* chunk_pairs, int* nchunks) {
-    const long long target = 8LL * c->prop.multiProcessorCount;
-    long long want = (target + (long long)slots * mblocks - 1) / ((long long)slots * mblocks);
-    const int max_chunks = std::max(1, max_pairs / (4 * USAC_TILE_PAIRS));
+    const long long ctas = (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS;
+    const long long base = (long long)slots * mblocks;
+    long long want = base >= ctas ? 1 : (2 * ctas + base - 1) / base;
+    const int max_chunks = std::max(1, max_pairs / USAC_TILE_PAIRS);
     int nc = (int)std::min<long long>(std::max<long long>(want, 1), max_chunks);
     int cp = (max_pairs + nc - 1) / nc;
-    cp = ((cp + USAC_TILE_PAIRS - 1) / USAC_TILE_PAIRS) * USAC_TILE_PAIRS;
+    cp = ((cp + 1) / 2) * 2;
     nc = (max_pairs + cp - 1) / cp;
     *chunk_pairs = cp;
     *nchunks = std::max(nc, 1);
@@ -753,8 +765,21 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
     cudaEventRecord(c->ev0, c->stream);
 
+    // Without SPRT and PROSAC the result does not depend on the round size (prefix semantics of select_kernel), so the
+    // round grows as problems finish: the tail of a batch then needs a few large rounds instead of many tiny ones.
+    const char* growth_env = getenv("USAC_GPU_ROUND_GROWTH");      // tuning knob: 0 disables, N caps the growth factor
+    const int growth_cap = growth_env ? atoi(growth_env) : 2;     // measured on C2 x 2368: 2 is the sweet spot
+    const bool k_free = growth_cap > 1 && !cfg->sprt && cfg->sampler.sampler != USAC_SAMPLER_PROSAC && cfg->sampler.rng != USAC_RNG_TABLE;
+    const int K0 = K;
     while (!active.empty()) {
         const int slots = (int)active.size();
+        if (k_free && slots < P) {
+            long long kr = std::min<long long>({2048LL, (long long)P * K0 / slots, (long long)K0 * growth_cap});
+            kr = std::min<long long>(kr, std::max(cfg->max_iterations, 1u));
+            kr = std::max<long long>(K0, kr / 128 * 128);
+            if (nranks > 1) kr = (kr + nranks - 1) / nranks * nranks;
+            K = (int)kr;
+        }
         int max_pairs = 0;
         for (int p : active) max_pairs = std::max(max_pairs, c->h_prob[p].n_pairs);
         const int mblocks = (K * S + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS;
@@ -769,7 +794,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         fill_round_args(c, a, cfg->sampler, K);
         a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
         a.table_rows = cfg->sample_table_rows; a.rank = rank; a.nranks = nranks; a.nchunks = nchunks;
-        a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
+        a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
 
         launch_sampler(c, a, slots);
         switch (c->est) {
@@ -808,13 +833,15 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
             case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
             default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
         }
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState) * P, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the one host sync of the round
+        // the one host sync of the round: one `done` flag per active problem
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_done, c->d_done.p, sizeof(int) * slots, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaGetLastError());
         std::vector<int> next;
-        for (int p : active) if (!c->h_state[p].done) next.push_back(p);
+        for (int q = 0; q < slots; q++) if (!c->h_done[q]) next.push_back(active[q]);
         active.swap(next);
     }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState) * P, cudaMemcpyDeviceToHost, c->stream));
     cudaEventRecord(c->ev1, c->stream);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     collect_timing(c);

@@ -45,19 +45,48 @@ def models_for(est, pts, mask, count, seed):
     return np.stack(out[:count])
 
 
+def errors64(est, pts, model):
+    """The error functions in float64 on the same float32 inputs (homography: with the float32 inverse the reference
+    caches, homography_estimator.hpp:33-45). Used to calibrate tolerances: |float32 reference - this| is the rounding
+    noise the reference's own result carries for that model."""
+    p = np.asarray(pts, np.float64)
+    m = np.asarray(model, np.float64).ravel()
+    with np.errstate(all="ignore"):
+        if est == O.EST_LINE2D:
+            return np.abs(m[0] * p[:, 0] + m[1] * p[:, 1] + m[2])
+        x1, y1, x2, y2 = p.T
+        if est == O.EST_HOMOGRAPHY:
+            g = O.inv3x3(np.asarray(model, np.float32))[0].astype(np.float64).ravel()
+            ez, fz = m[6] * x1 + m[7] * y1 + m[8], g[6] * x2 + g[7] * y2 + g[8]
+            ex, ey = (m[0] * x1 + m[1] * y1 + m[2]) / ez, (m[3] * x1 + m[4] * y1 + m[5]) / ez
+            fx, fy = (g[0] * x2 + g[1] * y2 + g[2]) / fz, (g[3] * x2 + g[4] * y2 + g[5]) / fz
+            return 0.5 * (np.hypot(x2 - ex, y2 - ey) + np.hypot(x1 - fx, y1 - fy))
+        if est == O.EST_FUNDAMENTAL:
+            a, b = m[0] * x1 + m[1] * y1 + m[2], m[3] * x1 + m[4] * y1 + m[5]
+            c, d = m[0] * x2 + m[3] * y2 + m[6], m[1] * x2 + m[4] * y2 + m[7]
+            n = x2 * a + y2 * b + m[6] * x1 + m[7] * y1 + m[8]
+            return n * n / (a * a + b * b + c * c + d * d)
+        l1, l2, l3 = m[0] * x2 + m[3] * y2 + m[6], m[1] * x2 + m[4] * y2 + m[7], m[2] * x2 + m[5] * y2 + m[8]
+        t1, t2, t3 = m[0] * x1 + m[1] * y1 + m[2], m[3] * x1 + m[4] * y1 + m[5], m[6] * x1 + m[7] * y1 + m[8]
+        return 0.5 * (np.abs(l1 * x1 + l2 * y1 + l3) / np.hypot(l1, l2) + np.abs(t1 * x2 + t2 * y2 + t3) / np.hypot(t1, t2))
+
+
 def check_scores(ctx, est, pts, models, thr):
     cnt, s = ctx.score(models, thr)
     flagged_total = 0
     for i, mod in enumerate(models):
-        c_ref, s_ref, flagged = O.score(est, pts, mod, thr)
+        c_ref, s_ref, flagged, ids = O.score(est, pts, mod, thr, want_inliers=True)
         flagged_total += flagged
         assert cnt[i] == c_ref, (i, cnt[i], c_ref, flagged)          # bit-exact, even inside the 1e-6 band
-        # error sum: 1e-4 relative plus the float32 resolution of the coordinates per inlier (a model scored on its own
-        # sample has errors at rounding level, where "relative" is meaningless); MSAC cost: 1e-4 relative (BASELINE.json)
+        # Error sum: 1e-4 relative (BASELINE.json) plus the rounding noise the float32 reference itself carries for this
+        # model - measured as its distance from a float64 evaluation of the same inliers. Ill-conditioned hypotheses
+        # (entries ~1e6 after the h33 = 1 normalisation) have float32 errors that are only good to ~1e-2 px.
+        e32, e64 = O.errors(est, pts, mod)[ids].astype(np.float64), errors64(est, pts, mod)[ids]
+        noise = float(np.abs(e32 - e64).sum()) if c_ref else 0.0
         coord = float(np.abs(pts).max())
-        assert abs(s[i] - s_ref) <= 1e-4 * abs(s_ref) + c_ref * 64 * 2.0 ** -24 * coord, (i, s[i], s_ref)
+        assert abs(s[i] - s_ref) <= 1e-4 * abs(s_ref) + 8 * noise + c_ref * 16 * 2.0 ** -24 * max(coord, thr), (i, s[i], s_ref, noise)
         msac, msac_ref = s[i] + (len(pts) - cnt[i]) * thr, s_ref + (len(pts) - c_ref) * thr
-        assert abs(msac - msac_ref) <= 1e-4 * msac_ref
+        assert abs(msac - msac_ref) <= 1e-4 * msac_ref                # MSAC truncated cost, 1e-4 relative
     return flagged_total
 
 
