@@ -573,7 +573,7 @@ static int ensure_round_buffers(usac_gpu_ctx* c, int slots, int K, int nchunks, 
     return USAC_OK;
 }
 
-static int setup_sampler_side(usac_gpu_ctx* c, const usac_sampler_cfg& s) {
+static int setup_sampler_side(usac_gpu_ctx* c, const usac_sampler_cfg& s, bool reset_cursors = true) {
     if (s.sampler == USAC_SAMPLER_PROSAC) {
         std::vector<unsigned> all, g;
         for (int p = 0; p < c->P; p++) {
@@ -589,7 +589,7 @@ static int setup_sampler_side(usac_gpu_ctx* c, const usac_sampler_cfg& s) {
         for (int p = 0; p < c->P; p++) {
             const ProblemDesc& d = c->h_prob[p];
             if (s.neighbors == USAC_NEIGH_KNN ? d.knn_off < 0 : d.grid_off < 0) return fail(c, USAC_ERR_STATE, "NAPSAC: neighbourhood of a problem was not set");
-            CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off, 0, sizeof(unsigned) * d.n, c->stream));
+            if (reset_cursors) CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off, 0, sizeof(unsigned) * d.n, c->stream));
         }
     }
     return USAC_OK;
@@ -633,7 +633,7 @@ extern "C" int usac_gpu_sample(usac_gpu_ctx* c, int problem, const usac_sampler_
     cudaSetDevice(c->device);
     int rc = ensure_round_buffers(c, 1, K, 1, 1);
     if (rc) return rc;
-    rc = setup_sampler_side(c, *cfg);
+    rc = setup_sampler_side(c, *cfg, first_hyp == 0);   // NAPSAC cursors persist across calls that continue a stream
     if (rc) return rc;
     rc = push_desc(c);
     if (rc) return rc;

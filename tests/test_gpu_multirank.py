@@ -1,0 +1,100 @@
+"""Hypothesis sharding (usac_fit_cfg.rank / nranks): results must be identical on every rank and identical to one GPU.
+(1) two ranks emulated on ONE GPU: two host threads, two contexts, the per-round exchange done by a host hook installed with
+    usac_gpu_set_allgather (device->host, thread barrier, host->device);
+(2) real NCCL over NVLink, one process per GPU under torchrun (skipped with fewer than 2 GPUs)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from ransac_b200 import generator as gen
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cudart():
+    for name in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so.12", "libcudart.so"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    pytest.skip("libcudart not found")
+
+
+class HostExchange:
+    """usac_allgather_fn for R ranks living in R threads of this process."""
+    def __init__(self, world):
+        from ransac_b200 import capi
+        self.world, self.rt = world, _cudart()
+        self.rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        self.rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+        self.barrier = threading.Barrier(world)
+        self.parts = [None] * world
+        self.calls = 0
+        self.fns = [capi.ALLGATHER_FN(self._make(r)) for r in range(world)]
+
+    def _make(self, rank):
+        def hook(user, d_send, d_recv, nbytes, stream):
+            assert self.rt.cudaStreamSynchronize(stream) == 0
+            buf = (C.c_ubyte * nbytes)()
+            assert self.rt.cudaMemcpy(buf, d_send, nbytes, 2) == 0            # device -> host
+            self.parts[rank] = bytes(buf)
+            self.barrier.wait()
+            allb = b"".join(self.parts)
+            assert self.rt.cudaMemcpy(d_recv, allb, len(allb), 1) == 0        # host -> device
+            self.barrier.wait()
+            if rank == 0:
+                self.calls += 1
+            return 0
+        return hook
+
+
+@pytest.mark.parametrize("cfg,world", [(2, 2), (2, 4), (3, 2)])
+def test_emulated_ranks_match_single_gpu_and_oracle(cfg, world):
+    from ransac_b200 import GpuContext
+    est = {2: O.EST_HOMOGRAPHY, 3: O.EST_FUNDAMENTAL}[cfg]
+    pts = gen.make(cfg, n=3000)[0]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    ex = HostExchange(world)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            ctx = GpuContext(0)
+            ctx.set_points(est, pts)
+            ctx._check(ctx.L.usac_gpu_set_allgather(ctx.h, ex.fns[rank], None), "set_allgather")
+            results[rank] = ctx.fit(thr, conf, 3000, seed=6, round_size=128, rank=rank, nranks=world)[0]
+            ctx.close()
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+            ex.barrier.abort()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    assert ex.calls >= 1
+    ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=3000, seed=6)
+    for r in results:
+        for k in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+            assert r[k] == ref[k] == results[0][k], (k, r[k], ref[k])
+        assert np.array_equal(r["model"].view(np.uint32), np.asarray(ref["model"], np.float32).view(np.uint32))
+    assert sum(r["useful_evals"] for r in results) == ref["evals"]           # the shards partition the sequential work
+
+
+def test_nccl_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:]

@@ -1,0 +1,90 @@
+"""The C++ host layer (ransac_b200/usac/): the reference's plugin surface re-authored over the C ABI, and its harness.
+CPU part: it builds, and refuses to run without a GPU (exit code 111 like the reference's fatal paths, no CPU fallback).
+GPU part: fused Ransac::run() == one-hypothesis-at-a-time run_sequential() over the virtual plugins == the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+USAC = os.path.join(ROOT, "ransac_b200", "usac")
+HARNESS = os.path.join(USAC, "usac_harness")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    from ransac_b200 import build
+    build.build()
+    subprocess.check_call(["make", "-s", "-C", USAC])
+    return HARNESS
+
+
+def write_points(path, pts):
+    with open(path, "w") as fh:
+        fh.write(f"{len(pts)}\n")
+        for row in pts:
+            fh.write(" ".join(f"{v:.9g}" for v in row) + "\n")
+
+
+def test_harness_builds_and_has_no_cpu_fallback(harness, tmp_path):
+    import torch
+    assert subprocess.run([harness, "--help"], stderr=subprocess.PIPE).returncode == 0
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = tmp_path / "p.txt"
+    write_points(p, np.arange(32, dtype=np.float32).reshape(8, 4))
+    r = subprocess.run([harness, str(p), "homography", "uniform", "2", "0.95"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 111 and "no CPU fallback" in r.stderr
+
+
+def test_plugin_headers_keep_the_reference_signatures():
+    text = open(os.path.join(USAC, "plugin.hpp")).read()
+    for sig in ("virtual unsigned int EstimateModel(const int* const sample, std::vector<Model*>& models) = 0;",
+                "virtual float GetError(unsigned int pidx) = 0;", "virtual int SampleNumber() = 0;",
+                "virtual void setModelParameters(const cv::Mat& model) = 0;", "virtual void generateSample(int* sample) = 0;",
+                "virtual unsigned int getUpBoundIterations(unsigned int inlier_size) = 0;",
+                "virtual void GetModelScore(Model* best_model, Score* best_score) = 0;"):
+        assert sig in text, sig
+
+
+def parse(out):
+    res = {}
+    for line in out.splitlines():
+        tag, *kv = line.split()
+        d = dict(x.split("=") for x in kv)
+        res[tag] = {"iterations": int(d["iterations"]), "inliers": int(d["inliers"]), "hash": d["inlier_hash"], "score": float(d["score"]),
+                    "model": np.array([int(x, 16) for x in d["model_bits"].split(",")], np.uint32)}
+    return res
+
+
+def fnv(ids):
+    h = 1469598103934665603
+    for i in ids:
+        h = ((h ^ int(i)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,est_name,sampler", [(1, "line2d", "uniform"), (2, "homography", "uniform"), (3, "fundamental", "uniform"),
+                                                    (2, "homography", "napsac")])
+def test_fused_equals_sequential_equals_oracle(harness, tmp_path, cfg, est_name, sampler):
+    from oracle import oracle as O
+    from ransac_b200 import generator as gen
+    est = {"line2d": O.EST_LINE2D, "homography": O.EST_HOMOGRAPHY, "fundamental": O.EST_FUNDAMENTAL}[est_name]
+    n = {1: 1000, 2: 1500, 3: 1200}[cfg]
+    pts = gen.make(cfg, n=n, clustered=True)[0] if sampler == "napsac" else gen.make(cfg, n=n)[0]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    p = tmp_path / "p.txt"
+    write_points(p, pts)
+    r = subprocess.run([harness, str(p), est_name, sampler, repr(thr), repr(conf), "5", "--both"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    got = parse(r.stdout)
+    f, s = got["fused"], got["sequential"]
+    assert f["iterations"] == s["iterations"] and f["inliers"] == s["inliers"] and f["hash"] == s["hash"]
+    assert np.array_equal(f["model"], s["model"])
+    kw = dict(sampler=O.SAMPLER_NAPSAC, neighbors=O.NEIGH_GRID, cell_size=50) if sampler == "napsac" else {}
+    ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, seed=5, **kw)
+    assert f["iterations"] == ref["iterations"] and f["inliers"] == ref["inliers"]
+    assert np.array_equal(f["model"], np.asarray(ref["model"], np.float32).view(np.uint32))
+    assert f["hash"] == fnv(O.score(est, pts, ref["model"], thr, want_inliers=True)[3])
