@@ -35,7 +35,10 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct SideUsed { size_t knn = 0, grid = 0, cell_start = 0, cursors = 0, pool = 0; };   // elements used in the appended side arrays
+
 struct usac_gpu_ctx {
+    SideUsed side;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -233,6 +236,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     }
     c->total_points = aos; c->total_pairs = pairs;
     c->h_pool_set.assign(P, 0);
+    c->side = SideUsed();                 // neighbourhoods / pools belong to the previous point sets
     const size_t pair_floats = (dim == 4) ? 8 : 4;
     CUDA_TRY(c, c->d_aos.ensure((size_t)aos * dim));
     CUDA_TRY(c, c->d_pairs.ensure((size_t)pairs * pair_floats));
@@ -299,13 +303,11 @@ static cudaError_t append_segment(DevBuf<T>& buf, size_t& used, const T* host, s
     return e;
 }
 
-struct SideUsed { size_t knn = 0, grid = 0, cell_start = 0, cursors = 0, pool = 0; };
-static std::map<usac_gpu_ctx*, SideUsed> g_side;   // bookkeeping of appended segments per context
 
 extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const int* neighbors, int k) {
     if (!c || problem < 0 || problem >= c->P || !neighbors || k < 1) return fail(c, USAC_ERR_ARG, "set_neighbors_knn: bad arguments");
     cudaSetDevice(c->device);
-    SideUsed& u = g_side[c];
+    SideUsed& u = c->side;
     ProblemDesc& d = c->h_prob[problem];
     CUDA_TRY(c, append_segment(c->d_knn, u.knn, neighbors, (size_t)d.n * k, &d.knn_off, c->stream));
     if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)d.n, &d.cursor_off, c->stream));
@@ -342,7 +344,7 @@ extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cel
     }
     cell_start.push_back(n);
     cell_start.resize(n + 1, n);
-    SideUsed& u = g_side[c];
+    SideUsed& u = c->side;
     size_t g0 = u.grid, g1 = u.grid, g2 = u.grid;
     long long o0, o1, o2;
     CUDA_TRY(c, append_segment(c->d_cell_of_point, g0, cell.data(), (size_t)n, &o0, c->stream));
@@ -359,7 +361,7 @@ extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cel
 extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* pool) {
     if (!c || problem < 0 || problem >= c->P || !pool) return fail(c, USAC_ERR_ARG, "set_sprt_pool: bad arguments");
     cudaSetDevice(c->device);
-    SideUsed& u = g_side[c];
+    SideUsed& u = c->side;
     ProblemDesc& d = c->h_prob[problem];
     CUDA_TRY(c, append_segment(c->d_pool, u.pool, pool, (size_t)d.n, &d.pool_off, c->stream));
     c->h_pool_set[problem] = 1;
