@@ -99,29 +99,45 @@ __device__ __forceinline__ void cv_inv3x3(const float* m, float* out) {
 // Minimal solvers (one thread per sample). Operation order is the contract of DESIGN.md S1-S4.
 // ---------------------------------------------------------------------------------------------------------------
 
-// Gauss-Jordan with partial (row) pivoting on a ROWS x 9 double system held in local memory. Rows are addressed
-// through a permutation instead of being swapped (same arithmetic). On success row perm[k] is the k-th reduced row:
-// unit in column k, zero in the other pivot columns, entries of the free columns ROWS..8 valid.
+// Gauss-Jordan with partial (row) pivoting on a ROWS x 9 double system held in REGISTERS: every loop is fully unrolled so
+// that all indices are compile-time constants, and the pivot row is brought into place by predicated swaps (only columns
+// >= k are live). The matrix is passed as two arrays (rows 0..3 and 4..ROWS-1): nvcc keeps a local array in registers only
+// up to ~300 bytes, a single 8x9 double array stays in local memory (measured: 720-byte stack frame, 3x slower kernel).
+// Same operations in the same order as the host restatement used by the parity tests: pivot = first row r >= k
+// maximising |A[r][k]|; scale row k by 1/pivot; A[r][j] -= A[r][k]*A[k][j] (product rounded, then difference rounded).
+// On success row k is the k-th reduced row: the entries of the free columns ROWS..8 are valid.
+#define GJ_AT(r, j) (*((r) < 4 ? &T[(r)][(j)] : &B[(r) - 4][(j)]))
 template <int ROWS>
-__device__ bool gauss_jordan9(double (*A)[9], int* perm) {
-#pragma unroll 1
+__device__ __forceinline__ bool gauss_jordan9(double (&T)[4][9], double (&B)[ROWS - 4][9]) {
+#pragma unroll
     for (int k = 0; k < ROWS; k++) {
         int piv = k;
-        double best = fabs(A[perm[k]][k]);
+        double best = fabs(GJ_AT(k, k));
+#pragma unroll
         for (int r = k + 1; r < ROWS; r++) {
-            const double v = fabs(A[perm[r]][k]);
+            const double v = fabs(GJ_AT(r, k));
             if (v > best) { best = v; piv = r; }
         }
         if (!(best > 0.0) || !dfinite(best)) return false;
-        const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
-        double* rowk = A[perm[k]];
-        const sd inv = sd(1.0) / sd(rowk[k]);
-        for (int j = k + 1; j < 9; j++) rowk[j] = (sd(rowk[j]) * inv).v;
+#pragma unroll
+        for (int r = k + 1; r < ROWS; r++) {
+            const bool sw = piv == r;
+#pragma unroll
+            for (int j = k; j < 9; j++) {
+                const double a = GJ_AT(k, j), b = GJ_AT(r, j);
+                GJ_AT(k, j) = sw ? b : a;
+                GJ_AT(r, j) = sw ? a : b;
+            }
+        }
+        const sd inv = sd(1.0) / sd(GJ_AT(k, k));
+#pragma unroll
+        for (int j = k + 1; j < 9; j++) GJ_AT(k, j) = (sd(GJ_AT(k, j)) * inv).v;
+#pragma unroll
         for (int r = 0; r < ROWS; r++) {
             if (r == k) continue;
-            double* row = A[perm[r]];
-            const sd f(row[k]);
-            for (int j = k + 1; j < 9; j++) row[j] = (sd(row[j]) - f * sd(rowk[j])).v;
+            const sd f(GJ_AT(r, k));
+#pragma unroll
+            for (int j = k + 1; j < 9; j++) GJ_AT(r, j) = (sd(GJ_AT(r, j)) - f * sd(GJ_AT(k, j))).v;
         }
     }
     return true;
@@ -162,22 +178,21 @@ __device__ int solve_homography4(const float* __restrict__ pts, const int* s, fl
     const float s2 = (float)(sd(SQRT2) / sd((double)(d2 / sf(4.f)).v)).v;
     const float t1x = (-m1x * sf(s1)).v, t1y = (-m1y * sf(s1)).v, t2x = (-m2x * sf(s2)).v, t2y = (-m2y * sf(s2)).v;
 
-    double A[8][9];
-    int perm[8];
+    double T[4][9], B[4][9];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const sd x1 = sd((double)s1) * sd((double)p[i].x) + sd((double)t1x), y1 = sd((double)s1) * sd((double)p[i].y) + sd((double)t1y);
         const sd x2 = sd((double)s2) * sd((double)p[i].z) + sd((double)t2x), y2 = sd((double)s2) * sd((double)p[i].w) + sd((double)t2y);
-        double* r0 = A[2 * i];
-        double* r1 = A[2 * i + 1];
-        r0[0] = -x1.v; r0[1] = -y1.v; r0[2] = -1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = (x2 * x1).v; r0[7] = (x2 * y1).v; r0[8] = x2.v;
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = -x1.v; r1[4] = -y1.v; r1[5] = -1; r1[6] = (y2 * x1).v; r1[7] = (y2 * y1).v; r1[8] = y2.v;
-        perm[2 * i] = 2 * i; perm[2 * i + 1] = 2 * i + 1;
+        const int a = 2 * i, b = 2 * i + 1;
+        GJ_AT(a, 0) = -x1.v; GJ_AT(a, 1) = -y1.v; GJ_AT(a, 2) = -1; GJ_AT(a, 3) = 0; GJ_AT(a, 4) = 0; GJ_AT(a, 5) = 0;
+        GJ_AT(a, 6) = (x2 * x1).v; GJ_AT(a, 7) = (x2 * y1).v; GJ_AT(a, 8) = x2.v;
+        GJ_AT(b, 0) = 0; GJ_AT(b, 1) = 0; GJ_AT(b, 2) = 0; GJ_AT(b, 3) = -x1.v; GJ_AT(b, 4) = -y1.v; GJ_AT(b, 5) = -1;
+        GJ_AT(b, 6) = (y2 * x1).v; GJ_AT(b, 7) = (y2 * y1).v; GJ_AT(b, 8) = y2.v;
     }
-    if (!gauss_jordan9<8>(A, perm)) return 0;
+    if (!gauss_jordan9<8>(T, B)) return 0;
     sd h[9];
 #pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = -sd(A[perm[i]][8]);
+    for (int i = 0; i < 8; i++) h[i] = -sd(GJ_AT(i, 8));
     h[8] = sd(1.0);
     sd M[9];
 #pragma unroll
@@ -303,21 +318,18 @@ __device__ bool fundamental_is_valid(const float4* p, const float* F) {
 // Seven-point algorithm (seven_points.cpp:49-156) + validity filter (fundamental_estimator.hpp:48-63). DESIGN.md S3.
 __device__ int solve_fundamental7(const float* __restrict__ pts, const int* s, float* out) {
     float4 p[7];
-    double A[7][9];
-    int perm[7];
+    double T[4][9], B[3][9];
 #pragma unroll
     for (int i = 0; i < 7; i++) {
         p[i] = reinterpret_cast<const float4*>(pts)[s[i]];
         const sd x1((double)p[i].x), y1((double)p[i].y), x2((double)p[i].z), y2((double)p[i].w);
-        double* r = A[i];
-        r[0] = (x2 * x1).v; r[1] = (x2 * y1).v; r[2] = x2.v; r[3] = (y2 * x1).v; r[4] = (y2 * y1).v; r[5] = y2.v;
-        r[6] = x1.v; r[7] = y1.v; r[8] = 1;
-        perm[i] = i;
+        GJ_AT(i, 0) = (x2 * x1).v; GJ_AT(i, 1) = (x2 * y1).v; GJ_AT(i, 2) = x2.v; GJ_AT(i, 3) = (y2 * x1).v; GJ_AT(i, 4) = (y2 * y1).v;
+        GJ_AT(i, 5) = y2.v; GJ_AT(i, 6) = x1.v; GJ_AT(i, 7) = y1.v; GJ_AT(i, 8) = 1;
     }
-    if (!gauss_jordan9<7>(A, perm)) return 0;
+    if (!gauss_jordan9<7>(T, B)) return 0;
     sd f1[9], f2[9];
 #pragma unroll
-    for (int i = 0; i < 7; i++) { f2[i] = -sd(A[perm[i]][8]); f1[i] = -sd(A[perm[i]][7]) - f2[i]; }
+    for (int i = 0; i < 7; i++) { f2[i] = -sd(GJ_AT(i, 8)); f1[i] = -sd(GJ_AT(i, 7)) - f2[i]; }
     f2[7] = sd(0.0); f2[8] = sd(1.0);
     f1[7] = sd(1.0) - f2[7]; f1[8] = sd(0.0) - f2[8];
 
