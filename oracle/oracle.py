@@ -86,6 +86,8 @@ def lib():
         L.orc_grid_cells.argtypes = [fp, C.c_int, C.c_int, ip, ip, ip, ip]
         L.orc_ransac.argtypes = [C.POINTER(Config), fp, C.c_int, C.POINTER(Result)]
         L.orc_ransac.restype = C.c_int
+        L.orc_sprt_pool.argtypes = [C.c_uint64, C.c_int, ip]
+        L.orc_sprt_pool.restype = None
         _lib = L
     return _lib
 
@@ -224,6 +226,12 @@ class Sampler:
             self.L.orc_sampler_free(self.h)
         except Exception:
             pass
+
+
+def sprt_pool(seed, n):
+    out = np.empty(n, np.int32)
+    lib().orc_sprt_pool(seed, n, _i(out))
+    return out
 
 
 def ransac(points, est, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, threshold=2.0, confidence=0.95, max_iterations=10000,

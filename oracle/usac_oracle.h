@@ -103,6 +103,8 @@ typedef struct {
 } orc_result;
 
 int orc_ransac(const orc_config* cfg, const float* points, int n, orc_result* out);
+/* the SPRT pool permutation orc_ransac uses for this seed (sprt.hpp:93-107) */
+void orc_sprt_pool(uint64_t seed, int n, int* pool_out);
 
 #ifdef __cplusplus
 }

@@ -260,6 +260,16 @@ inline bool bigger(int inl_a, float sc_a, int inl_b, float sc_b) {   /* Score::b
  *   model, delta from the pooled rejected models) and the cursor advances by 32*K*S. Without SPRT and PROSAC the
  *   result is identical to batch==0 for every K.
  * ------------------------------------------------------------------------------------------------------ */
+/* The SPRT point pool (sprt.hpp:93-107) a fit with this seed uses: Fisher-Yates over the sampler's glibc stream. Exposed so
+ * that the tests can hand the identical pool to the CUDA path (usac_gpu_set_sprt_pool). */
+extern "C" void orc_sprt_pool(uint64_t seed, int n, int* pool_out) {
+    orc_sampler* sampler = orc_sampler_new(ORC_SAMPLER_UNIFORM, ORC_RNG_PHILOX, n, 2, seed);
+    Sprt sprt;
+    sprt.init(ORC_EST_HOMOGRAPHY, 1.f, (unsigned)n, 2, 1, [&]() { return orc_sampler_glibc_next(sampler); });
+    for (int i = 0; i < n; i++) pool_out[i] = (int)sprt.pool[i];
+    orc_sampler_free(sampler);
+}
+
 extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc_result* out) {
     const int est = cfg->estimator;
     const int m = est == ORC_EST_LINE2D ? 2 : est == ORC_EST_HOMOGRAPHY ? 4 : est == ORC_EST_FUNDAMENTAL ? 7 : 5;

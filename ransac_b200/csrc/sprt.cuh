@@ -1,6 +1,15 @@
 // sprt.cuh - Wald SPRT verification (usac/sprt.hpp) on the device.
+//
+// sprt_walk_kernel: one thread per model of the round walks the shuffled point pool (sprt.hpp:93-107; the points are stored
+// once in pool order, so the walk is a contiguous stream) from its start offset (cursor + 32*q) mod N, updating the
+// likelihood ratio lambda in double exactly as sprt.hpp:205-234 does (lambda *= delta/eps for an inlier, (1-delta)/(1-eps)
+// otherwise; reject when lambda > A), under the test (eps, delta, A) frozen for the round. Errors come from the packed fast
+// evaluator with the same guard band + strict re-evaluation as the scoring kernel, so every inlier decision - hence
+// tested_pts / tested_inl - is bit-exact. Models rejected during the first 20 hypotheses finish counting their inliers
+// (sprt.hpp:243-257).
 #pragma once
 #include "pipeline.cuh"
+#include "score.cuh"
 
 struct SprtModelResult { int good, tested_inl, tested_pts, full_inl; };
 
@@ -12,6 +21,116 @@ __host__ inline void sprt_init_state(FitState& s, int est) {
     s.sprt_A = 0; s.sprt_cursor = 0; s.sprt_last_update = 0; s.sprt_ntests = 0;
 }
 
-static void launch_sprt(int est, const RoundArgs& a, int slots, cudaStream_t stream) {
-    (void)est; (void)a; (void)slots; (void)stream;
+// pool-ordered copy of the points: dst[i] = aos[pool[i]]
+__global__ void pool_gather_kernel(const float* __restrict__ aos, const int* __restrict__ pool, int n, int dim, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int src = pool[i];
+    if (dim == 4) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(aos)[src];
+    else reinterpret_cast<float2*>(dst)[i] = reinterpret_cast<const float2*>(aos)[src];
+}
+
+template <int EST>
+struct PoolPoint {
+    float4 v;
+    __device__ __forceinline__ void load(const float* __restrict__ P, int i) {
+        if (EST == USAC_EST_LINE2D) { const float2 p = reinterpret_cast<const float2*>(P)[i]; v = make_float4(p.x, p.y, 0.f, 0.f); }
+        else v = reinterpret_cast<const float4*>(P)[i];
+    }
+};
+
+// inlier decisions of two pool points (positions i0, i1) for one model: fast value, strict when undecided
+template <int EST>
+__device__ __forceinline__ void decide_pair(const FastModel<EST>& fm, const float* __restrict__ rec, const float* __restrict__ P, int n,
+                                            const PoolPoint<EST>& a, const PoolPoint<EST>& b, int i0, int i1, bool& in0, bool& in1) {
+    float4 A, B;
+    if (EST == USAC_EST_LINE2D) { A = make_float4(a.v.x, b.v.x, a.v.y, b.v.y); B = A; }
+    else { A = make_float4(a.v.x, b.v.x, a.v.y, b.v.y); B = make_float4(a.v.z, b.v.z, a.v.w, b.v.w); }
+    float2 t, s, w;
+    fm.eval(A, B, t, s, w);
+    in0 = t.x < 0.f; in1 = t.y < 0.f;
+    if (!(fabsf(t.x) > s.x)) in0 = __float_as_uint(strict_em<EST>(rec, P, i0, n)) >> 31;
+    if (!(fabsf(t.y) > s.y)) in1 = __float_as_uint(strict_em<EST>(rec, P, i1, n)) >> 31;
+}
+
+template <int EST>
+__global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const float* __restrict__ pool_pts) {
+    const int slot = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.K * a.S) return;
+    const int j = q / a.S, i = q % a.S;
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const FitState& st = a.state[pid];
+    SprtModelResult res = {0, 0, 0, 0};
+    SprtModelResult* out = a.sprt_res + (size_t)slot * a.mstride + q;
+    if (i >= a.nmodels[(size_t)slot * a.K + j]) { *out = res; return; }
+    const float* rec = a.recs + ((size_t)slot * a.mstride + a.offsets[(size_t)slot * a.K + j] + i) * USAC_REC_STRIDE;
+    FastModel<EST> fm;
+    fm.load(rec);
+    const int n = pd.n;
+    const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+    const double eps = st.sprt_eps, delta = st.sprt_delta, A = st.sprt_A;
+    const double r_in = __ddiv_rn(delta, eps), r_out = __ddiv_rn(__dsub_rn(1.0, delta), __dsub_rn(1.0, eps));
+    auto wrap = [n](int v) { return v >= n ? v - n : v; };
+    int idx = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q) % (unsigned long long)n);
+    double lambda = 1.0;
+    int tp = 0, tin = 0;
+    bool good = true;
+    PoolPoint<EST> pa, pb, na, nb;
+    pa.load(P, idx); pb.load(P, wrap(idx + 1));
+#pragma unroll 1
+    while (tp < n) {
+        const int i0 = idx, i1 = wrap(idx + 1);
+        na.load(P, wrap(idx + 2)); nb.load(P, wrap(idx + 3));          // next pair in flight while this one is evaluated
+        bool in0, in1;
+        decide_pair<EST>(fm, rec, P, n, pa, pb, i0, i1, in0, in1);
+        double ln = __dmul_rn(lambda, in0 ? r_in : r_out);
+        tin += in0; tp++;
+        if (ln > A) { good = false; break; }
+        lambda = ln;
+        if (tp >= n) break;
+        ln = __dmul_rn(lambda, in1 ? r_in : r_out);
+        tin += in1; tp++;
+        if (ln > A) { good = false; break; }
+        lambda = ln;
+        pa = na; pb = nb; idx = wrap(idx + 2);
+    }
+    res.good = good; res.tested_inl = tin; res.tested_pts = tp; res.full_inl = tin;
+    if (!good && (unsigned long long)st.samples_drawn + (unsigned long long)j < 20ull) {
+        // sprt.hpp:243-257: keep counting from the point after the rejecting one
+        int pos = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q + (unsigned long long)tp) % (unsigned long long)n);
+        int rest = n - tp, c = 0;
+#pragma unroll 1
+        while (rest > 0) {
+            const int i0 = pos, i1 = wrap(pos + 1);
+            pa.load(P, i0); pb.load(P, i1);
+            bool in0, in1;
+            decide_pair<EST>(fm, rec, P, n, pa, pb, i0, i1, in0, in1);
+            c += in0; rest--;
+            if (rest > 0) { c += in1; rest--; }
+            pos = wrap(pos + 2);
+        }
+        res.full_inl = tin + c;
+    }
+    *out = res;
+}
+
+// per-model (count, sum) of a fully scored round, in (sample, root) slot order q = j*S + i (count -1 = no such model):
+// the input of the host replay used with PROSAC termination
+__global__ void model_scores_kernel(const RoundArgs a, int2* __restrict__ out) {
+    const int slot = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.K * a.S) return;
+    const int j = q / a.S, i = q % a.S;
+    int c = -1;
+    float s = 0.f;
+    if (i < a.nmodels[(size_t)slot * a.K + j]) {
+        const int off = a.offsets[(size_t)slot * a.K + j] + i;
+        c = 0;
+        for (int ch = 0; ch < a.nchunks; ch++) {
+            const size_t o = ((size_t)slot * a.nchunks + ch) * a.mstride + off;
+            c += a.part_cnt[o];
+            s += a.part_sum[o];
+        }
+    }
+    out[(size_t)slot * a.mstride + q] = make_int2(c, __float_as_int(s));
 }

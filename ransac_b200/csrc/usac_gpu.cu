@@ -16,6 +16,7 @@
 #include "pipeline.cuh"
 #include "score.cuh"
 #include "sprt.cuh"
+#include "host_replay.hpp"
 
 // ------------------------------------------------------------------------------------------------------------------
 // context
@@ -67,6 +68,8 @@ struct usac_gpu_ctx {
     DevBuf<float> d_models_raw, d_recs, d_part_sum;
     DevBuf<uint2> d_scores, d_scores_all;
     DevBuf<SprtModelResult> d_sprt_res;
+    DevBuf<int2> d_model_scores;
+    DevBuf<float> d_pool_pts;          // the points in SPRT pool order (same offsets as d_aos)
     // scoring API buffers
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
     DevBuf<int> d_q_cnt, d_q_ids;
@@ -146,7 +149,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -363,7 +366,13 @@ extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* p
     cudaSetDevice(c->device);
     SideUsed& u = c->side;
     ProblemDesc& d = c->h_prob[problem];
+    for (int i = 0; i < d.n; i++) if (pool[i] < 0 || pool[i] >= d.n) return fail(c, USAC_ERR_ARG, "set_sprt_pool: index out of range");
     CUDA_TRY(c, append_segment(c->d_pool, u.pool, pool, (size_t)d.n, &d.pool_off, c->stream));
+    const int dim = usac_point_dim(c->est);
+    CUDA_TRY(c, c->d_pool_pts.ensure((size_t)c->total_points * dim));
+    pool_gather_kernel<<<(d.n + 255) / 256, 256, 0, c->stream>>>(c->d_aos.p + (size_t)d.aos_off * dim, c->d_pool.p + d.pool_off, d.n, dim,
+                                                                  c->d_pool_pts.p + (size_t)d.aos_off * dim);
+    CUDA_TRY(c, cudaGetLastError());
     c->h_pool_set[problem] = 1;
     return push_desc(c);
 }
@@ -713,6 +722,192 @@ static void launch_winner_est(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
     c->last_launches++;
 }
 
+// inlier mask of one model over the points in their given (quality-sorted) order: Quality::getInliers -> bytes
+static int fetch_mask(usac_gpu_ctx* c, int problem, const float* model, float thr, std::vector<unsigned char>& mask, std::vector<int>& ids) {
+    const ProblemDesc& d = c->h_prob[problem];
+    const int dim = usac_point_dim(c->est);
+    int rc = upload_one_record(c, problem, model, thr);
+    if (rc) return rc;
+    CUDA_TRY(c, c->d_q_ids.ensure((size_t)d.n + 1));
+    const float* aos = c->d_aos.p + (size_t)d.aos_off * dim;
+    int* cnt = c->d_q_ids.p + d.n;
+    switch (c->est) {
+        case USAC_EST_LINE2D: inliers_kernel<USAC_EST_LINE2D><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, thr, c->d_q_ids.p, cnt); break;
+        case USAC_EST_HOMOGRAPHY: inliers_kernel<USAC_EST_HOMOGRAPHY><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, thr, c->d_q_ids.p, cnt); break;
+        case USAC_EST_FUNDAMENTAL: inliers_kernel<USAC_EST_FUNDAMENTAL><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, thr, c->d_q_ids.p, cnt); break;
+        default: inliers_kernel<USAC_EST_ESSENTIAL><<<1, 1024, 0, c->stream>>>(aos, d.n, c->d_q_recs.p, thr, c->d_q_ids.p, cnt); break;
+    }
+    c->last_launches += 2;
+    ids.resize((size_t)d.n + 1);
+    CUDA_TRY(c, cudaMemcpyAsync(ids.data(), c->d_q_ids.p, sizeof(int) * ((size_t)d.n + 1), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    mask.assign((size_t)d.n, 0);
+    for (int i = 0; i < ids[d.n]; i++) mask[ids[i]] = 1;
+    return USAC_OK;
+}
+
+template <int EST>
+static void launch_solve(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+    dim3 gs((a.K + 63) / 64, slots);
+    solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    c->last_launches++;
+}
+template <int EST>
+static void launch_walk(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+    dim3 g((a.K * a.S + 63) / 64, slots);
+    sprt_walk_kernel<EST><<<g, 64, 0, c->stream>>>(a, c->d_pool_pts.p);
+    c->last_launches++;
+}
+
+// Rounds with SPRT and/or PROSAC termination (host_replay.hpp): device = sample, solve, verify/score; host = replay.
+static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results, int K) {
+    const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    const bool is_prosac = cfg->sampler.sampler == USAC_SAMPLER_PROSAC, is_sprt = cfg->sprt != 0;
+    const float log_1_p = (float)logf(1 - cfg->confidence);
+    const int KS = K * S;
+    std::vector<int> h_nmodels(K), ids;
+    std::vector<SprtModelResult> h_res(KS);
+    std::vector<int2> h_scores(KS);
+    std::vector<float> h_models((size_t)KS * 9);
+    std::vector<unsigned char> mask;
+    std::vector<unsigned> growth;
+    int rc = ensure_round_buffers(c, 1, K, 1, 1);
+    if (rc) return rc;
+    CUDA_TRY(c, c->d_model_scores.ensure(KS));
+
+    for (int p = 0; p < P; p++) {
+        const ProblemDesc& pd = c->h_prob[p];
+        const unsigned n = (unsigned)pd.n;
+        FitState& hs = c->h_state[p];
+        init_state(hs, pd, c->est, cfg->max_iterations, 0);
+        SprtHost sprt;
+        ProsacTermHost pterm;
+        if (is_sprt) sprt.init(c->est, n, (unsigned)m, cfg->max_iterations);
+        if (is_prosac) { prosac_growth(n, (unsigned)m, growth); pterm.init(growth, n, (unsigned)m, cfg->confidence, cfg->max_iterations); }
+        bool done = false;
+        while (!done && hs.iters < hs.max_iters) {
+            if (is_prosac) hs.prosac_term_len = pterm.termination_length;
+            if (is_sprt) { const SprtTestH& t = sprt.current(); hs.sprt_eps = t.epsilon; hs.sprt_delta = t.delta; hs.sprt_A = t.A; hs.sprt_cursor = sprt.cursor; }
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p + p, &hs, sizeof(FitState), cudaMemcpyHostToDevice, c->stream));
+            c->h_active[0] = p;
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            int chunk_pairs = pd.n_pairs, nchunks = 1;
+            const int mblocks = (KS + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS;
+            if (!is_sprt) {
+                plan_chunks(c, 1, mblocks, pd.n_pairs, &chunk_pairs, &nchunks);
+                rc = ensure_round_buffers(c, 1, K, nchunks, 1);
+                if (rc) return rc;
+            }
+            RoundArgs a;
+            fill_round_args(c, a, cfg->sampler, K);
+            a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
+            a.table_rows = cfg->sample_table_rows; a.nchunks = nchunks; a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
+            launch_sampler(c, a, 1);
+            switch (c->est) {
+                case USAC_EST_LINE2D: launch_solve<USAC_EST_LINE2D>(c, a, 1); break;
+                case USAC_EST_HOMOGRAPHY: launch_solve<USAC_EST_HOMOGRAPHY>(c, a, 1); break;
+                case USAC_EST_FUNDAMENTAL: launch_solve<USAC_EST_FUNDAMENTAL>(c, a, 1); break;
+                default: launch_solve<USAC_EST_ESSENTIAL>(c, a, 1); break;
+            }
+            prepare_kernel<<<1, 256, 0, c->stream>>>(a);
+            c->last_launches++;
+            if (is_sprt) {
+                switch (c->est) {
+                    case USAC_EST_LINE2D: launch_walk<USAC_EST_LINE2D>(c, a, 1); break;
+                    case USAC_EST_HOMOGRAPHY: launch_walk<USAC_EST_HOMOGRAPHY>(c, a, 1); break;
+                    case USAC_EST_FUNDAMENTAL: launch_walk<USAC_EST_FUNDAMENTAL>(c, a, 1); break;
+                    default: launch_walk<USAC_EST_ESSENTIAL>(c, a, 1); break;
+                }
+                CUDA_TRY(c, cudaMemcpyAsync(h_res.data(), c->d_sprt_res.p, sizeof(SprtModelResult) * KS, cudaMemcpyDeviceToHost, c->stream));
+            } else {
+                ScoreArgs sa;
+                sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
+                sa.mvalid = c->d_mvalid.p; sa.M = KS; sa.mstride = KS; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
+                sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
+                launch_score(c, sa, 1, mblocks);
+                model_scores_kernel<<<dim3((KS + 127) / 128, 1), 128, 0, c->stream>>>(a, c->d_model_scores.p);
+                c->last_launches++;
+                CUDA_TRY(c, cudaMemcpyAsync(h_scores.data(), c->d_model_scores.p, sizeof(int2) * KS, cudaMemcpyDeviceToHost, c->stream));
+            }
+            FitState dev_state;
+            CUDA_TRY(c, cudaMemcpyAsync(h_nmodels.data(), c->d_nmodels.p, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(h_models.data(), c->d_models_raw.p, sizeof(float) * KS * 9, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(&dev_state, c->d_state.p + p, sizeof(FitState), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the host sync of the round
+            CUDA_TRY(c, cudaGetLastError());
+
+            // ---- replay the round in hypothesis order (ransac.cpp:58-139) ----
+            const unsigned long long hyp0 = hs.samples_drawn;
+            const unsigned iters_round_start = hs.iters;
+            long long last_improving = -1;
+            unsigned long long rej_inl = 0, rej_pts = 0, evals = 0, useful = 0;
+            bool stopped = false;
+            for (int j = 0; j < K; j++) {
+                if (!stopped && !(hs.iters < hs.max_iters)) { stopped = true; done = true; }
+                for (int i = 0; i < h_nmodels[j]; i++) {
+                    const int q = j * S + i;
+                    unsigned long long cost;
+                    if (is_sprt) cost = (unsigned long long)h_res[q].tested_pts + ((!h_res[q].good && hyp0 + j < 20) ? (unsigned long long)(n - h_res[q].tested_pts) : 0ull);
+                    else cost = n;
+                    evals += cost;
+                    if (stopped) continue;
+                    useful += cost;
+                    int inl;
+                    float score;
+                    if (is_sprt) {
+                        const SprtModelResult& r = h_res[q];
+                        if (r.good) { if (r.tested_inl > hs.best_cnt) last_improving = r.tested_inl; }
+                        else { rej_inl += (unsigned long long)r.tested_inl; rej_pts += (unsigned long long)r.tested_pts; }
+                        if (!r.good && hs.iters >= 20) { hs.iters++; continue; }       // ransac.cpp:77-85
+                        inl = r.full_inl; score = (float)inl;                           // sprt.hpp:240-241
+                    } else {
+                        inl = h_scores[q].x; memcpy(&score, &h_scores[q].y, 4);
+                    }
+                    if (inl > hs.best_cnt || (inl == hs.best_cnt && score > hs.best_sum)) {   // Score::bigger
+                        hs.best_cnt = inl; hs.best_sum = score; hs.best_hyp = (long long)(hyp0 + j); hs.best_midx = i;
+                        for (int k = 0; k < w; k++) hs.best_model[k] = h_models[(size_t)q * 9 + k];
+                        if (is_prosac) {                                                 // ransac.cpp:123-125
+                            rc = fetch_mask(c, p, hs.best_model, cfg->threshold, mask, ids);
+                            if (rc) return rc;
+                            hs.max_iters = pterm.update(hs.iters, mask, dev_state.prosac_largest_next);
+                        } else {
+                            hs.max_iters = standard_termination_value((unsigned)inl, n, m, log_1_p, cfg->max_iterations);
+                        }
+                        if (is_sprt) hs.max_iters = std::min(hs.max_iters, sprt.upper_bound(inl));   // ransac.cpp:129-133
+                    }
+                }
+                if (!stopped) hs.iters++;
+            }
+            if (is_sprt) {                                       // one re-design per round (state is frozen within a round)
+                const SprtTestH t = sprt.current();
+                double eps = t.epsilon, delta = t.delta;
+                bool redesign = false;
+                if (last_improving >= 0) { eps = (float)last_improving / n; redesign = true; }
+                if (rej_pts > 0) {
+                    const float delta_estimated = (float)rej_inl / (unsigned)rej_pts;
+                    if (delta_estimated > 0 && std::fabs(t.delta - delta_estimated) / t.delta > 0.05) { delta = delta_estimated; redesign = true; }
+                }
+                if (redesign) sprt.push(eps, delta, (int)iters_round_start);
+                sprt.cursor = (unsigned)(((unsigned long long)sprt.cursor + 32ull * (unsigned long long)KS) % n);
+                hs.sprt_ntests = (int)sprt.hist.size();
+            }
+            hs.prosac_t = dev_state.prosac_t_next; hs.prosac_n = dev_state.prosac_n_next; hs.prosac_largest = dev_state.prosac_largest_next;
+            hs.prosac_t_next = hs.prosac_t; hs.prosac_n_next = hs.prosac_n; hs.prosac_largest_next = hs.prosac_largest;
+            hs.samples_drawn += (unsigned)K;
+            hs.rounds++;
+            hs.evals += evals;
+            hs.useful_evals += useful;
+        }
+        hs.done = 1;
+        usac_fit_result& r = results[p];
+        memset(&r, 0, sizeof(r));
+        for (int i = 0; i < w; i++) r.model[i] = hs.best_model[i];
+        r.inliers = hs.best_cnt; r.score = hs.best_sum; r.iterations = hs.iters; r.samples_drawn = hs.samples_drawn;
+        r.best_hyp = hs.best_hyp; r.best_model_idx = hs.best_midx; r.rounds = hs.rounds; r.evals = hs.evals; r.useful_evals = hs.useful_evals;
+    }
+    return USAC_OK;
+}
+
 extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results) {
     if (!c || !cfg || !results) return fail(c, USAC_ERR_ARG, "fit: bad arguments");
     if (c->P <= 0) return fail(c, USAC_ERR_STATE, "fit: no points uploaded");
@@ -721,7 +916,8 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     if (rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "fit: rank out of range");
     if (nranks > 1 && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_nccl_init or usac_gpu_set_allgather");
     if (cfg->sampler.rng == USAC_RNG_TABLE && (!cfg->sample_table || cfg->sample_table_rows == 0)) return fail(c, USAC_ERR_ARG, "fit: empty sample table");
-    if (cfg->sprt && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT with hypothesis sharding is not supported");
+    const bool host_replay = cfg->sprt || cfg->sampler.sampler == USAC_SAMPLER_PROSAC;
+    if (host_replay && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT / PROSAC termination with hypothesis sharding is not supported");
     cudaSetDevice(c->device);
     const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est);
     int max_n = 0;
@@ -758,6 +954,15 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     if (cfg->sampler.rng == USAC_RNG_TABLE) {
         CUDA_TRY(c, c->d_table.ensure((size_t)cfg->sample_table_rows * m));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_table.p, cfg->sample_table, sizeof(int) * (size_t)cfg->sample_table_rows * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (host_replay) {
+        c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
+        cudaEventRecord(c->ev0, c->stream);
+        rc = fit_host_replay(c, cfg, results, K);
+        cudaEventRecord(c->ev1, c->stream);
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        collect_timing(c);
+        return rc;
     }
     for (int p = 0; p < P; p++) init_state(c->h_state[p], c->h_prob[p], c->est, cfg->max_iterations, 0);
     CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof(FitState) * P, cudaMemcpyHostToDevice, c->stream));
@@ -807,10 +1012,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         }
         prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
         c->last_launches++;
-        if (cfg->sprt) {
-            launch_sprt(c->est, a, slots, c->stream);
-            c->last_launches += 2;
-        } else {
+        {
             ScoreArgs sa;
             sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
             sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;

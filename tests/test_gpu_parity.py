@@ -298,3 +298,43 @@ def test_full_size_properties_1m(ctx):
     many = np.repeat(models, 40, axis=0)                              # 280 models: several CTAs along x, many chunks
     cm, _ = ctx.score(many, 2.0)
     assert np.array_equal(cm, np.repeat(c2, 40))
+
+
+# ---- SPRT and PROSAC termination (device verification + host replay) ------------------------------
+def assert_fit_equal_sprt(r, ref):
+    for key in ("inliers", "iterations", "best_hyp", "best_model_idx", "samples_drawn", "evals"):
+        assert r[key] == ref[key], (key, r[key], ref[key])
+    assert np.array_equal(bits(r["model"]), bits(ref["model"]))
+    assert r["score"] == ref["score"]                                 # under SPRT the score is the inlier count (sprt.hpp:240-241)
+
+
+@pytest.mark.parametrize("cfg,K,max_it", [(1, 64, 2000), (2, 128, 10000), (2, 512, 10000), (3, 128, 1500)])
+def test_fit_sprt_matches_oracle(ctx, cfg, K, max_it):
+    pts, gt, mask = gen.make(cfg) if cfg != 3 else gen.make(cfg, n=4000)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    ctx.set_points(est, pts)
+    for seed in (1, 2):
+        ctx.set_sprt_pool(0, O.sprt_pool(seed, len(pts)))
+        r = ctx.fit(thr, conf, max_it, seed=seed, round_size=K, sprt=True)[0]
+        ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=max_it, seed=seed, sprt=True, batch=K)
+        assert_fit_equal_sprt(r, ref)
+
+
+@pytest.mark.parametrize("sprt", [False, True])
+def test_fit_prosac_termination_matches_oracle(ctx, sprt):
+    """BASELINE config 3: fundamental, PROSAC sampler (+ SPRT) on quality-sorted correspondences."""
+    from ransac_b200.api import SAMPLER_PROSAC
+    pts, gt, mask = gen.make(3, n=5000)
+    thr, conf, K, max_it = 2.0, 0.95, 128, 3000
+    ctx.set_points(O.EST_FUNDAMENTAL, pts)
+    for seed in (1, 4):
+        if sprt:
+            ctx.set_sprt_pool(0, O.sprt_pool(seed, len(pts)))
+        r = ctx.fit(thr, conf, max_it, sampler=SAMPLER_PROSAC, seed=seed, round_size=K, sprt=sprt)[0]
+        ref = O.ransac(pts, O.EST_FUNDAMENTAL, sampler=O.SAMPLER_PROSAC, rng=O.RNG_PHILOX, threshold=thr, confidence=conf,
+                       max_iterations=max_it, seed=seed, sprt=sprt, batch=K)
+        for key in ("inliers", "iterations", "best_hyp", "best_model_idx", "samples_drawn"):
+            assert r[key] == ref[key], (key, r[key], ref[key], seed)
+        assert np.array_equal(bits(r["model"]), bits(ref["model"]))
+        assert r["iterations"] < max_it                               # the PROSAC criterion did stop the run early
