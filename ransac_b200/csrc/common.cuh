@@ -10,10 +10,10 @@
 #define USAC_STAGES 4               // bulk-copy pipeline depth of the scoring kernel
 #define USAC_SCORE_THREADS 128      // models per scoring CTA
 #ifndef USAC_SCORE_MIN_CTAS
-#define USAC_SCORE_MIN_CTAS 8        // resident scoring CTAs per SM (8 -> <= 64 registers per thread)
+#define USAC_SCORE_MIN_CTAS 5        // resident scoring CTAs per SM (5 -> <= 102 registers per thread; measured best with USAC_PPI 4)
 #endif
 #ifndef USAC_PPI
-#define USAC_PPI 2                  // point pairs per trip of the scoring loop (independent instruction streams)
+#define USAC_PPI 4                  // point pairs per trip of the scoring loop (independent instruction streams)
 #endif
 
 // Prepared-model record (one per valid model, written by prepare_kernel, read by the scoring kernels):

@@ -397,14 +397,26 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     c->last_score_launches++;
 }
 
-// Work items of the persistent scoring kernel = slots x mblocks x nchunks; all items cost about the same, so aim at a
-// whole number (>= 2) of items per resident CTA when the model axis alone does not fill the machine.
+// Work items of the persistent scoring kernel = slots x mblocks x nchunks, all of about the same cost, handed to
+// SMs x USAC_SCORE_MIN_CTAS resident CTAs round-robin. The point axis is split (a) to fill the machine when the model
+// axis alone cannot and (b) so that the items divide evenly over the CTAs (2368 items on 740 CTAs would cost 4 item
+// times instead of 3.2; 5 chunks each make it 16 exactly).
 static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_pairs, int* chunk_pairs, int* nchunks) {
     const long long ctas = (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS;
     const long long base = (long long)slots * mblocks;
-    long long want = base >= ctas ? 1 : (2 * ctas + base - 1) / base;
     const int max_chunks = std::max(1, max_pairs / USAC_TILE_PAIRS);
-    int nc = (int)std::min<long long>(std::max<long long>(want, 1), max_chunks);
+    int nc;
+    if (base < ctas) {
+        nc = (int)std::min<long long>((2 * ctas + base - 1) / base, max_chunks);
+    } else {
+        nc = 1;
+        double best = 1e30;
+        for (int t = 1; t <= std::min(8, std::max(1, max_pairs / (4 * USAC_TILE_PAIRS))); t++) {
+            const long long items = base * t;
+            const double waste = (double)((items + ctas - 1) / ctas * ctas) / (double)items;
+            if (waste < best - 1e-3) { best = waste; nc = t; }
+        }
+    }
     int cp = (max_pairs + nc - 1) / nc;
     cp = ((cp + 1) / 2) * 2;
     nc = (max_pairs + cp - 1) / cp;

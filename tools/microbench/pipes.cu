@@ -10,9 +10,9 @@ constexpr int ITERS = 4096;
 template<int MODE>
 __global__ void __launch_bounds__(256) bench(float* out, long long* cycles, float seed) {
     float a[8], b = seed, c = seed * 0.5f;
-    float2 p[8]; double d[4];
+    float2 p[8], q[8], r[8]; double d[4];
     #pragma unroll
-    for (int i = 0; i < 8; i++) { a[i] = seed + i + threadIdx.x; p[i] = make_float2(a[i], a[i] + 1.f); }
+    for (int i = 0; i < 8; i++) { a[i] = seed + i + threadIdx.x; p[i] = make_float2(a[i], a[i] + 1.f); q[i] = make_float2(0.999f + 1e-6f * a[i], 0.998f); r[i] = make_float2(1e-3f * a[i], 2e-3f); }
     #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = seed + i;
     float2 b2 = make_float2(b, b), c2 = make_float2(c, c);
@@ -48,6 +48,15 @@ __global__ void __launch_bounds__(256) bench(float* out, long long* cycles, floa
             #pragma unroll
             for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], b, c);
             asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(p[0].x));
+        } else if (MODE == 9) {     // FFMA2 with three distinct vector operands
+            #pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], q[i], r[i]);
+        } else if (MODE == 10) {    // FFMA2 with two vector operands + one scalar
+            #pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], q[i], c2);
+        } else if (MODE == 11) {    // FMUL2 two vector operands
+            #pragma unroll
+            for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], q[i]);
         } else if (MODE == 8) {     // 8 FFMA2 + 8 scalar FFMA
             #pragma unroll
             for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], b2, c2);
@@ -58,7 +67,7 @@ __global__ void __launch_bounds__(256) bench(float* out, long long* cycles, floa
     long long t1 = clock64();
     float s = 0;
     #pragma unroll
-    for (int i = 0; i < 8; i++) s += a[i] + p[i].x + p[i].y;
+    for (int i = 0; i < 8; i++) s += a[i] + p[i].x + p[i].y + q[i].x + r[i].y;
     #pragma unroll
     for (int i = 0; i < 4; i++) s += (float)d[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
@@ -90,7 +99,7 @@ int main() {
     printf("device %s sms=%d clock=%d kHz\n", pr.name, sms, pr.clockRate);
     float* out; long long* cyc;
     CHK(cudaMalloc(&out, sizeof(float) * 4096 * 256)); CHK(cudaMalloc(&cyc, sizeof(long long) * 4096));
-    for (int c : {1, 2, 4, 8}) {
+    for (int c : {1, 2, 4}) {
         run<0>("FFMA x8", 8, c, sms, out, cyc);
         run<1>("FFMA2 x8 (16 lane-fma)", 16, c, sms, out, cyc);
         run<2>("MUFU.RCP x8", 8, c, sms, out, cyc);
@@ -100,6 +109,9 @@ int main() {
         run<6>("8 FFMA + ~24 ALU (8 fma)", 8, c, sms, out, cyc);
         run<7>("8 FFMA + 1 MUFU (9)", 9, c, sms, out, cyc);
         run<8>("8 FFMA2 + 8 FFMA (24)", 24, c, sms, out, cyc);
+        run<9>("FFMA2 3 vector operands", 16, c, sms, out, cyc);
+        run<10>("FFMA2 2 vector + scalar", 16, c, sms, out, cyc);
+        run<11>("FMUL2 2 vector", 16, c, sms, out, cyc);
     }
     return 0;
 }
