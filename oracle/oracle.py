@@ -86,6 +86,8 @@ def lib():
         L.orc_grid_cells.argtypes = [fp, C.c_int, C.c_int, ip, ip, ip, ip]
         L.orc_ransac.argtypes = [C.POINTER(Config), fp, C.c_int, C.POINTER(Result)]
         L.orc_ransac.restype = C.c_int
+        L.orc_essential5_candidates.argtypes = [fp, ip, dp, ip]
+        L.orc_essential5_candidates.restype = C.c_int
         L.orc_sprt_pool.argtypes = [C.c_uint64, C.c_int, ip]
         L.orc_sprt_pool.restype = None
         _lib = L
@@ -156,6 +158,16 @@ def solve_minimal(est, points, sample):
     k = lib().orc_solve_minimal(est, _f(p), _i(s), _f(out))
     w = 3 if est == EST_LINE2D else 9
     return out[:k * w].reshape(k, w).copy() if est != EST_LINE2D else out[:3 * k].reshape(k, 3).copy()
+
+
+def essential5_candidates(points, sample):
+    """-> (E [k,3,3] float64, valid [k] bool) in the solver's visiting order"""
+    p, _ = _pts(points)
+    s = np.ascontiguousarray(sample, dtype=np.int32)
+    Es = np.zeros(90, np.float64)
+    valid = np.zeros(10, np.int32)
+    k = lib().orc_essential5_candidates(_f(p), _i(s), Es.ctypes.data_as(C.POINTER(C.c_double)), _i(valid))
+    return Es[:9 * k].reshape(k, 3, 3).copy(), valid[:k].astype(bool)
 
 
 def solve_cubic(c):

@@ -55,6 +55,9 @@ int orc_solve_cubic(const double c[4], double roots[3]);       /* c0 x^3 + c1 x^
 int orc_fundamental_is_valid(const float* points, const float* F, const int* sample);
 int orc_null_space(double* A, int rows, double* basis_out);    /* A rows x 9 row-major, destroyed; basis (9-rows) x 9 */
 
+/* five-point candidates in visiting order (ascending |z|): Es_out[10*9] doubles, valid_out[10] = passed the cheirality vote */
+int orc_essential5_candidates(const float* points, const int* sample, double* Es_out, int* valid_out);
+
 /* ---- samplers ---- */
 typedef struct orc_sampler orc_sampler;
 orc_sampler* orc_sampler_new(int kind, int rng, int n, int m, uint64_t seed);

@@ -1,8 +1,357 @@
-// essential.cuh - five-point essential-matrix solver (EssentialEstimator::EstimateModel, essential_estimator.hpp:52-62).
+// essential.cuh - five-point essential-matrix solver, one thread per sample, double precision, strict IEEE arithmetic.
+//
+// Replaces EssentialEstimator::EstimateModel -> EssentialSolver::FivePoints -> Solve5PointEssential
+// (essential_estimator.hpp:52-62, essential/five_points.cpp:13-274): 5x9 design matrix (:48-63), 4-D null space
+// E = x*B0 + y*B1 + z*B2 + B3 (:65-105), the ten cubic constraints 2EE'E - tr(EE')E = 0, det E = 0 as a 10x10 matrix M(z) over
+// [x^3 y^3 x^2y xy^2 x^2 y^2 xy x y 1] (essential/mblock.hpp), det M(z) by interpolation (:117-138), its real roots
+// (:140-157), per root the null vector of M(z) -> x, y -> E (:181-204) and the cheirality vote of the five points over the
+// four (R, t) decompositions (:206-252); 0 or 1 model, cast to float (:28).
+//
+// Deterministic choices where the reference depends on cv::SVD / Jenkins-Traub internals: null
+// spaces by Gauss-Jordan with partial pivoting, made orthonormal by modified Gram-Schmidt; two interpolations on 11 nodes
+// in [-1, 1] (p(z) for |z| <= 1.05, the reversed polynomial for the rest) by Newton divided differences; real roots by
+// derivative bracketing + bisection, visited by ascending |z|; eight Gauss-Newton steps on the ten constraints per root;
+// closed-form (R, t) = (cof(E) -/+ [t]x E, +/-t) and least-squares depths for the vote. Operation order is a contract with
+// the host restatement used by the parity tests: the models are bit-identical.
 #pragma once
 #include "strict_math.cuh"
 
-__device__ int solve_essential5(const float* __restrict__ pts, const int* s, float* out) {
-    (void)pts; (void)s; (void)out;
-    return 0;   // built in a later milestone (essential row)
+namespace e5 {
+
+__device__ __constant__ signed char MONO[20][3] = {{3, 0, 0}, {0, 3, 0}, {2, 1, 0}, {1, 2, 0}, {2, 0, 0}, {2, 0, 1}, {0, 2, 0}, {0, 2, 1}, {1, 1, 0}, {1, 1, 1},
+                                                   {1, 0, 0}, {1, 0, 1}, {1, 0, 2}, {0, 1, 0}, {0, 1, 1}, {0, 1, 2}, {0, 0, 0}, {0, 0, 1}, {0, 0, 2}, {0, 0, 3}};
+__device__ __constant__ signed char COL_FIRST[10] = {0, 1, 2, 3, 4, 6, 8, 10, 13, 16};
+__device__ __constant__ signed char COL_DEG[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
+__device__ __constant__ signed char LL[4][4] = {{0, 3, 4, 6}, {3, 1, 5, 7}, {4, 5, 2, 8}, {6, 7, 8, 9}};                 // linear x linear -> quadratic
+__device__ __constant__ signed char QL[10][4] = {{0, 2, 5, 4}, {3, 1, 7, 6}, {12, 15, 19, 18}, {2, 3, 9, 8}, {5, 9, 12, 11},
+                                                 {9, 7, 15, 14}, {4, 8, 11, 10}, {8, 6, 14, 13}, {11, 14, 18, 17}, {10, 13, 17, 16}};   // quadratic x linear -> cubic
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ void acc_ll(double* q, const double* a, const double* b, double s) {
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) { const int k = LL[i][j]; q[k] = add(q[k], mul(mul(a[i], b[j]), s)); }
+}
+__device__ void acc_ql(double* c, const double* q, const double* l, double s) {
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 4; j++) { const int k = QL[i][j]; c[k] = add(c[k], mul(mul(q[i], l[j]), s)); }
+}
+
+__device__ double det_lu(double* a, int n) {
+    double det = 1.0;
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double best = fabs(a[k * n + k]);
+        for (int r = k + 1; r < n; r++) { const double v = fabs(a[r * n + k]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0)) return 0.0;
+        if (piv != k) { for (int j = 0; j < n; j++) { const double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t; } det = -det; }
+        det = mul(det, a[k * n + k]);
+        const double inv = dvd(1.0, a[k * n + k]);
+        for (int r = k + 1; r < n; r++) {
+            const double f = mul(a[r * n + k], inv);
+            for (int j = k + 1; j < n; j++) a[r * n + j] = sub(a[r * n + j], mul(f, a[k * n + j]));
+        }
+    }
+    return det;
+}
+
+__device__ double horner(const double* c, int deg, double x) {
+    double v = c[deg];
+    for (int i = deg - 1; i >= 0; i--) v = add(mul(v, x), c[i]);
+    return v;
+}
+__device__ double horner_rev(const double* c, int deg, double w) {
+    double v = c[0];
+    for (int i = 1; i <= deg; i++) v = add(mul(v, w), c[i]);
+    return v;
+}
+
+__device__ double bisect(const double* c, int deg, double l, double r, double pl) {
+    if (pl == 0.0) return l;
+    const bool neg_left = pl < 0.0;
+    for (int it = 0; it < 200; it++) {
+        const double m = mul(0.5, add(l, r));
+        if (m == l || m == r) break;
+        const double pm = horner(c, deg, m);
+        if (pm == 0.0) return m;
+        if ((pm < 0.0) == neg_left) l = m; else r = m;
+    }
+    return mul(0.5, add(l, r));
+}
+
+__device__ int real_roots(const double* c, int deg, double* roots) {
+    if (deg < 1) return 0;
+    double bound = 0.0;
+    for (int i = 0; i < deg; i++) { const double v = fabs(dvd(c[i], c[deg])); if (v > bound) bound = v; }
+    bound = add(bound, 1.0);
+    if (!(bound < 1e300)) return 0;
+    double der[11][11];
+    for (int i = 0; i <= deg; i++) der[deg][i] = c[i];
+    for (int d = deg; d > 1; d--)
+        for (int i = 0; i < d; i++) der[d - 1][i] = mul(der[d][i + 1], (double)(i + 1));
+    double prev[11], cur[11];
+    int nprev = 1;
+    prev[0] = -dvd(der[1][0], der[1][1]);
+    if (!(fabs(prev[0]) <= bound)) nprev = 0;
+    for (int d = 2; d <= deg; d++) {
+        const double* p = der[d];
+        int ncur = 0;
+        double left = -bound, pl = horner(p, d, left);
+        for (int s = 0; s <= nprev; s++) {
+            const double right = s < nprev ? prev[s] : bound;
+            const double pr = horner(p, d, right);
+            if (pl == 0.0) { cur[ncur++] = left; }
+            else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { cur[ncur++] = bisect(p, d, left, right, pl); }
+            left = right; pl = pr;
+        }
+        if (pl == 0.0) cur[ncur++] = left;
+        for (int i = 0; i < ncur; i++) prev[i] = cur[i];
+        nprev = ncur;
+    }
+    for (int i = 0; i < nprev; i++) roots[i] = prev[i];
+    return nprev;
+}
+
+// Gauss-Jordan null space of the 5 x 9 design matrix (rows x 9, row-major, destroyed): same operations as gauss_jordan9
+// and as the host restatement; basis vector q has v[5+q] = 1, v[i<5] = -A[i][5+q].
+__device__ bool null_space5(double* A, double* basis) {
+    for (int k = 0; k < 5; k++) {
+        int piv = k;
+        double best = fabs(A[k * 9 + k]);
+        for (int r = k + 1; r < 5; r++) { const double v = fabs(A[r * 9 + k]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0) || !dfinite(best)) return false;
+        if (piv != k) for (int j = 0; j < 9; j++) { const double t = A[k * 9 + j]; A[k * 9 + j] = A[piv * 9 + j]; A[piv * 9 + j] = t; }
+        const double inv = dvd(1.0, A[k * 9 + k]);
+        for (int j = k + 1; j < 9; j++) A[k * 9 + j] = mul(A[k * 9 + j], inv);
+        for (int r = 0; r < 5; r++) {
+            if (r == k) continue;
+            const double f = A[r * 9 + k];
+            for (int j = k + 1; j < 9; j++) A[r * 9 + j] = sub(A[r * 9 + j], mul(f, A[k * 9 + j]));
+        }
+    }
+    for (int q = 0; q < 4; q++) {
+        double* v = basis + q * 9;
+        for (int i = 0; i < 5; i++) v[i] = -A[i * 9 + 5 + q];
+        for (int i = 5; i < 9; i++) v[i] = (i == 5 + q) ? 1.0 : 0.0;
+    }
+    return true;
+}
+
+}  // namespace e5
+
+__device__ __noinline__ int solve_essential5(const float* __restrict__ pts, const int* s, float* out) {
+    using namespace e5;
+    double x1[5], y1[5], x2[5], y2[5], A[45];
+    for (int i = 0; i < 5; i++) {
+        const float4 p = reinterpret_cast<const float4*>(pts)[s[i]];
+        x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w;
+        double* r = A + 9 * i;
+        r[0] = mul(x1[i], x2[i]); r[1] = mul(x2[i], y1[i]); r[2] = x2[i]; r[3] = mul(x1[i], y2[i]); r[4] = mul(y1[i], y2[i]); r[5] = y2[i];
+        r[6] = x1[i]; r[7] = y1[i]; r[8] = 1.0;
+    }
+    double Bs[36];
+    if (!null_space5(A, Bs)) return 0;
+    for (int a = 3; a >= 0; a--) {                                        // modified Gram-Schmidt, last vector first
+        double* v = Bs + 9 * a;
+        for (int b = 3; b > a; b--) {
+            const double* u = Bs + 9 * b;
+            double dot = 0.0;
+            for (int e = 0; e < 9; e++) dot = add(dot, mul(v[e], u[e]));
+            for (int e = 0; e < 9; e++) v[e] = sub(v[e], mul(dot, u[e]));
+        }
+        double nn = 0.0;
+        for (int e = 0; e < 9; e++) nn = add(nn, mul(v[e], v[e]));
+        if (!(nn > 0.0)) return 0;
+        const double inv = dvd(1.0, __dsqrt_rn(nn));
+        for (int e = 0; e < 9; e++) v[e] = mul(v[e], inv);
+    }
+    double L[9][4];
+    for (int e = 0; e < 9; e++) for (int q = 0; q < 4; q++) L[e][q] = Bs[q * 9 + e];
+    double C[10][20];
+    for (int r = 0; r < 10; r++) for (int m = 0; m < 20; m++) C[r][m] = 0.0;
+    {
+        double Q[3][3][10];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int m = 0; m < 10; m++) Q[i][j][m] = 0.0;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) acc_ll(Q[i][j], L[3 * i + k], L[3 * j + k], 1.0);
+        double tr[10];
+        for (int m = 0; m < 10; m++) tr[m] = add(add(Q[0][0][m], Q[1][1][m]), Q[2][2][m]);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double* c = C[3 * i + j];
+                for (int k = 0; k < 3; k++) acc_ql(c, Q[i][k], L[3 * k + j], 2.0);
+                acc_ql(c, tr, L[3 * i + j], -1.0);
+            }
+        double m0[10], m1[10], m2[10];
+        for (int m = 0; m < 10; m++) { m0[m] = 0.0; m1[m] = 0.0; m2[m] = 0.0; }
+        acc_ll(m0, L[4], L[8], 1.0); acc_ll(m0, L[5], L[7], -1.0);
+        acc_ll(m1, L[3], L[8], 1.0); acc_ll(m1, L[5], L[6], -1.0);
+        acc_ll(m2, L[3], L[7], 1.0); acc_ll(m2, L[4], L[6], -1.0);
+        acc_ql(C[9], m0, L[0], 1.0); acc_ql(C[9], m1, L[1], -1.0); acc_ql(C[9], m2, L[2], 1.0);
+    }
+    double roots[20];
+    int nroots = 0;
+    double Mz[100];
+    for (int pass = 0; pass < 2; pass++) {
+        double zs[11], dd[11];
+        for (int t = 0; t < 11; t++) {
+            const double z = dvd((double)(t - 5), 5.0);
+            for (int r = 0; r < 10; r++)
+                for (int c = 0; c < 10; c++)
+                    Mz[r * 10 + c] = pass == 0 ? horner(&C[r][COL_FIRST[c]], COL_DEG[c], z) : horner_rev(&C[r][COL_FIRST[c]], COL_DEG[c], z);
+            zs[t] = z;
+            dd[t] = det_lu(Mz, 10);
+        }
+        for (int lev = 1; lev < 11; lev++)
+            for (int t = 10; t >= lev; t--) dd[t] = dvd(sub(dd[t], dd[t - 1]), sub(zs[t], zs[t - lev]));
+        double coef[11];
+        for (int i = 0; i < 11; i++) coef[i] = 0.0;
+        coef[0] = dd[10];
+        for (int t = 9; t >= 0; t--) {
+            for (int i = 10; i >= 1; i--) coef[i] = sub(coef[i - 1], mul(coef[i], zs[t]));
+            coef[0] = sub(dd[t], mul(coef[0], zs[t]));
+        }
+        int deg = 10;
+        double cmax = 0.0;
+        bool finite = true;
+        for (int i = 0; i <= 10; i++) { if (!dfinite(coef[i])) finite = false; if (fabs(coef[i]) > cmax) cmax = fabs(coef[i]); }
+        if (!finite) return 0;
+        while (deg > 0 && !(fabs(coef[deg]) > mul(1e-13, cmax))) deg--;
+        if (deg < 1) continue;
+        double rr[10];
+        const int nr = real_roots(coef, deg, rr);
+        for (int i = 0; i < nr; i++) {
+            if (pass == 0) { if (fabs(rr[i]) <= 1.05) roots[nroots++] = rr[i]; }
+            else if (fabs(rr[i]) < dvd(1.0, 1.05) && rr[i] != 0.0) roots[nroots++] = dvd(1.0, rr[i]);
+        }
+    }
+    if (nroots > 10) nroots = 10;
+    for (int i = 1; i < nroots; i++) {
+        const double v = roots[i];
+        int j = i - 1;
+        while (j >= 0 && fabs(roots[j]) > fabs(v)) { roots[j + 1] = roots[j]; j--; }
+        roots[j + 1] = v;
+    }
+    for (int ri = 0; ri < nroots; ri++) {
+        const double z = roots[ri];
+        for (int r = 0; r < 10; r++)
+            for (int c = 0; c < 10; c++) Mz[r * 10 + c] = horner(&C[r][COL_FIRST[c]], COL_DEG[c], z);
+        bool ok = true;
+        for (int k = 0; k < 9 && ok; k++) {
+            int piv = k;
+            double best = fabs(Mz[k * 10 + k]);
+            for (int r = k + 1; r < 10; r++) { const double v = fabs(Mz[r * 10 + k]); if (v > best) { best = v; piv = r; } }
+            if (!(best > 0.0) || !dfinite(best)) { ok = false; break; }
+            if (piv != k) for (int j = 0; j < 10; j++) { const double t = Mz[k * 10 + j]; Mz[k * 10 + j] = Mz[piv * 10 + j]; Mz[piv * 10 + j] = t; }
+            const double inv = dvd(1.0, Mz[k * 10 + k]);
+            for (int j = k + 1; j < 10; j++) Mz[k * 10 + j] = mul(Mz[k * 10 + j], inv);
+            for (int r = 0; r < 10; r++) {
+                if (r == k) continue;
+                const double f = Mz[r * 10 + k];
+                for (int j = k + 1; j < 10; j++) Mz[r * 10 + j] = sub(Mz[r * 10 + j], mul(f, Mz[k * 10 + j]));
+            }
+        }
+        if (!ok) continue;
+        double u[3] = {-Mz[7 * 10 + 9], -Mz[8 * 10 + 9], z};
+        for (int it = 0; it < 8; it++) {                                  // Gauss-Newton on the ten constraints
+            double pw[3][4];
+            for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
+            double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
+            for (int r = 0; r < 10; r++) {
+                double val = 0.0, g[3] = {0, 0, 0};
+                for (int m = 0; m < 20; m++) {
+                    const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
+                    const double c = C[r][m];
+                    val = add(val, mul(c, mul(mul(pw[0][e[0]], pw[1][e[1]]), pw[2][e[2]])));
+                    for (int a = 0; a < 3; a++) {
+                        if (e[a] == 0) continue;
+                        double t = (double)e[a];
+                        for (int b = 0; b < 3; b++) t = mul(t, pw[b][b == a ? e[b] - 1 : e[b]]);
+                        g[a] = add(g[a], mul(c, t));
+                    }
+                }
+                JtJ[0] = add(JtJ[0], mul(g[0], g[0])); JtJ[1] = add(JtJ[1], mul(g[0], g[1])); JtJ[2] = add(JtJ[2], mul(g[0], g[2]));
+                JtJ[3] = add(JtJ[3], mul(g[1], g[1])); JtJ[4] = add(JtJ[4], mul(g[1], g[2])); JtJ[5] = add(JtJ[5], mul(g[2], g[2]));
+                Jtr[0] = add(Jtr[0], mul(g[0], val)); Jtr[1] = add(Jtr[1], mul(g[1], val)); Jtr[2] = add(Jtr[2], mul(g[2], val));
+            }
+            const double a = JtJ[0], b = JtJ[1], c = JtJ[2], d = JtJ[3], e = JtJ[4], f = JtJ[5];
+            const double c00 = sub(mul(d, f), mul(e, e)), c01 = sub(mul(c, e), mul(b, f)), c02 = sub(mul(b, e), mul(c, d));
+            const double c11 = sub(mul(a, f), mul(c, c)), c12 = sub(mul(b, c), mul(a, e)), c22 = sub(mul(a, d), mul(b, b));
+            const double det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
+            if (!(fabs(det) > 0.0) || !dfinite(det)) break;
+            const double dx = dvd(add(add(mul(c00, Jtr[0]), mul(c01, Jtr[1])), mul(c02, Jtr[2])), det);
+            const double dy = dvd(add(add(mul(c01, Jtr[0]), mul(c11, Jtr[1])), mul(c12, Jtr[2])), det);
+            const double dz = dvd(add(add(mul(c02, Jtr[0]), mul(c12, Jtr[1])), mul(c22, Jtr[2])), det);
+            if (!dfinite(dx) || !dfinite(dy) || !dfinite(dz)) break;
+            u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
+        }
+        double E[9];
+        bool finite = true;
+        for (int e = 0; e < 9; e++) {
+            double v = mul(L[e][0], u[0]);
+            v = add(v, mul(L[e][1], u[1]));
+            v = add(v, mul(L[e][2], u[2]));
+            v = add(v, L[e][3]);
+            E[e] = v;
+            if (!dfinite(v)) finite = false;
+        }
+        if (!finite) continue;
+        double n2 = 0.0;
+        for (int e = 0; e < 9; e++) n2 = add(n2, mul(E[e], E[e]));
+        const double sc = __dsqrt_rn(mul(0.5, n2));
+        if (!(sc > 0.0)) continue;
+        double En[9];
+        for (int e = 0; e < 9; e++) En[e] = dvd(E[e], sc);
+        double tv[3] = {0, 0, 0}, tbest = -1.0;
+        for (int a = 0; a < 3; a++) {
+            const int b = (a + 1) % 3;
+            // columns a and b of En: col[c][r] = En[3r + c]
+            const double cx = sub(mul(En[3 + a], En[6 + b]), mul(En[6 + a], En[3 + b]));
+            const double cy = sub(mul(En[6 + a], En[0 + b]), mul(En[0 + a], En[6 + b]));
+            const double cz = sub(mul(En[0 + a], En[3 + b]), mul(En[3 + a], En[0 + b]));
+            const double nn = add(add(mul(cx, cx), mul(cy, cy)), mul(cz, cz));
+            if (nn > tbest) { tbest = nn; tv[0] = cx; tv[1] = cy; tv[2] = cz; }
+        }
+        if (!(tbest > 0.0)) continue;
+        { const double inv = dvd(1.0, __dsqrt_rn(tbest)); tv[0] = mul(tv[0], inv); tv[1] = mul(tv[1], inv); tv[2] = mul(tv[2], inv); }
+        double cof[9], tE[9];
+        cof[0] = sub(mul(En[4], En[8]), mul(En[5], En[7])); cof[1] = sub(mul(En[5], En[6]), mul(En[3], En[8])); cof[2] = sub(mul(En[3], En[7]), mul(En[4], En[6]));
+        cof[3] = sub(mul(En[2], En[7]), mul(En[1], En[8])); cof[4] = sub(mul(En[0], En[8]), mul(En[2], En[6])); cof[5] = sub(mul(En[1], En[6]), mul(En[0], En[7]));
+        cof[6] = sub(mul(En[1], En[5]), mul(En[2], En[4])); cof[7] = sub(mul(En[2], En[3]), mul(En[0], En[5])); cof[8] = sub(mul(En[0], En[4]), mul(En[1], En[3]));
+        for (int c = 0; c < 3; c++) {
+            tE[0 + c] = sub(mul(tv[1], En[6 + c]), mul(tv[2], En[3 + c]));
+            tE[3 + c] = sub(mul(tv[2], En[0 + c]), mul(tv[0], En[6 + c]));
+            tE[6 + c] = sub(mul(tv[0], En[3 + c]), mul(tv[1], En[0 + c]));
+        }
+        bool pass = false;
+        for (int cam = 0; cam < 4 && !pass; cam++) {
+            double R[9], t[3];
+            const double rs = (cam < 2) ? -1.0 : 1.0, ts = (cam & 1) ? -1.0 : 1.0;
+            for (int e = 0; e < 9; e++) R[e] = add(cof[e], mul(rs, tE[e]));
+            for (int e = 0; e < 3; e++) t[e] = mul(ts, tv[e]);
+            int infront = 0;
+            for (int k = 0; k < 5; k++) {
+                const double a0 = add(add(mul(R[0], x1[k]), mul(R[1], y1[k])), R[2]);
+                const double a1 = add(add(mul(R[3], x1[k]), mul(R[4], y1[k])), R[5]);
+                const double a2 = add(add(mul(R[6], x1[k]), mul(R[7], y1[k])), R[8]);
+                const double b0 = x2[k], b1 = y2[k], b2 = 1.0;
+                const double aa = add(add(mul(a0, a0), mul(a1, a1)), mul(a2, a2)), bb = add(add(mul(b0, b0), mul(b1, b1)), mul(b2, b2));
+                const double ab = add(add(mul(a0, b0), mul(a1, b1)), mul(a2, b2));
+                const double at = add(add(mul(a0, t[0]), mul(a1, t[1])), mul(a2, t[2])), bt = add(add(mul(b0, t[0]), mul(b1, t[1])), mul(b2, t[2]));
+                const double det = sub(mul(aa, bb), mul(ab, ab));
+                const double l1 = dvd(sub(mul(ab, bt), mul(bb, at)), det), l2 = dvd(sub(mul(aa, bt), mul(ab, at)), det);
+                if (l1 > 0.0 && l2 > 0.0) infront++; else break;
+            }
+            if (infront == 5) pass = true;
+        }
+        if (pass) {
+            for (int e = 0; e < 9; e++) out[e] = (float)E[e];
+            return 1;
+        }
+    }
+    return 0;
 }

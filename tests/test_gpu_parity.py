@@ -164,9 +164,9 @@ def test_errors_and_inliers_bit_exact(ctx, cfg):
         assert np.array_equal(ids, O.score(est, pts, mod, thr, want_inliers=True)[3])
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
 def test_solvers_bit_identical_to_oracle(ctx, cfg):
-    pts, gt, mask = gen.make(cfg)
+    pts, gt, mask = gen.make(cfg) if cfg != 4 else gen.make(cfg, n=3000)
     est = EST[gen.CONFIGS[cfg]["estimator"]]
     m = O.SAMPLE_SIZE[est]
     g = np.random.default_rng(cfg)
@@ -338,3 +338,18 @@ def test_fit_prosac_termination_matches_oracle(ctx, sprt):
             assert r[key] == ref[key], (key, r[key], ref[key], seed)
         assert np.array_equal(bits(r["model"]), bits(ref["model"]))
         assert r["iterations"] < max_it                               # the PROSAC criterion did stop the run early
+
+
+def test_fit_essential_matches_oracle(ctx):
+    """BASELINE config 4 (essential 5-pt, uniform sampler, with and without SPRT; LO is SURVEY 8f "next") at a reduced size."""
+    pts, E, mask = gen.essential(n=2000, inlier_ratio=0.35, seed=41)
+    thr = 2.5e-3
+    ctx.set_points(O.EST_ESSENTIAL, pts)
+    r = ctx.fit(thr, 0.95, 1500, seed=2, round_size=256)[0]
+    ref = O.ransac(pts, O.EST_ESSENTIAL, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95, max_iterations=1500, seed=2)
+    assert_fit_equal(r, ref, O.EST_ESSENTIAL)
+    assert r["inliers"] > 0.25 * len(pts)                             # the fit did find the epipolar geometry
+    ctx.set_sprt_pool(0, O.sprt_pool(2, len(pts)))
+    r = ctx.fit(thr, 0.95, 1500, seed=2, round_size=256, sprt=True)[0]
+    ref = O.ransac(pts, O.EST_ESSENTIAL, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95, max_iterations=1500, seed=2, sprt=True, batch=256)
+    assert_fit_equal_sprt(r, ref)

@@ -283,3 +283,60 @@ def test_prosac_run_finds_model_early():
     r = O.ransac(pts, O.EST_FUNDAMENTAL, sampler=O.SAMPLER_PROSAC, threshold=2.0, seed=2, max_iterations=10000)
     assert r["inliers"] >= 0.5 * mask.sum()
     assert r["iterations"] < 10000                                  # PROSAC's prefix criterion stops early
+
+
+# ---- five-point essential solver -------------------------------------------------------------------------------------
+def _unit(E):
+    E = np.asarray(E, np.float64).reshape(3, 3)
+    E = E / np.linalg.norm(E)
+    return E * np.sign(E.ravel()[np.argmax(np.abs(E))])
+
+
+def test_essential5_candidates_match_opencv_solution_sets(golden_dir):
+    """The oracle's candidate set equals the set of real solutions OpenCV's five-point solver returns (scale/sign free) on
+    at least 57 of the 60 samples; on the rest (nearly double roots) every oracle candidate still has to be a solution of
+    the five-point system - nothing spurious is ever returned."""
+    z = np.load(os.path.join(golden_dir, "essential5_cv.npz"))
+    dist = lambda a, b: min(np.abs(a - b).max(), np.abs(a + b).max())   # noqa: E731
+    exact, total = 0, 0
+    for pts, sols, k in zip(z["points"], z["solutions"], z["counts"]):
+        Es, valid = O.essential5_candidates(pts, np.arange(5, dtype=np.int32))
+        cv_set = [_unit(sols[i]) for i in range(k)]
+        mine = [_unit(E) for E in Es]
+        p = pts.astype(np.float64)
+        for En in mine:
+            res = [np.array([x2, y2, 1.0]) @ En @ np.array([x1, y1, 1.0]) for x1, y1, x2, y2 in p]
+            assert np.abs(res).max() < 1e-9 and np.abs(2 * En @ En.T @ En - np.trace(En @ En.T) * En).max() < 1e-7
+        ok = all(min(dist(c, m) for m in mine) < 1e-6 for c in cv_set) and all(min(dist(c, m) for c in cv_set) < 1e-6 for m in mine)
+        exact += ok
+        total += k
+    assert exact >= 57 and total > 200
+
+
+def test_essential5_identities_and_selection():
+    from ransac_b200 import generator as gen
+    pts, E_gt, mask = gen.essential(n=3000, noise=0.0, seed=21)
+    inl = np.where(mask)[0]
+    g = np.random.default_rng(3)
+    found = 0
+    for _ in range(100):
+        s = g.choice(inl, 5, replace=False).astype(np.int32)
+        Es, valid = O.essential5_candidates(pts, s)
+        m = O.solve_minimal(O.EST_ESSENTIAL, pts, s)
+        if valid.any():                                               # EstimateModel returns the FIRST candidate that passes the vote
+            assert len(m) == 1
+            first = Es[np.argmax(valid)]
+            assert np.array_equal(m[0], first.astype(np.float32).ravel())
+        else:
+            assert len(m) == 0
+        for E in Es:
+            En = E / np.linalg.norm(E)
+            p = pts[s].astype(np.float64)
+            res = [np.array([x2, y2, 1.0]) @ En @ np.array([x1, y1, 1.0]) for x1, y1, x2, y2 in p]
+            assert np.abs(res).max() < 1e-9                           # annihilates its own sample
+            assert abs(np.linalg.det(En)) < 1e-9 and np.abs(2 * En @ En.T @ En - np.trace(En @ En.T) * En).max() < 1e-9
+        d = [np.abs(_unit(E) - _unit(E_gt)).max() for E in Es]
+        if d and min(d) < 1e-5:
+            found += 1
+            assert valid[int(np.argmin(d))]                           # the true E passes the cheirality vote
+    assert found >= 95
