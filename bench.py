@@ -298,8 +298,15 @@ def run_native(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes_launch = (16.0 * N_POINTS * B + 128.0 * executed / N_POINTS) / 1.0       # every point once per pass + the model records
+        traffic, traffic_note = None, None
+        try:   # DRAM bytes of one ncu --set full capture of this kernel (profiles/): a full-size launch, not this run's average
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_note = f"{tj['launch']}: {traffic / 1e6:.1f} MB DRAM vs {tj['algorithmic_bytes'] / 1e6:.1f} MB algorithmic ({tj['source']})"
+        except Exception:   # noqa: BLE001
+            pass
         roofline = {"bound": "fp32", "kernel": "score_kernel<HOMOGRAPHY>", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp32_peak, "traffic": None,
+                    "frac": ach / fp32_peak, "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": "2*128 lanes*SMs*max SM clock from the device (no FP32 figure in MEASURED_PEAKS.json); "
                                    f"register-resident FFMA loop measured in this run: {measured_ffma:.1f} TFLOP/s",
                     "flops_per_eval": 42, "evals_per_launch": executed / max(score_launches, 1),
