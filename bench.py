@@ -337,6 +337,96 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload c5: BASELINE.json configs[4] - ONE homography problem with 1M correspondences (10 % inliers, clustered),
+# NAPSAC over the device grid, 10 000 samples; the hypotheses of every round are sharded over the ranks and one NCCL
+# all-gather per round exchanges the per-sample scores (strong scaling: the job is fixed, more GPUs finish it sooner).
+# ---------------------------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+
+    from ransac_b200 import GpuContext, capi, nccl_unique_id
+    from ransac_b200 import dist as D
+    from ransac_b200 import generator as gen
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    rank, world = D.init("nccl")
+    n, K = args.c5_points, 2048
+    pts = gen.make(5, n=n)[0]
+    host = torch.from_numpy(pts).pin_memory()
+    ctx = GpuContext(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        ctx.nccl_init(D.broadcast_bytes(nccl_unique_id() if rank == 0 else None), rank, world)
+    info = ctx.device_info()
+    fit_kw = dict(threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=1, round_size=K, sampler=capi.SAMPLER_NAPSAC,
+                  neighbors=capi.NEIGH_GRID, rank=rank, nranks=world)
+    ctx.set_points(capi.EST_HOMOGRAPHY, host)
+    ctx.set_neighbors_grid(0, 50)
+
+    def bracket(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier(); torch.cuda.synchronize()
+        out = []
+        ev0.record(stream)
+        for _ in range(steps):
+            out.append(fn())
+        ev1.record(stream)
+        D.barrier(); torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1), out
+
+    def step():
+        r = ctx.fit_records(**fit_kw)[0]
+        t = ctx.last_timing()
+        return int(r["useful_evals"]), int(r["evals"]), t["launches"], t["score_launches"], t["score_ms"], int(r["iterations"]), int(r["inliers"])
+
+    def step_e2e():
+        ctx.set_points(capi.EST_HOMOGRAPHY, host)          # H2D of the 16 MB point set; the neighbourhood grid (built on the host by
+        ctx.set_neighbors_grid(0, 50)                       # set_neighbors_grid, the reference times it separately: test/test.cpp:17-29) too
+        return step()
+
+    bracket(step, args.warmup)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, st = bracket(step, args.steps)
+    clk = clocks.stop()
+    ms_e2e, st_e2e = bracket(step_e2e, max(1, min(args.steps, 3)))
+    t_all = D.reduce_max([ms, ms_e2e / max(1, min(args.steps, 3)) * args.steps])
+    sums = D.reduce_sum([sum(x[0] for x in st), sum(x[1] for x in st), sum(x[2] for x in st), sum(x[0] for x in st_e2e) / len(st_e2e) * args.steps])
+    if rank == 0:
+        peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
+        executed, launches, score_ms = sum(x[1] for x in st), sum(x[3] for x in st), sum(x[4] for x in st)
+        ach = 42.0 * executed / (score_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": sums[0] / (t_all[0] * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_all[0] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"C5 homography N={n}, 10% inliers (clustered), NAPSAC grid cell 50, max_iter {MAX_IT}, conf {CONF}; "
+                                       f"step = one robust fit, hypotheses sharded over {world} GPU(s), one NCCL all-gather per round of {K} samples",
+                           "ms_per_fit": t_all[0] / args.steps, "iterations": st[-1][5], "inliers": st[-1][6],
+                           "l2": "the 32 MB point set (AoS + pair layout) is L2 resident by design: it is re-read by every model block",
+                           "evals_executed_per_s": sums[1] / (t_all[0] * 1e-3)},
+                "clocks": clk, "gpu_launches": int(sums[2]),
+                "e2e": {"value": sums[3] / (t_all[1] * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 168 + 4 * st[-1][2],
+                        "ms_per_step": t_all[1] / args.steps, "note": "includes the host-side grid build of set_neighbors_grid"},
+                "roofline": {"bound": "fp32", "kernel": "score_kernel<HOMOGRAPHY>", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                             "traffic": None, "flops_per_eval": 42, "avg_launch_ms": score_ms / max(launches, 1)}}
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_GRID, cell_size=50,
+                           threshold=THR, confidence=CONF, max_iterations=128, seed=1)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ref["evals"] / dt, "unit": "evals/s", "cores": 1, "kind": "port",
+                                    "sample": "the first 128 hypotheses of the same fit (sequential oracle, one thread; includes its grid build)"}
+        print(json.dumps(line))
+    ctx.close()
+    D.finalize()
+
+
 def single_fit_latency(ctx, pts, timed):
     """ms per robust fit when ONE image pair is fitted alone (launch/sync latency bound), median of 20."""
     from ransac_b200 import capi
@@ -360,11 +450,15 @@ def main():
     ap.add_argument("--round-size", type=int, default=128, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
+    ap.add_argument("--c5-points", type=int, default=1000000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_native(args)
 

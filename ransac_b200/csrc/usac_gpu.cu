@@ -2,6 +2,9 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (ransac_b200/build.py)
 #include <dlfcn.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -70,6 +73,9 @@ struct usac_gpu_ctx {
     DevBuf<SprtModelResult> d_sprt_res;
     DevBuf<int2> d_model_scores;
     DevBuf<float> d_pool_pts;          // the points in SPRT pool order (same offsets as d_aos)
+    DevBuf<unsigned long long> d_grid_keys;   // grid build scratch: 2n keys
+    DevBuf<int> d_grid_ints;                  // grid build scratch: 4n ints + 1
+    DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
     // scoring API buffers
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
     DevBuf<int> d_q_cnt, d_q_ids;
@@ -149,7 +155,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -318,44 +324,98 @@ extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const in
     return push_desc(c);
 }
 
+// ---- device-side grid build (nearest_neighbors.cpp:160-201): cell = (int(x1/c), int(y1/c), int(x2/c), int(y2/c)), truncation
+// toward zero; a point's neighbours are the other members of its cell in ascending index order. Stored as CSR: points sorted
+// by a 64-bit cell key (stable radix sort keeps the index order inside a cell) + the rank of each point in its cell.
+__global__ void grid_keys_kernel(const float* __restrict__ aos, int n, float cell, unsigned long long* __restrict__ keys, int* __restrict__ idx,
+                                 int* __restrict__ overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = reinterpret_cast<const float4*>(aos)[i];
+    const int c0 = (int)__fdiv_rn(p.x, cell), c1 = (int)__fdiv_rn(p.y, cell), c2 = (int)__fdiv_rn(p.z, cell), c3 = (int)__fdiv_rn(p.w, cell);
+    if (max(max(abs(c0), abs(c1)), max(abs(c2), abs(c3))) >= 32768) *overflow = 1;
+    keys[i] = ((unsigned long long)(unsigned)(c0 + 32768) << 48) | ((unsigned long long)(unsigned)(c1 + 32768) << 32) |
+              ((unsigned long long)(unsigned)(c2 + 32768) << 16) | (unsigned long long)(unsigned)(c3 + 32768);
+    idx[i] = i;
+}
+__global__ void grid_flags_kernel(const unsigned long long* __restrict__ skeys, int n, int* __restrict__ flags) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) flags[q] = (q == 0 || skeys[q] != skeys[q - 1]) ? 1 : 0;
+}
+__global__ void grid_starts_kernel(const int* __restrict__ flags, const int* __restrict__ cellid1, int n, int* __restrict__ cell_start) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n && flags[q]) cell_start[cellid1[q] - 1] = q;
+}
+__global__ void grid_fill_tail_kernel(const int* __restrict__ cellid1, int n, int* __restrict__ cell_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n && c >= cellid1[n - 1]) cell_start[c] = n;
+}
+__global__ void grid_scatter_kernel(const int* __restrict__ sidx, const int* __restrict__ cellid1, const int* __restrict__ cell_start, int n,
+                                    int* __restrict__ cell_of_point, int* __restrict__ members, int* __restrict__ rank) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int p = sidx[q], cid = cellid1[q] - 1;
+    members[q] = p;
+    cell_of_point[p] = cid;
+    rank[p] = q - cell_start[cid];
+}
+
+// reserve a segment of `count` elements at the end of a side array (contents undefined)
+template <class T>
+static cudaError_t reserve_segment(DevBuf<T>& buf, size_t used, size_t count, cudaStream_t s) {
+    if (used + count <= buf.cap) return cudaSuccess;
+    DevBuf<T> nb;
+    cudaError_t e = nb.ensure(std::max((used + count) * 2, (size_t)1024));
+    if (e != cudaSuccess) return e;
+    if (used) cudaMemcpyAsync(nb.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    cudaStreamSynchronize(s);
+    buf.release();
+    buf = nb;
+    return cudaSuccess;
+}
+
 extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cell_size) {
     if (!c || problem < 0 || problem >= c->P || cell_size <= 0) return fail(c, USAC_ERR_ARG, "set_neighbors_grid: bad arguments");
     if (usac_point_dim(c->est) != 4) return fail(c, USAC_ERR_ARG, "set_neighbors_grid: needs correspondences (nearest_neighbors.cpp:172 reads 4 columns)");
     cudaSetDevice(c->device);
     ProblemDesc& d = c->h_prob[problem];
     const int n = d.n;
-    // nearest_neighbors.cpp:160-201: cell = (int(x1/c), int(y1/c), int(x2/c), int(y2/c)); a point's neighbours are the other
-    // members of its cell in ascending index order. Stored as CSR (sorted by cell key, then index) + rank of each point.
-    std::vector<float> pts((size_t)n * 4);
-    CUDA_TRY(c, cudaMemcpyAsync(pts.data(), c->d_aos.p + (size_t)d.aos_off * 4, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    typedef std::tuple<int, int, int, int, int> Key;
-    std::vector<Key> keys(n);
-    for (int i = 0; i < n; i++) {
-        const float* p = &pts[4 * (size_t)i];
-        keys[i] = Key((int)(p[0] / cell_size), (int)(p[1] / cell_size), (int)(p[2] / cell_size), (int)(p[3] / cell_size), i);
-    }
-    std::sort(keys.begin(), keys.end());
-    std::vector<int> cell(n), members(n), rank(n), cell_start;
-    int ncell = -1;
-    for (int q = 0; q < n; q++) {
-        const bool first = q == 0 || std::get<0>(keys[q]) != std::get<0>(keys[q - 1]) || std::get<1>(keys[q]) != std::get<1>(keys[q - 1]) ||
-                           std::get<2>(keys[q]) != std::get<2>(keys[q - 1]) || std::get<3>(keys[q]) != std::get<3>(keys[q - 1]);
-        if (first) { ncell++; cell_start.push_back(q); }
-        const int idx = std::get<4>(keys[q]);
-        members[q] = idx; cell[idx] = ncell; rank[idx] = q - cell_start.back();
-    }
-    cell_start.push_back(n);
-    cell_start.resize(n + 1, n);
     SideUsed& u = c->side;
-    size_t g0 = u.grid, g1 = u.grid, g2 = u.grid;
-    long long o0, o1, o2;
-    CUDA_TRY(c, append_segment(c->d_cell_of_point, g0, cell.data(), (size_t)n, &o0, c->stream));
-    CUDA_TRY(c, append_segment(c->d_members, g1, members.data(), (size_t)n, &o1, c->stream));
-    CUDA_TRY(c, append_segment(c->d_rank, g2, rank.data(), (size_t)n, &o2, c->stream));
-    u.grid = g0;
-    d.grid_off = o0;
-    CUDA_TRY(c, append_segment(c->d_cell_start, u.cell_start, cell_start.data(), (size_t)n + 1, &d.cell_start_off, c->stream));
+    CUDA_TRY(c, reserve_segment(c->d_cell_of_point, u.grid, (size_t)n, c->stream));
+    CUDA_TRY(c, reserve_segment(c->d_members, u.grid, (size_t)n, c->stream));
+    CUDA_TRY(c, reserve_segment(c->d_rank, u.grid, (size_t)n, c->stream));
+    CUDA_TRY(c, reserve_segment(c->d_cell_start, u.cell_start, (size_t)n + 1, c->stream));
+    CUDA_TRY(c, c->d_grid_keys.ensure(2 * (size_t)n));
+    CUDA_TRY(c, c->d_grid_ints.ensure(4 * (size_t)n + 1));
+    struct { unsigned long long* p; } keys{c->d_grid_keys.p}, skeys{c->d_grid_keys.p + n};
+    struct { int* p; } idx{c->d_grid_ints.p}, sidx{c->d_grid_ints.p + n}, flags{c->d_grid_ints.p + 2 * (size_t)n}, cellid1{c->d_grid_ints.p + 3 * (size_t)n},
+        ovf{c->d_grid_ints.p + 4 * (size_t)n};
+    CUDA_TRY(c, cudaMemsetAsync(ovf.p, 0, sizeof(int), c->stream));
+    const int g = (n + 255) / 256;
+    grid_keys_kernel<<<g, 256, 0, c->stream>>>(c->d_aos.p + (size_t)d.aos_off * 4, n, (float)cell_size, keys.p, idx.p, ovf.p);
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb1, keys.p, skeys.p, idx.p, sidx.p, n, 0, 64, c->stream);
+    cub::DeviceScan::InclusiveSum(nullptr, tb2, flags.p, cellid1.p, n, c->stream);
+    CUDA_TRY(c, c->d_grid_temp.ensure(std::max(tb1, tb2)));
+    struct { unsigned char* p; } temp{c->d_grid_temp.p};
+    size_t tb = std::max(tb1, tb2);
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(temp.p, tb, keys.p, skeys.p, idx.p, sidx.p, n, 0, 64, c->stream));
+    grid_flags_kernel<<<g, 256, 0, c->stream>>>(skeys.p, n, flags.p);
+    tb = std::max(tb1, tb2);
+    CUDA_TRY(c, cub::DeviceScan::InclusiveSum(temp.p, tb, flags.p, cellid1.p, n, c->stream));
+    int* cs = c->d_cell_start.p + u.cell_start;
+    grid_fill_tail_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(cellid1.p, n, cs);
+    grid_starts_kernel<<<g, 256, 0, c->stream>>>(flags.p, cellid1.p, n - 0, cs);
+    grid_scatter_kernel<<<g, 256, 0, c->stream>>>(sidx.p, cellid1.p, cs, n, c->d_cell_of_point.p + u.grid, c->d_members.p + u.grid, c->d_rank.p + u.grid);
+    int h_ovf = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    if (h_ovf) return fail(c, USAC_ERR_ARG, "set_neighbors_grid: cell coordinates exceed 16 bits (cell_size too small for this coordinate range)");
+    d.grid_off = (long long)u.grid;
+    d.cell_start_off = (long long)u.cell_start;
+    u.grid += (size_t)n;
+    u.cell_start += (size_t)n + 1;
     if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_GRID;
     return push_desc(c);
