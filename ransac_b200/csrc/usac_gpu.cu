@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -84,6 +85,9 @@ struct usac_gpu_ctx {
     void* allgather_user = nullptr;
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
+    // termination tables of the last fit (rebuilt only when (n, m, confidence, max_iterations) change)
+    std::map<std::tuple<int, int, float, unsigned>, std::vector<unsigned>> term_cache;
+    std::vector<long long> term_signature;   // what d_term currently holds: (m, confidence bits, max_iterations, n of every problem)
     // timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
     size_t score_events_used = 0;
@@ -611,13 +615,16 @@ extern "C" int usac_gpu_get_inliers(usac_gpu_ctx* c, int problem, const float* m
 static void standard_termination_table(unsigned n, int m, float confidence, unsigned max_iterations, std::vector<unsigned>& out) {
     out.resize((size_t)n + 1);
     const float log_1_p = (float)logf(1 - confidence);
-    for (unsigned inl = 0; inl <= n; inl++) {
-        float inl_ratio = (float)inl / n;
-        float inl_prob = inl_ratio * inl_ratio;
-        int k = m;
-        while (k > 2) { inl_prob *= inl_ratio; k--; }
-        out[inl] = (inl_prob < 0.0005f) ? max_iterations : (unsigned)(log_1_p / logf(1 - inl_prob));
-    }
+    auto fill = [&](unsigned lo, unsigned hi) {
+        for (unsigned inl = lo; inl < hi; inl++) out[inl] = standard_termination_value(inl, n, m, log_1_p, max_iterations);
+    };
+    const unsigned total = n + 1;
+    unsigned nthreads = total >= (1u << 16) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    if (nthreads <= 1) { fill(0, total); return; }
+    std::vector<std::thread> pool;                       // 1M-point problems: a million logf calls, spread over the host cores
+    const unsigned per = (total + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(fill, std::min(total, t * per), std::min(total, (t + 1) * per));
+    for (auto& th : pool) th.join();
 }
 
 static void prosac_growth(unsigned n, unsigned m, std::vector<unsigned>& g) {
@@ -1004,20 +1011,32 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     // termination tables (cached by n) and sampler side data
     {
         std::map<int, long long> by_n;
-        std::vector<unsigned> all, t;
+        std::vector<unsigned> all;
+        if (c->term_cache.size() > 64) c->term_cache.clear();
         for (int p = 0; p < P; p++) {
             const int n = c->h_prob[p].n;
             auto it = by_n.find(n);
             if (it == by_n.end()) {
-                standard_termination_table((unsigned)n, m, cfg->confidence, cfg->max_iterations, t);
+                auto key = std::make_tuple(n, m, cfg->confidence, cfg->max_iterations);
+                auto ct = c->term_cache.find(key);
+                if (ct == c->term_cache.end()) {
+                    std::vector<unsigned> t;
+                    standard_termination_table((unsigned)n, m, cfg->confidence, cfg->max_iterations, t);
+                    ct = c->term_cache.emplace(key, std::move(t)).first;
+                }
                 it = by_n.insert({n, (long long)all.size()}).first;
-                all.insert(all.end(), t.begin(), t.end());
+                all.insert(all.end(), ct->second.begin(), ct->second.end());
             }
             c->h_prob[p].term_off = it->second;
         }
-        CUDA_TRY(c, c->d_term.ensure(all.size()));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_term.p, all.data(), sizeof(unsigned) * all.size(), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        std::vector<long long> sig = {(long long)m, (long long)__builtin_bit_cast(unsigned, cfg->confidence), (long long)cfg->max_iterations};
+        for (int p = 0; p < P; p++) sig.push_back(c->h_prob[p].n);
+        if (sig != c->term_signature || c->d_term.cap < all.size()) {
+            CUDA_TRY(c, c->d_term.ensure(all.size()));
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_term.p, all.data(), sizeof(unsigned) * all.size(), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            c->term_signature = sig;
+        }
     }
     int rc = setup_sampler_side(c, cfg->sampler);
     if (rc) return rc;
