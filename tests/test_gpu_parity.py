@@ -353,3 +353,63 @@ def test_fit_essential_matches_oracle(ctx):
     r = ctx.fit(thr, 0.95, 1500, seed=2, round_size=256, sprt=True)[0]
     ref = O.ransac(pts, O.EST_ESSENTIAL, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95, max_iterations=1500, seed=2, sprt=True, batch=256)
     assert_fit_equal_sprt(r, ref)
+
+
+# ---- argument checking and edge cases of the C ABI ------------------------------------------------------------------------
+def test_cabi_rejects_bad_arguments(ctx):
+    from ransac_b200 import UsacGpuError, capi
+    import ctypes as C
+    L, h = ctx.L, ctx.h
+    pts, H, _ = gen.homography(n=100, seed=1)
+    with pytest.raises(UsacGpuError):
+        ctx.set_points(O.EST_HOMOGRAPHY, pts[:3])                     # fewer points than the minimal sample
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    with pytest.raises(UsacGpuError):
+        ctx.score(H.ravel()[None], 0.0)                               # threshold must be positive
+    with pytest.raises(UsacGpuError):
+        ctx.estimate(np.array([[0, 1, 2, 100]], np.int32))            # index out of range
+    with pytest.raises(UsacGpuError):
+        ctx.fit(2.0, 0.95, 0)                                         # max_iterations == 0
+    with pytest.raises(UsacGpuError):
+        ctx.fit(2.0, 0.95, 100, sprt=True)                            # SPRT without a pool
+    with pytest.raises(UsacGpuError):
+        ctx.fit(2.0, 0.95, 100, rank=0, nranks=2)                     # sharding without an exchange
+    with pytest.raises(UsacGpuError):
+        ctx.set_neighbors_grid(0, 0)
+    assert L.usac_gpu_score(h, 5, None, 1, C.c_float(2.0), None, None) == capi.ERR_ARG   # unknown problem / NULL models
+    assert b"score" in L.usac_gpu_last_error(h)
+    cnt, s = ctx.score(np.zeros((0, 9), np.float32), 2.0)             # zero models: nothing to do, not an error
+    assert len(cnt) == 0
+    r = ctx.fit(2.0, 0.95, 500, seed=1)[0]                            # the context is still usable after the failures
+    assert r["inliers"] > 20
+
+
+def test_minimal_point_sets_and_all_outliers(ctx):
+    """Exactly m points (every sample is the whole set) and a set without structure (the loop runs to max_iterations)."""
+    pts, H, _ = gen.homography(n=40, seed=2)
+    four = pts[:4]
+    ctx.set_points(O.EST_HOMOGRAPHY, four)
+    r = ctx.fit(2.0, 0.95, 50, seed=1, round_size=16)[0]
+    ref = O.ransac(four, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=2.0, confidence=0.95, max_iterations=50, seed=1)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+    noise = gen.homography(n=3000, inlier_ratio=0.0, seed=9)[0]
+    ctx.set_points(O.EST_HOMOGRAPHY, noise)
+    r = ctx.fit(2.0, 0.95, 700, seed=3, round_size=128)[0]
+    ref = O.ransac(noise, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=2.0, confidence=0.95, max_iterations=700, seed=3)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+    assert r["iterations"] == 700 and r["useful_evals"] == ref["evals"]
+
+
+def test_line_and_essential_known_geometry(ctx):
+    """Line and essential scoring have no reference known answers; anchor them on geometry: the ground-truth model's inliers
+    are exactly the generator's inlier set (noise below the threshold), counted identically by GPU and oracle."""
+    pts, line, mask = gen.line2d(n=2000, seed=5)
+    ctx.set_points(O.EST_LINE2D, pts)
+    cnt, _ = ctx.score(line[None], 8.0)
+    assert cnt[0] == O.score(O.EST_LINE2D, pts, line, 8.0)[0] and cnt[0] >= mask.sum()
+    pts, E, mask = gen.essential(n=4000, noise=0.2, seed=6)
+    ctx.set_points(O.EST_ESSENTIAL, pts)
+    cnt, _ = ctx.score(E.ravel()[None], 2.5e-3)
+    assert cnt[0] == O.score(O.EST_ESSENTIAL, pts, E, 2.5e-3)[0] and cnt[0] >= 0.99 * mask.sum()
+    ids = ctx.get_inliers(E.ravel(), 2.5e-3)
+    assert mask[ids].mean() > 0.95
