@@ -110,6 +110,20 @@ typedef struct {
 
 int usac_gpu_fit(usac_gpu_ctx* ctx, const usac_fit_cfg* cfg, usac_fit_result* results /* [num_problems] */);
 
+/* ---- non-minimal estimation and the final refit ------------------------------------------------------------------ */
+/* replaces Estimator::EstimateModelNonMinimalSample(sample, sample_size, model) (estimator.hpp:22; homography_estimator.hpp:
+ * 67-75 -> dlt/normalized_dlt.cpp:7-23, fundamental/essential -> fundamental/eight_points.cpp:4-100, line2d_estimator.hpp:59-106):
+ * one model from `count` point ids; *ok_out = 0 when the estimation failed. model_out: 9 floats (line: 3). */
+int usac_gpu_estimate_nonminimal(usac_gpu_ctx* ctx, int problem, const int* ids, int count, float* model_out, int* ok_out);
+/* replaces the refit loop that follows the main loop of Ransac::run (ransac.cpp:157-207): up to four rounds of "estimate from
+ * the first `inliers` inliers of the current model, re-score, keep unless it lost more than 20 % or did not improve". */
+typedef struct {
+    float model[9];
+    int inliers;      /* best_score->inlier_number after the loop */
+    int accepted;     /* refits that replaced the model (0..4) */
+} usac_refit_result;
+int usac_gpu_refit(usac_gpu_ctx* ctx, int problem, const float* model_in, int best_inliers, float threshold, usac_refit_result* out);
+
 /* Exchange hook for nranks > 1: called once per round with this rank's packed per-sample scores; must fill `all`
  * with the nranks contributions in rank order (an all-gather). `d_` pointers are device memory on ctx's stream.
  * libusac_gpu's own NCCL binding (usac_gpu_nccl_*) installs one; tests install a host emulation. */

@@ -88,6 +88,10 @@ def lib():
         L.orc_ransac.restype = C.c_int
         L.orc_essential5_candidates.argtypes = [fp, ip, dp, ip]
         L.orc_essential5_candidates.restype = C.c_int
+        L.orc_nonminimal.argtypes = [C.c_int, fp, ip, C.c_int, fp]
+        L.orc_nonminimal.restype = C.c_int
+        L.orc_refit.argtypes = [C.c_int, fp, C.c_int, C.c_float, fp, C.c_int, ip, ip]
+        L.orc_refit.restype = C.c_int
         L.orc_sprt_pool.argtypes = [C.c_uint64, C.c_int, ip]
         L.orc_sprt_pool.restype = None
         _lib = L
@@ -238,6 +242,28 @@ class Sampler:
             self.L.orc_sampler_free(self.h)
         except Exception:
             pass
+
+
+def nonminimal(est, points, ids):
+    """EstimateModelNonMinimalSample on point ids -> model or None"""
+    p, _ = _pts(points)
+    t = np.ascontiguousarray(ids, dtype=np.int32)
+    out = np.zeros(9, np.float32)
+    ok = lib().orc_nonminimal(est, _f(p), _i(t), len(t), _f(out))
+    return out[:3 if est == EST_LINE2D else 9].copy() if ok else None
+
+
+def refit(est, points, model, best_inliers, thr):
+    """ransac.cpp:157-207 -> dict(model, inliers, accepted, ids)"""
+    p, n = _pts(points)
+    m = np.zeros(9, np.float32)
+    w = 3 if est == EST_LINE2D else 9
+    m[:w] = np.asarray(model, np.float32).ravel()[:w]
+    ids = np.zeros(n + 1, np.int32)
+    acc = C.c_int()
+    best = lib().orc_refit(est, _f(p), n, thr, _f(m), int(best_inliers), _i(ids), C.byref(acc))
+    cnt = score(est, points, m[:w], thr)[0]
+    return {"model": m[:w].copy(), "inliers": best, "accepted": acc.value, "ids": ids[:cnt].copy()}
 
 
 def sprt_pool(seed, n):

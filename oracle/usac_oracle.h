@@ -106,6 +106,9 @@ typedef struct {
 } orc_result;
 
 int orc_ransac(const orc_config* cfg, const float* points, int n, orc_result* out);
+/* ---- non-minimal estimation and the final refit (usac_oracle_refit.cpp) ---- */
+int orc_nonminimal(int est, const float* pts, const int* ids, int n, float* model_out);
+int orc_refit(int est, const float* pts, int n_points, float thr, float* model_io, int best_inliers, int* ids_out, int* accepted_out);
 /* the SPRT pool permutation orc_ransac uses for this seed (sprt.hpp:93-107) */
 void orc_sprt_pool(uint64_t seed, int n, int* pool_out);
 

@@ -1,0 +1,200 @@
+/*
+ * usac_oracle_refit.cpp - non-minimal estimation and the final refit loop of the CPU oracle. TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates Estimator::EstimateModelNonMinimalSample for the four estimators
+ *   homography   homography_estimator.hpp:67-75 -> DLt::NormalizedDLT dlt/normalized_dlt.cpp:7-23, DLT dlt/dlt.cpp:55-101,
+ *                GetNormalizingTransformation dlt/normalizing_transformation.cpp:7-112
+ *   fundamental  fundamental_estimator.hpp:65-75 -> EightPointsAlgorithm fundamental/eight_points.cpp:4-100 (no rank-2 step, :47-70)
+ *   essential    essential_estimator.hpp:64-74 (the same eight-point solver, no essential-constraint projection)
+ *   line2d       line2d_estimator.hpp:59-106 (PCA; `sum_xy` is uninitialised there, :70 - zero here)
+ * and the loop that follows the main loop of Ransac::run (usac/ransac/ransac.cpp:157-207): up to four rounds of
+ * "estimate from all inliers, re-score, keep if it did not lose more than 20 % of the inliers and improved".
+ *
+ * Deterministic choices shared with the CUDA path (the reference uses sequential float sums and cv::SVD on A):
+ *  - every sum over points is a "lane sum": lane t of 256 adds elements t, t+256, ... in order, then the 256 partial sums are
+ *    combined by a fixed binary tree (stride 128, 64, ..., 1) - the order a 256-thread block reduces in;
+ *  - the null vector of A is the eigenvector of the smallest eigenvalue of A'A (A in float like the reference, A'A in double),
+ *    found by 12 cyclic Jacobi sweeps;  - H = T2^-1 Hn T1 and F = T2' Fn T1 are evaluated in double, then rounded to float.
+ */
+#include "oracle_internal.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int LANES = 256;
+
+template <class T, class F>
+T lane_sum(int n, F value) {
+    T part[LANES];
+    for (int t = 0; t < LANES; t++) {
+        T acc = 0;
+        for (int i = t; i < n; i += LANES) acc = acc + value(i);
+        part[t] = acc;
+    }
+    for (int s = LANES / 2; s > 0; s >>= 1)
+        for (int t = 0; t < s; t++) part[t] = part[t] + part[t + s];
+    return part[0];
+}
+
+/* eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (row-major, destroyed): cyclic Jacobi, 12 sweeps */
+void smallest_eigenvector(double* S, int n, double* vec) {
+    double V[81];
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; sweep++)
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = S[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (S[q * n + q] - S[p * n + p]) / (2.0 * apq);
+                const double tt = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double t = theta < 0.0 ? -tt : tt;
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                if (!std::isfinite(c) || !std::isfinite(s)) continue;
+                for (int k = 0; k < n; k++) {                     /* columns p, q of S */
+                    const double skp = S[k * n + p], skq = S[k * n + q];
+                    S[k * n + p] = c * skp - s * skq;
+                    S[k * n + q] = s * skp + c * skq;
+                }
+                for (int k = 0; k < n; k++) {                     /* rows p, q of S */
+                    const double spk = S[p * n + k], sqk = S[q * n + k];
+                    S[p * n + k] = c * spk - s * sqk;
+                    S[q * n + k] = s * spk + c * sqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq;
+                    V[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    int best = 0;
+    for (int i = 1; i < n; i++) if (S[i * n + i] < S[best * n + best]) best = i;
+    for (int k = 0; k < n; k++) vec[k] = V[k * n + best];
+}
+
+/* normalizing_transformation.cpp:7-112: T = [s 0 tx; 0 s ty; 0 0 1] per image, floats */
+struct Norm { float s1, t1x, t1y, s2, t2x, t2y; };
+
+bool normalizing(const float* pts, const int* ids, int n, Norm& T) {
+    const float fn = (float)n;
+    float m[4];
+    for (int c = 0; c < 4; c++) m[c] = lane_sum<float>(n, [&](int i) { return pts[4 * (size_t)ids[i] + c]; }) / fn;
+    const float d1 = lane_sum<float>(n, [&](int i) { const float* p = pts + 4 * (size_t)ids[i]; float a = p[0] - m[0], b = p[1] - m[1]; return sqrtf(a * a + b * b); });
+    const float d2 = lane_sum<float>(n, [&](int i) { const float* p = pts + 4 * (size_t)ids[i]; float a = p[2] - m[2], b = p[3] - m[3]; return sqrtf(a * a + b * b); });
+    T.s1 = (float)(M_SQRT2 / (double)(d1 / fn));
+    T.s2 = (float)(M_SQRT2 / (double)(d2 / fn));
+    T.t1x = -m[0] * T.s1; T.t1y = -m[1] * T.s1; T.t2x = -m[2] * T.s2; T.t2y = -m[3] * T.s2;
+    return std::isfinite(T.s1) && std::isfinite(T.s2);
+}
+
+bool nonminimal_two_view(int est, const float* pts, const int* ids, int n, float* out) {
+    Norm T;
+    if (n < 4 || !normalizing(pts, ids, n, T)) return false;
+    auto rows = [&](int i, float r[2][9]) {
+        const float* p = pts + 4 * (size_t)ids[i];
+        const float x1 = T.s1 * p[0] + T.t1x, y1 = T.s1 * p[1] + T.t1y, x2 = T.s2 * p[2] + T.t2x, y2 = T.s2 * p[3] + T.t2y;
+        if (est == ORC_EST_HOMOGRAPHY) {                          /* dlt.cpp:66-88 */
+            const float a[9] = {-x1, -y1, -1, 0, 0, 0, x2 * x1, x2 * y1, x2}, b[9] = {0, 0, 0, -x1, -y1, -1, y2 * x1, y2 * y1, y2};
+            memcpy(r[0], a, sizeof(a)); memcpy(r[1], b, sizeof(b));
+        } else {                                                  /* eight_points.cpp:21-35 */
+            const float a[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+            memcpy(r[0], a, sizeof(a));
+        }
+    };
+    const int nrows = est == ORC_EST_HOMOGRAPHY ? 2 : 1;
+    double S[81];
+    for (int i = 0; i < 9; i++)
+        for (int j = i; j < 9; j++) {
+            const double v = lane_sum<double>(n, [&](int k) {
+                float r[2][9];
+                rows(k, r);
+                double acc = 0;
+                for (int q = 0; q < nrows; q++) { double t = (double)r[q][i] * (double)r[q][j]; acc = acc + t; }
+                return acc;
+            });
+            S[i * 9 + j] = v; S[j * 9 + i] = v;
+        }
+    double h[9];
+    smallest_eigenvector(S, 9, h);
+    double M[9], R[9];
+    const double s1 = T.s1, t1x = T.t1x, t1y = T.t1y, s2 = T.s2, t2x = T.t2x, t2y = T.t2y;
+    for (int i = 0; i < 3; i++) {                                 /* M = Xn * T1 */
+        M[3 * i] = h[3 * i] * s1; M[3 * i + 1] = h[3 * i + 1] * s1;
+        M[3 * i + 2] = (h[3 * i] * t1x + h[3 * i + 1] * t1y) + h[3 * i + 2];
+    }
+    if (est == ORC_EST_HOMOGRAPHY) {                              /* H = T2^-1 M, / h33 (normalized_dlt.cpp:18-20) */
+        const double is2 = 1.0 / s2, ux = -(t2x * is2), uy = -(t2y * is2);
+        for (int j = 0; j < 3; j++) { R[j] = is2 * M[j] + ux * M[6 + j]; R[3 + j] = is2 * M[3 + j] + uy * M[6 + j]; R[6 + j] = M[6 + j]; }
+        const double inv = 1.0 / R[8];
+        for (int i = 0; i < 9; i++) { const double v = R[i] * inv; if (!std::isfinite(v)) return false; out[i] = (float)v; }
+        out[8] = 1.f;
+    } else {                                                      /* F = T2' M, / f33 if |f33| > FLT_EPSILON (eight_points.cpp:72-97) */
+        for (int j = 0; j < 3; j++) { R[j] = s2 * M[j]; R[3 + j] = s2 * M[3 + j]; R[6 + j] = (t2x * M[j] + t2y * M[3 + j]) + M[6 + j]; }
+        const bool scale = std::fabs((float)R[8]) > FLT_EPSILON;
+        const double inv = scale ? 1.0 / R[8] : 1.0;
+        for (int i = 0; i < 9; i++) { const double v = R[i] * inv; if (!std::isfinite(v)) return false; out[i] = (float)v; }
+    }
+    return true;
+}
+
+bool nonminimal_line(const float* pts, const int* ids, int n, float* out) {     /* line2d_estimator.hpp:59-106 */
+    if (n < 2) return false;
+    const float fn = (float)n;
+    const float sx = lane_sum<float>(n, [&](int i) { return pts[2 * (size_t)ids[i]]; });
+    const float sy = lane_sum<float>(n, [&](int i) { return pts[2 * (size_t)ids[i] + 1]; });
+    const float sxy = lane_sum<float>(n, [&](int i) { const float* p = pts + 2 * (size_t)ids[i]; return p[0] * p[1]; });
+    const float sx2 = lane_sum<float>(n, [&](int i) { const float* p = pts + 2 * (size_t)ids[i]; return p[0] * p[0]; });
+    const float sy2 = lane_sum<float>(n, [&](int i) { const float* p = pts + 2 * (size_t)ids[i]; return p[1] * p[1]; });
+    const float mx = sx / fn, my = sy / fn;
+    const float c00 = sx2 - 2 * sx * mx + fn * mx * mx;
+    const float c01 = sxy - sx * my - sy * mx + fn * mx * my;
+    const float c11 = sy2 - 2 * sy * my + fn * my * my;
+    /* eigenvector of the smaller eigenvalue of [[c00 c01][c01 c11]] (the line normal), in double */
+    const double p = c00, q = c01, r = c11;
+    const double half = 0.5 * (p - r), rad = std::sqrt(half * half + q * q), lam = 0.5 * (p + r) - rad;
+    double vx = q, vy = lam - p;
+    const double wx = lam - r, wy = q;
+    if (wx * wx + wy * wy > vx * vx + vy * vy) { vx = wx; vy = wy; }
+    const double nn = std::sqrt(vx * vx + vy * vy);
+    if (!(nn > 0.0)) { vx = 1.0; vy = 0.0; } else { vx = vx / nn; vy = vy / nn; }
+    const float a = (float)vx, b = (float)vy;
+    out[0] = a; out[1] = b; out[2] = -a * mx - b * my;
+    return std::isfinite(out[0]) && std::isfinite(out[1]) && std::isfinite(out[2]);
+}
+
+}  // namespace
+
+extern "C" int orc_nonminimal(int est, const float* pts, const int* ids, int n, float* model_out) {
+    return est == ORC_EST_LINE2D ? nonminimal_line(pts, ids, n, model_out) : nonminimal_two_view(est, pts, ids, n, model_out);
+}
+
+/* ransac.cpp:157-207. model_io: best minimal model in, final model out; returns the final inlier count, the final inlier ids in
+ * ids_out (>= n_points entries) and the number of refits that were accepted in *accepted_out. */
+extern "C" int orc_refit(int est, const float* pts, int n_points, float thr, float* model_io, int best_inliers, int* ids_out, int* accepted_out) {
+    const int w = est == ORC_EST_LINE2D ? 3 : 9;
+    std::vector<int> cur((size_t)n_points);
+    int cnt = 0;
+    float sum = 0;
+    orc_score(est, pts, n_points, model_io, thr, &cnt, &sum, cur.data(), 0, nullptr);          /* quality->getInliers, :163 */
+    int prev = 0, accepted = 0, best = best_inliers;
+    for (int norm = 0; norm < 4; norm++) {
+        float m[9];
+        if (!orc_nonminimal(est, pts, cur.data(), best, m)) break;                               /* :173 uses best_score->inlier_number ids */
+        int c2 = 0;
+        std::vector<int> ids2((size_t)n_points);
+        orc_score(est, pts, n_points, m, thr, &c2, &sum, ids2.data(), 0, nullptr);               /* :180 */
+        if ((float)c2 / best < 0.8f) break;                                                      /* :187 */
+        if ((unsigned)c2 <= (unsigned)prev) break;                                               /* :195 */
+        prev = c2;
+        best = c2; cur.swap(ids2);
+        memcpy(model_io, m, sizeof(float) * w);
+        accepted++;
+    }
+    int fin = 0;
+    orc_score(est, pts, n_points, model_io, thr, &fin, &sum, ids_out, 0, nullptr);               /* :210 */
+    if (accepted_out) *accepted_out = accepted;
+    return best;
+}

@@ -152,6 +152,23 @@ class GpuContext:
                  "best_model_idx": int(r["best_model_idx"]), "rounds": int(r["rounds"]), "evals": int(r["evals"]),
                  "useful_evals": int(r["useful_evals"])} for r in rec]
 
+    def estimate_nonminimal(self, ids, problem=0):
+        """Estimator::EstimateModelNonMinimalSample on a list of point ids -> model (9 or 3 floats) or None."""
+        t = np.ascontiguousarray(ids, dtype=np.int32)
+        w = 3 if self.est == EST_LINE2D else 9
+        m = np.zeros(9, np.float32)
+        ok = C.c_int()
+        self._check(self.L.usac_gpu_estimate_nonminimal(self.h, problem, _ptr(t, C.c_int), len(t), _ptr(m, C.c_float), C.byref(ok)), "estimate_nonminimal")
+        return m[:w].copy() if ok.value else None
+
+    def refit(self, model, best_inliers, threshold, problem=0):
+        """The final refit loop of Ransac::run (ransac.cpp:157-207)."""
+        m = np.ascontiguousarray(model, dtype=np.float32).ravel()
+        r = capi.RefitResult()
+        self._check(self.L.usac_gpu_refit(self.h, problem, _ptr(m, C.c_float), int(best_inliers), threshold, C.byref(r)), "refit")
+        w = 3 if self.est == EST_LINE2D else 9
+        return {"model": np.array(r.model[:w], np.float32), "inliers": r.inliers, "accepted": r.accepted}
+
     def last_timing(self):
         t, s = C.c_float(), C.c_float()
         n, ns = C.c_int(), C.c_int()

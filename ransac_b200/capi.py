@@ -37,6 +37,10 @@ class FitResult(C.Structure):
                 ("evals", C.c_ulonglong), ("useful_evals", C.c_ulonglong)]
 
 
+class RefitResult(C.Structure):
+    _fields_ = [("model", C.c_float * 9), ("inliers", C.c_int), ("accepted", C.c_int)]
+
+
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
@@ -76,6 +80,8 @@ def load():
     L.usac_gpu_sample.argtypes = [vp, C.c_int, C.POINTER(SamplerCfg), C.c_uint64, C.c_int, ip]
     L.usac_gpu_estimate.argtypes = [vp, C.c_int, ip, C.c_int, fp, ip]
     L.usac_gpu_fit.argtypes = [vp, C.POINTER(FitCfg), C.POINTER(FitResult)]
+    L.usac_gpu_estimate_nonminimal.argtypes = [vp, C.c_int, ip, C.c_int, fp, ip]
+    L.usac_gpu_refit.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.POINTER(RefitResult)]
     L.usac_gpu_set_allgather.argtypes = [vp, ALLGATHER_FN, vp]
     L.usac_gpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.usac_gpu_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]

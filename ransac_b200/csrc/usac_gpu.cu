@@ -20,6 +20,7 @@
 #include "pipeline.cuh"
 #include "score.cuh"
 #include "sprt.cuh"
+#include "refit.cuh"
 #include "host_replay.hpp"
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -79,7 +80,8 @@ struct usac_gpu_ctx {
     DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
     // scoring API buffers
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
-    DevBuf<int> d_q_cnt, d_q_ids;
+    DevBuf<int> d_q_cnt, d_q_ids, d_q_ids2, d_q_ok;
+    DevBuf<float> d_q_model2;
     // exchange
     usac_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
@@ -160,7 +162,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
     c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release();
-    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release();
+    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -604,6 +606,90 @@ extern "C" int usac_gpu_get_inliers(usac_gpu_ctx* c, int problem, const float* m
     if (*n_out > 0) CUDA_TRY(c, cudaMemcpyAsync(ids_out, c->d_q_ids.p, sizeof(int) * (*n_out), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Non-minimal estimation and the final refit (ransac.cpp:157-207)
+// ------------------------------------------------------------------------------------------------------------------
+static void launch_nonminimal(usac_gpu_ctx* c, const float* aos, const int* d_ids, int n, float* d_model, int* d_ok) {
+    switch (c->est) {
+        case USAC_EST_LINE2D: nonminimal_kernel<USAC_EST_LINE2D><<<1, REFIT_THREADS, 0, c->stream>>>(aos, d_ids, n, d_model, d_ok); break;
+        case USAC_EST_HOMOGRAPHY: nonminimal_kernel<USAC_EST_HOMOGRAPHY><<<1, REFIT_THREADS, 0, c->stream>>>(aos, d_ids, n, d_model, d_ok); break;
+        case USAC_EST_FUNDAMENTAL: nonminimal_kernel<USAC_EST_FUNDAMENTAL><<<1, REFIT_THREADS, 0, c->stream>>>(aos, d_ids, n, d_model, d_ok); break;
+        default: nonminimal_kernel<USAC_EST_ESSENTIAL><<<1, REFIT_THREADS, 0, c->stream>>>(aos, d_ids, n, d_model, d_ok); break;
+    }
+    c->last_launches++;
+}
+static void launch_inliers(usac_gpu_ctx* c, const float* aos, int n, const float* d_rec, float thr, int* d_ids, int* d_cnt) {
+    switch (c->est) {
+        case USAC_EST_LINE2D: inliers_kernel<USAC_EST_LINE2D><<<1, 1024, 0, c->stream>>>(aos, n, d_rec, thr, d_ids, d_cnt); break;
+        case USAC_EST_HOMOGRAPHY: inliers_kernel<USAC_EST_HOMOGRAPHY><<<1, 1024, 0, c->stream>>>(aos, n, d_rec, thr, d_ids, d_cnt); break;
+        case USAC_EST_FUNDAMENTAL: inliers_kernel<USAC_EST_FUNDAMENTAL><<<1, 1024, 0, c->stream>>>(aos, n, d_rec, thr, d_ids, d_cnt); break;
+        default: inliers_kernel<USAC_EST_ESSENTIAL><<<1, 1024, 0, c->stream>>>(aos, n, d_rec, thr, d_ids, d_cnt); break;
+    }
+    c->last_launches++;
+}
+
+extern "C" int usac_gpu_estimate_nonminimal(usac_gpu_ctx* c, int problem, const int* ids, int count, float* model_out, int* ok_out) {
+    if (!c || problem < 0 || problem >= c->P || !ids || count < 0 || !model_out || !ok_out) return fail(c, USAC_ERR_ARG, "estimate_nonminimal: bad arguments");
+    cudaSetDevice(c->device);
+    const ProblemDesc& d = c->h_prob[problem];
+    for (int i = 0; i < count; i++) if (ids[i] < 0 || ids[i] >= d.n) return fail(c, USAC_ERR_ARG, "estimate_nonminimal: point id out of range");
+    const int dim = usac_point_dim(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    CUDA_TRY(c, c->d_q_ids.ensure((size_t)std::max(count, d.n) + 1));
+    CUDA_TRY(c, c->d_q_model2.ensure(9));
+    CUDA_TRY(c, c->d_q_ok.ensure(1));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q_ids.p, ids, sizeof(int) * count, cudaMemcpyHostToDevice, c->stream));
+    c->last_launches = 0;
+    launch_nonminimal(c, c->d_aos.p + (size_t)d.aos_off * dim, c->d_q_ids.p, count, c->d_q_model2.p, c->d_q_ok.p);
+    CUDA_TRY(c, cudaMemcpyAsync(model_out, c->d_q_model2.p, sizeof(float) * w, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(ok_out, c->d_q_ok.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_refit(usac_gpu_ctx* c, int problem, const float* model_in, int best_inliers, float threshold, usac_refit_result* out) {
+    if (!c || problem < 0 || problem >= c->P || !model_in || !out || !(threshold > 0.f) || best_inliers < 0) return fail(c, USAC_ERR_ARG, "refit: bad arguments");
+    cudaSetDevice(c->device);
+    const ProblemDesc& d = c->h_prob[problem];
+    const int dim = usac_point_dim(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    const float* aos = c->d_aos.p + (size_t)d.aos_off * dim;
+    CUDA_TRY(c, c->d_q_ids.ensure((size_t)d.n + 1));
+    CUDA_TRY(c, c->d_q_ids2.ensure((size_t)d.n + 1));
+    CUDA_TRY(c, c->d_q_model2.ensure(9));
+    CUDA_TRY(c, c->d_q_ok.ensure(1));
+    c->last_launches = 0;
+    int rc = upload_one_record(c, problem, model_in, threshold);
+    if (rc) return rc;
+    int* cur = c->d_q_ids.p;
+    int* alt = c->d_q_ids2.p;
+    launch_inliers(c, aos, d.n, c->d_q_recs.p, threshold, cur, cur + d.n);                 // quality->getInliers(best_model), ransac.cpp:163
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < w; i++) out->model[i] = model_in[i];
+    int best = std::min(best_inliers, d.n), prev = 0;
+    for (int norm = 0; norm < 4; norm++) {
+        float m2[9];
+        int ok = 0, c2 = 0;
+        launch_nonminimal(c, aos, cur, best, c->d_q_model2.p, c->d_q_ok.p);                // :173
+        prepare_models_kernel<<<1, 32, 0, c->stream>>>(c->est, c->d_q_model2.p, 1, w, threshold, c->d_prob.p, problem, c->d_q_recs.p);
+        launch_inliers(c, aos, d.n, c->d_q_recs.p, threshold, alt, alt + d.n);             // :180 (count + ids of the refitted model)
+        c->last_launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(m2, c->d_q_model2.p, sizeof(float) * w, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&ok, c->d_q_ok.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&c2, alt + d.n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaGetLastError());
+        if (!ok) break;
+        if ((float)c2 / best < 0.8f) break;                                                 // :187
+        if ((unsigned)c2 <= (unsigned)prev) break;                                          // :195
+        prev = c2; best = c2;
+        std::swap(cur, alt);
+        for (int i = 0; i < w; i++) out->model[i] = m2[i];
+        out->accepted++;
+    }
+    out->inliers = best;
     return USAC_OK;
 }
 

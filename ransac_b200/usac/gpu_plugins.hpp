@@ -80,7 +80,17 @@ public:
         dev->check(usac_gpu_estimate(dev->ctx, 0, samples, K, models_out, nmodels_out), "usac_gpu_estimate");
         return (unsigned int)K;
     }
-    bool EstimateModelNonMinimalSample(const int* const, unsigned int, Model&) override { return false; }   // SURVEY 8f "next"
+    bool EstimateModelNonMinimalSample(const int* const sample, unsigned int sample_size, Model& model) override {
+        float out[9];
+        int ok = 0;
+        dev->check(usac_gpu_estimate_nonminimal(dev->ctx, 0, sample, (int)sample_size, out, &ok), "usac_gpu_estimate_nonminimal");
+        if (!ok) return false;
+        const bool line = dev->estimator == USAC_EST_LINE2D;
+        cv::Mat d = line ? cv::Mat(1, 3) : cv::Mat(3, 3);
+        for (int k = 0; k < (line ? 3 : 9); k++) d.ptr()[k] = out[k];
+        model.setDescriptor(d);
+        return true;
+    }
     void setModelParameters(const cv::Mat& model) override {
         const int w = dev->estimator == USAC_EST_LINE2D ? 3 : 9;
         for (int k = 0; k < w; k++) model_params[k] = model.ptr()[k];

@@ -1,6 +1,6 @@
 // ransac.hpp - the driver, same construction and accessors as usac/ransac/ransac.hpp:17-118; run() has two forms:
 //   run()            the GPU hypothesis batch: the whole loop of ransac.cpp:58-139 in usac_gpu_fit (rounds of K samples, one
-//                    host sync per round), then the final inlier list;
+//                    host sync per round), the refit loop of ransac.cpp:157-207 in usac_gpu_refit, then the final inlier list;
 //   run_sequential() the reference's one-hypothesis-at-a-time loop (ransac.cpp:58-139) over the virtual plugin interfaces,
 //                    each call forwarding to the C ABI - the same results, used to show the drop-in at plugin granularity.
 #pragma once
@@ -53,7 +53,10 @@ public:
         cfg.threshold = model->threshold; cfg.confidence = model->desired_prob; cfg.max_iterations = model->max_iterations;
         cfg.sprt = model->sprt; cfg.round_size = model->gpu_round_size; cfg.rank = 0; cfg.nranks = 1;
         device->check(usac_gpu_fit(device->ctx, &cfg, &last_fit), "usac_gpu_fit");
-        finish(last_fit.model, last_fit.inliers, last_fit.iterations, t0);
+        if (last_fit.inliers <= 0) throw std::runtime_error("Ransac: best score is 0");           // ransac.cpp:143-147
+        usac_refit_result rf{};                                                                   // ransac.cpp:157-207 on the device
+        device->check(usac_gpu_refit(device->ctx, 0, last_fit.model, last_fit.inliers, model->threshold, &rf), "usac_gpu_refit");
+        finish(rf.model, rf.inliers, last_fit.iterations, t0);
     }
 
     void run_sequential() {
@@ -84,7 +87,24 @@ public:
         last_fit.inliers = best.inlier_number; last_fit.score = best.score; last_fit.iterations = iters;
         const cv::Mat d = best_model.returnDescriptor();
         for (int k = 0; k < d.rows * d.cols; k++) last_fit.model[k] = d.ptr()[k];
-        finish(last_fit.model, best.inlier_number, iters, t0);
+        // the refit loop of ransac.cpp:157-207 over the virtual plugin calls
+        std::vector<int> max_inliers(points_size);
+        quality->getInliers(best_model.returnDescriptor(), max_inliers.data());
+        Model non_minimal(model);
+        unsigned int previous = 0;
+        for (unsigned int norm = 0; norm < 4; norm++) {
+            if (!estimator->EstimateModelNonMinimalSample(max_inliers.data(), (unsigned int)best.inlier_number, non_minimal)) break;
+            quality->getNumberInliers(&cur, non_minimal.returnDescriptor(), model->threshold, true, max_inliers.data());
+            if ((float)cur.inlier_number / best.inlier_number < 0.8) break;
+            if ((unsigned int)cur.inlier_number <= previous) break;
+            previous = (unsigned int)cur.inlier_number;
+            best.copyFrom(&cur);
+            best_model.setDescriptor(non_minimal.returnDescriptor());
+        }
+        const cv::Mat fd = best_model.returnDescriptor();
+        float params[9] = {0};
+        for (int k = 0; k < fd.rows * fd.cols; k++) params[k] = fd.ptr()[k];
+        finish(params, best.inlier_number, iters, t0);
     }
 
 private:

@@ -413,3 +413,26 @@ def test_line_and_essential_known_geometry(ctx):
     assert cnt[0] == O.score(O.EST_ESSENTIAL, pts, E, 2.5e-3)[0] and cnt[0] >= 0.99 * mask.sum()
     ids = ctx.get_inliers(E.ravel(), 2.5e-3)
     assert mask[ids].mean() > 0.95
+
+
+# ---- non-minimal estimation and the final refit (first "next" row) -----------------------------------------
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_nonminimal_and_refit_match_oracle(ctx, cfg):
+    pts, gt, mask = gen.make(cfg) if cfg != 4 else gen.essential(n=5000, inlier_ratio=0.4, seed=8)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    ctx.set_points(est, pts)
+    g = np.random.default_rng(cfg)
+    inl = np.where(mask)[0]
+    for count in (8, 37, 256, 257, len(inl)):
+        ids = g.choice(inl, min(count, len(inl)), replace=False).astype(np.int32)
+        a, b = ctx.estimate_nonminimal(ids), O.nonminimal(est, pts, ids)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(bits(a), bits(b)), (count, a, b)
+    r = ctx.fit(thr, conf, 2000, seed=2)[0]
+    rf = ctx.refit(r["model"], r["inliers"], thr)
+    ref = O.refit(est, pts, r["model"], r["inliers"], thr)
+    assert rf["inliers"] == ref["inliers"] and rf["accepted"] == ref["accepted"]
+    assert np.array_equal(bits(rf["model"]), bits(ref["model"]))
+    assert np.array_equal(ctx.get_inliers(rf["model"], thr), ref["ids"])

@@ -85,6 +85,7 @@ def test_fused_equals_sequential_equals_oracle(harness, tmp_path, cfg, est_name,
     assert np.array_equal(f["model"], s["model"])
     kw = dict(sampler=O.SAMPLER_NAPSAC, neighbors=O.NEIGH_GRID, cell_size=50) if sampler == "napsac" else {}
     ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, seed=5, **kw)
-    assert f["iterations"] == ref["iterations"] and f["inliers"] == ref["inliers"]
-    assert np.array_equal(f["model"], np.asarray(ref["model"], np.float32).view(np.uint32))
-    assert f["hash"] == fnv(O.score(est, pts, ref["model"], thr, want_inliers=True)[3])
+    fin = O.refit(est, pts, ref["model"], ref["inliers"], thr)       # Ransac::run = main loop + refit loop (ransac.cpp:157-207)
+    assert f["iterations"] == ref["iterations"] and f["inliers"] == fin["inliers"]
+    assert np.array_equal(f["model"], np.asarray(fin["model"], np.float32).view(np.uint32))
+    assert f["hash"] == fnv(fin["ids"][:fin["inliers"]])

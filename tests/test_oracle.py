@@ -340,3 +340,32 @@ def test_essential5_identities_and_selection():
             found += 1
             assert valid[int(np.argmin(d))]                           # the true E passes the cheirality vote
     assert found >= 95
+
+
+# ---- non-minimal estimation and the final refit (ransac.cpp:157-207) ---------------------------------------------------------
+def test_nonminimal_recovers_ground_truth_on_noise_free_inliers():
+    from ransac_b200 import generator as gen
+
+    def dist(a, b):
+        a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+        a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+        return min(np.abs(a - b).max(), np.abs(a + b).max())
+    for est, make, tol in ((O.EST_HOMOGRAPHY, gen.homography, 1e-7), (O.EST_FUNDAMENTAL, gen.fundamental, 1e-6), (O.EST_ESSENTIAL, gen.essential, 1e-5)):
+        pts, gt, mask = make(n=3000, noise=0.0, seed=3)
+        m = O.nonminimal(est, pts, np.where(mask)[0])
+        assert m is not None and dist(m, gt) < tol
+    pts, line, mask = gen.line2d(n=2000, noise=0.0, seed=3)
+    m = O.nonminimal(O.EST_LINE2D, pts, np.where(mask)[0])
+    assert dist(m[:2], line[:2]) < 1e-5 and abs(abs(m[2]) - abs(line[2])) < 1e-2
+    assert O.nonminimal(O.EST_HOMOGRAPHY, pts.repeat(2, axis=1), np.arange(3)) is None     # fewer than four points
+
+
+def test_refit_loop_improves_or_keeps_the_minimal_model():
+    from ransac_b200 import generator as gen
+    for seed in (4, 5, 6):
+        pts, H, mask = gen.homography(n=4000, seed=seed)
+        r = O.ransac(pts, O.EST_HOMOGRAPHY, seed=1)
+        rf = O.refit(O.EST_HOMOGRAPHY, pts, r["model"], r["inliers"], 2.0)
+        assert rf["inliers"] >= r["inliers"] and 0 <= rf["accepted"] <= 4
+        assert len(rf["ids"]) == O.score(O.EST_HOMOGRAPHY, pts, rf["model"], 2.0)[0]
+        assert rf["inliers"] > 0.97 * mask.sum()                      # noise 0.5 px, threshold 2 px: essentially every true inlier
