@@ -354,7 +354,8 @@ def run_c5(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     rank, world = D.init("nccl")
-    n, K = args.c5_points, 2048
+    n = args.c5_points
+    K = args.c5_round if args.c5_round > 0 else max(2048, 1024 * world)   # >= 1024 samples per rank and round (results do not depend on K)
     pts = gen.make(5, n=n)[0]
     host = torch.from_numpy(pts).pin_memory()
     ctx = GpuContext(local)
@@ -452,6 +453,7 @@ def main():
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
+    ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 workload (0 = max(2048, 1024 x ranks))")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = max(args.warmup, 1)
