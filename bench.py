@@ -216,7 +216,7 @@ def run_native(args):
     # e2e: the public API with HOST buffers. Two contexts (two streams, two host threads) each own half of the step's image
     # pairs, so that the host->device copy of one half overlaps the fit of the other (the copy engine and the SMs run
     # concurrently); every step still uploads every point set and reads every result back.
-    n_pipe = 2 if B >= 2 else 1
+    n_pipe = max(1, min(args.pipe, B))
     halves = [(i * B // n_pipe, (i + 1) * B // n_pipe) for i in range(n_pipe)]
     pipe_ctx, pipe_streams = [], []
     for _ in range(n_pipe):
@@ -451,6 +451,7 @@ def main():
     ap.add_argument("--round-size", type=int, default=128, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
+    ap.add_argument("--pipe", type=int, default=2, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
     ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 workload (0 = max(2048, 1024 x ranks))")

@@ -92,6 +92,9 @@ typedef struct {
     /* multi-GPU hypothesis sharding (one process per GPU): this rank scores samples j with j % nranks == rank of
      * every round and the per-sample scores are exchanged with one all-gather per round */
     int rank, nranks;
+    /* model.hpp:13,25: LocOpt - 0 NullLO, 1 InItLORsc (inner + iterative LO), 2 InItFLORsc (limited samples); runs on every new
+     * best model (ransac.cpp:108-110; local_optimization/inner_local_optimization.hpp:74-133, iterative_local_optimization.hpp) */
+    int lo;
 } usac_fit_cfg;
 
 typedef struct {
@@ -106,6 +109,7 @@ typedef struct {
     unsigned long long evals;    /* hypothesis x point evaluations executed on this GPU (whole rounds) */
     unsigned long long useful_evals; /* the part of `evals` the sequential loop of ransac.cpp:58-139 would also have
                                         executed: models of the samples up to the one that ended the loop */
+    unsigned lo_inner_iters, lo_iterative_iters;   /* RansacOutput::getLOInnerIters / getLOIterativeIters */
 } usac_fit_result;
 
 int usac_gpu_fit(usac_gpu_ctx* ctx, const usac_fit_cfg* cfg, usac_fit_result* results /* [num_problems] */);

@@ -33,13 +33,13 @@ class Config(C.Structure):
                 ("confidence", C.c_float), ("max_iterations", C.c_uint), ("sprt", C.c_int), ("batch", C.c_int),
                 ("neighbors", C.c_int), ("knn", C.c_int), ("cell_size", C.c_int), ("seed", C.c_uint64),
                 ("sample_table", C.POINTER(C.c_int)), ("sample_table_rows", C.c_uint),
-                ("knn_table", C.POINTER(C.c_int))]
+                ("knn_table", C.POINTER(C.c_int)), ("lo", C.c_int)]
 
 
 class Result(C.Structure):
     _fields_ = [("model", C.c_float * 9), ("inliers", C.c_int), ("score", C.c_float), ("iterations", C.c_uint),
                 ("samples_drawn", C.c_uint), ("best_hyp", C.c_longlong), ("best_model_idx", C.c_int),
-                ("evals", C.c_ulonglong), ("models_scored", C.c_uint)]
+                ("evals", C.c_ulonglong), ("models_scored", C.c_uint), ("lo_inner", C.c_uint), ("lo_iterative", C.c_uint)]
 
 
 _lib = None
@@ -273,12 +273,13 @@ def sprt_pool(seed, n):
 
 
 def ransac(points, est, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, threshold=2.0, confidence=0.95, max_iterations=10000,
-           sprt=False, batch=0, seed=1, neighbors=NEIGH_NONE, knn=5, cell_size=50, sample_table=None, knn_table=None):
+           sprt=False, batch=0, seed=1, neighbors=NEIGH_NONE, knn=5, cell_size=50, sample_table=None, knn_table=None, lo=0):
     p, n = _pts(points)
     cfg = Config()
     cfg.estimator, cfg.sampler, cfg.rng = est, sampler, rng
     cfg.threshold, cfg.confidence, cfg.max_iterations = threshold, confidence, max_iterations
     cfg.sprt, cfg.batch, cfg.neighbors, cfg.knn, cfg.cell_size, cfg.seed = int(sprt), batch, neighbors, knn, cell_size, seed
+    cfg.lo = lo
     keep = []
     if sample_table is not None:
         t = np.ascontiguousarray(sample_table, dtype=np.int32)
@@ -293,4 +294,5 @@ def ransac(points, est, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, threshold=2.0, 
     w = 3 if est == EST_LINE2D else 9
     return {"rc": rc, "model": np.array(res.model[:w], np.float32), "inliers": res.inliers, "score": res.score,
             "iterations": res.iterations, "samples_drawn": res.samples_drawn, "best_hyp": res.best_hyp,
-            "best_model_idx": res.best_model_idx, "evals": res.evals, "models_scored": res.models_scored}
+            "best_model_idx": res.best_model_idx, "evals": res.evals, "models_scored": res.models_scored,
+            "lo_inner": res.lo_inner, "lo_iterative": res.lo_iterative}

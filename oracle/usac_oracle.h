@@ -91,6 +91,7 @@ typedef struct {
     const int* sample_table;  /* rng==ORC_RNG_TABLE: K_total x m */
     unsigned sample_table_rows;
     const int* knn_table;     /* neighbors==KNN: n x knn */
+    int lo;                   /* LocOpt: 0 none, 1 InItLORsc, 2 InItFLORsc (model.hpp:13; inner_local_optimization.hpp) */
 } orc_config;
 
 typedef struct {
@@ -103,12 +104,19 @@ typedef struct {
     int best_model_idx;       /* which root of that sample */
     unsigned long long evals; /* GetError calls executed */
     unsigned models_scored;
+    unsigned lo_inner, lo_iterative;   /* RansacOutput::getLOInnerIters / getLOIterativeIters */
 } orc_result;
 
 int orc_ransac(const orc_config* cfg, const float* points, int n, orc_result* out);
 /* ---- non-minimal estimation and the final refit (usac_oracle_refit.cpp) ---- */
 int orc_nonminimal(int est, const float* pts, const int* ids, int n, float* model_out);
 int orc_refit(int est, const float* pts, int n_points, float thr, float* model_io, int best_inliers, int* ids_out, int* accepted_out);
+/* LO-RANSAC (usac_oracle_refit.cpp) */
+typedef struct orc_lo orc_lo;
+orc_lo* orc_lo_new(int est, const float* pts, int n, float theta, int kind, uint64_t seed);
+void orc_lo_free(orc_lo*);
+void orc_lo_counters(orc_lo*, unsigned* inner, unsigned* iterative, unsigned long long* calls);
+void orc_lo_get_model_score(orc_lo*, float* best_model, int* best_inl_io, float* best_sum_io);
 /* the SPRT pool permutation orc_ransac uses for this seed (sprt.hpp:93-107) */
 void orc_sprt_pool(uint64_t seed, int n, int* pool_out);
 

@@ -313,7 +313,12 @@ extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc
         }
         hyp++;
     };
-    auto on_new_best = [&](const float* model, int inl, float score, long long h, int mi) {
+    orc_lo* lo = cfg->lo ? orc_lo_new(est, points, n, cfg->threshold, cfg->lo, cfg->seed) : nullptr;
+    auto on_new_best = [&](const float* model_in, int inl, float score, long long h, int mi) {
+        float lo_model[9] = {0};
+        memcpy(lo_model, model_in, sizeof(float) * msize);
+        if (lo) orc_lo_get_model_score(lo, lo_model, &inl, &score);                 /* ransac.cpp:108-110 */
+        const float* model = lo_model;
         best_inl = inl; best_score = score;
         memcpy(best_model, model, sizeof(float) * msize);
         out->best_hyp = h; out->best_model_idx = mi;
@@ -436,6 +441,7 @@ extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc
     out->samples_drawn = (unsigned)hyp;
     out->evals = evals;
     out->models_scored = models_scored;
+    if (lo) { unsigned a, b; unsigned long long c; orc_lo_counters(lo, &a, &b, &c); out->lo_inner = a; out->lo_iterative = b; orc_lo_free(lo); }
     orc_sampler_free(sampler);
     return best_inl > 0 ? 0 : 1;   /* ransac.cpp:143-147: the reference exits(111) when nothing was found */
 }

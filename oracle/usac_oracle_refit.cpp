@@ -198,3 +198,146 @@ extern "C" int orc_refit(int est, const float* pts, int n_points, float thr, flo
     if (accepted_out) *accepted_out = accepted;
     return best;
 }
+
+/* ======================================================================================================
+ * LO-RANSAC: inner + iterative local optimisation (local_optimization/inner_local_optimization.hpp:74-133,
+ * iterative_local_optimization.hpp:61-135), kinds InItLORsc (unlimited) and InItFLORsc (limited samples).
+ * Deterministic choices shared with the CUDA path: the random subsets come from Philox keyed by (seed, call counter) instead of
+ * mt19937 seeded from random_device (uniform_random_generator.hpp:11-47); error sums are lane sums over 1024 lanes.
+ * Quirks kept: lo_model->threshold is multiplied on every inner iteration, also after a `continue` that skipped the iterative
+ * stage (inner_local_optimization.hpp:101-105); the threshold of a failed iterative stage is reset, a successful one ends at
+ * theta again only up to float rounding.
+ * ====================================================================================================== */
+extern "C" void orc_philox_unique(uint64_t seed, uint64_t hyp_id, uint32_t stream, int n, int m, int* out);
+
+namespace {
+const int SLANES = 1024;
+
+struct LoState {
+    int est, n, m, kind, sample_limit, inner_iters, iter_iters, mult;
+    const float* pts;
+    float theta, lo_thr, step;
+    uint64_t seed, calls;
+    std::vector<int> lo_inliers, max_inliers;
+    unsigned inner_done, iterative_done;
+};
+
+/* Quality::getNumberInliers(score, model, thr, get_inliers=true, ids): strict errors, ascending ids, lane-summed errors */
+void lo_score(const LoState& L, const float* model, float thr, int& cnt, float& sum, std::vector<int>& ids) {
+    ErrFn f;
+    f.set(L.est, model);
+    ids.resize((size_t)L.n);
+    cnt = 0;
+    float part[SLANES];
+    for (int t = 0; t < SLANES; t++) part[t] = 0.f;
+    for (int i = 0; i < L.n; i++) {
+        const float e = f(L.pts, (unsigned)i);
+        if (e < thr) { ids[cnt++] = i; part[i % SLANES] = part[i % SLANES] + e; }
+    }
+    for (int s = SLANES / 2; s > 0; s >>= 1)
+        for (int t = 0; t < s; t++) part[t] = part[t] + part[t + s];
+    sum = part[0];
+}
+
+/* draws 14 distinct positions in [0, count-1] with generalised philox draws (two blocks of 8) */
+void lo_random_subset(LoState& L, int count, const std::vector<int>& from, int* sample) {
+    int pos[16];
+    /* sample_limit <= 16: first 8 from the whole range, the rest from the remaining indices, mapped past the first 8 */
+    const int k = L.sample_limit;
+    int a[8], b[8];
+    orc_philox_unique(L.seed, L.calls, 7, count, k < 8 ? k : 8, a);
+    for (int i = 0; i < (k < 8 ? k : 8); i++) pos[i] = a[i];
+    if (k > 8) {
+        orc_philox_unique(L.seed, L.calls, 8, count - 8, k - 8, b);
+        int sorted[8];
+        for (int i = 0; i < 8; i++) sorted[i] = a[i];
+        for (int i = 1; i < 8; i++) { int v = sorted[i], j = i - 1; while (j >= 0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; } sorted[j + 1] = v; }
+        for (int i = 0; i < k - 8; i++) {
+            int v = b[i];
+            for (int q = 0; q < 8; q++) if (v >= sorted[q]) v++;
+            pos[8 + i] = v;
+        }
+    }
+    L.calls++;
+    for (int i = 0; i < k; i++) sample[i] = from[pos[i]];
+}
+
+bool bigger2(int ia, float sa, int ib, float sb) { return ia > ib || (ia == ib && sa > sb); }
+
+bool lo_iterative(LoState& L, int& lo_inl, float& lo_sum, float* lo_model, int best_inl, float best_sum) {
+    int sample[16];
+    for (int it = 0; it < L.iter_iters; it++) {
+        L.lo_thr -= L.step;
+        if (lo_inl <= L.m) break;
+        if (L.kind == 2) {                                            /* GetScoreLimited, iterative_local_optimization.hpp:61-100 */
+            if (lo_inl > L.sample_limit) {
+                lo_random_subset(L, lo_inl, L.lo_inliers, sample);
+                if (!orc_nonminimal(L.est, L.pts, sample, L.sample_limit, lo_model)) continue;
+            } else if (!orc_nonminimal(L.est, L.pts, L.lo_inliers.data(), lo_inl, lo_model)) break;
+            lo_score(L, lo_model, L.lo_thr, lo_inl, lo_sum, L.lo_inliers);
+        } else {                                                      /* GetScoreUnlimited, :102-135 */
+            if (!orc_nonminimal(L.est, L.pts, L.lo_inliers.data(), lo_inl, lo_model)) break;
+            lo_score(L, lo_model, L.lo_thr, lo_inl, lo_sum, L.lo_inliers);
+            if (bigger2(best_inl, best_sum, lo_inl, lo_sum)) break;
+        }
+        L.iterative_done++;
+    }
+    bool fail = false;
+    if (fabsf(L.lo_thr - L.theta) > 0.00001) { fail = true; L.lo_thr = L.theta; }
+    return fail;
+}
+}  // namespace
+
+struct orc_lo { LoState L; };   /* opaque handle of usac_oracle.h */
+
+extern "C" orc_lo* orc_lo_new(int est, const float* pts, int n, float theta, int kind, uint64_t seed) {
+    orc_lo* o = new orc_lo;
+    LoState& L = o->L;
+    L.est = est; L.pts = pts; L.n = n; L.kind = kind; L.seed = seed; L.calls = 0;
+    L.m = est == ORC_EST_LINE2D ? 2 : est == ORC_EST_HOMOGRAPHY ? 4 : est == ORC_EST_FUNDAMENTAL ? 7 : 5;
+    L.sample_limit = 14; L.inner_iters = 20; L.iter_iters = 4; L.mult = 10;       /* model.hpp:26-29 */
+    L.theta = theta; L.lo_thr = theta;
+    L.step = (theta * (unsigned)L.mult - theta) / (unsigned)L.iter_iters;          /* iterative_local_optimization.hpp:43 */
+    L.inner_done = L.iterative_done = 0;
+    return o;
+}
+extern "C" void orc_lo_free(orc_lo* o) { delete o; }
+extern "C" void orc_lo_counters(orc_lo* o, unsigned* inner, unsigned* iterative, unsigned long long* calls) {
+    *inner = o->L.inner_done; *iterative = o->L.iterative_done; *calls = o->L.calls;
+}
+
+/* InnerLocalOptimization::GetModelScore, inner_local_optimization.hpp:74-133; model/score updated in place */
+extern "C" void orc_lo_get_model_score(orc_lo* o, float* best_model, int* best_inl_io, float* best_sum_io) {
+    LoState& L = o->L;
+    int best_inl = *best_inl_io;
+    float best_sum = *best_sum_io;
+    if (best_inl < 12) return;
+    const int w = 9;
+    int cnt;
+    float sum;
+    lo_score(L, best_model, L.theta, cnt, sum, L.max_inliers);                       /* quality->getInliers(best_model), :79 */
+    float lo_model[9];
+    int sample[16];
+    for (int it = 0; it < L.inner_iters; it++) {
+        if (best_inl > L.sample_limit) {
+            lo_random_subset(L, best_inl, L.max_inliers, sample);
+            if (!orc_nonminimal(L.est, L.pts, sample, L.sample_limit, lo_model)) continue;
+        } else if (!orc_nonminimal(L.est, L.pts, L.max_inliers.data(), best_inl, lo_model)) {
+            break;
+        }
+        L.lo_thr = (unsigned)L.mult * L.lo_thr;                                      /* :101 */
+        int lo_inl;
+        float lo_sum;
+        lo_score(L, lo_model, L.lo_thr, lo_inl, lo_sum, L.lo_inliers);
+        if (lo_inl <= L.m) continue;                                                 /* :105 */
+        const bool fail = lo_iterative(L, lo_inl, lo_sum, lo_model, best_inl, best_sum);
+        if (!fail && bigger2(lo_inl, lo_sum, best_inl, best_sum)) {
+            memcpy(best_model, lo_model, sizeof(float) * w);
+            best_inl = lo_inl; best_sum = lo_sum;
+            L.max_inliers.resize((size_t)L.n);
+            for (int i = 0; i < lo_inl; i++) L.max_inliers[i] = L.lo_inliers[i];
+        }
+        L.inner_done++;
+    }
+    *best_inl_io = best_inl; *best_sum_io = best_sum;
+}

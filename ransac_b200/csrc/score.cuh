@@ -385,3 +385,50 @@ __global__ void __launch_bounds__(1024) inliers_kernel(const float* __restrict__
     }
     if (threadIdx.x == 0) *count = base;
 }
+
+// Quality::getNumberInliers(score, model, thr, get_inliers = true, ids) (quality.hpp:60-101) for local optimisation: ids in
+// ascending order, count, and the error sum as a lane sum (thread t adds the errors of its inliers t, t+1024, ... in order,
+// then a fixed binary tree over the 1024 lanes) - the order the parity tests' host restatement uses. stat = {count, sum bits}.
+template <int EST>
+__global__ void __launch_bounds__(1024) inliers_sum_kernel(const float* __restrict__ aos, int n, const float* __restrict__ rec, float thr,
+                                                           int* __restrict__ ids, int* __restrict__ stat) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    __shared__ float part[1024];
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + threadIdx.x;
+        bool in = false;
+        if (i < n) {
+            float e;
+            if (EST == USAC_EST_LINE2D) { const float2 p = reinterpret_cast<const float2*>(aos)[i]; e = strict_error<EST>(rec, p.x, p.y, 0.f, 0.f); }
+            else { const float4 p = reinterpret_cast<const float4*>(aos)[i]; e = strict_error<EST>(rec, p.x, p.y, p.z, p.w); }
+            in = e < thr;
+            if (in) acc = __fadd_rn(acc, e);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; w++) { const int v = warp_tot[w]; if (w < warp) before += v; total += v; }
+        if (in) ids[base + before + __popc(bal & ((1u << lane) - 1))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] = __fadd_rn(part[threadIdx.x], part[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stat[0] = base; stat[1] = __float_as_int(part[0]); }
+}
+
+__global__ void gather_ids_kernel(const int* __restrict__ from, const int* __restrict__ pos, int k, int* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i < k) out[i] = from[pos[i]];
+}

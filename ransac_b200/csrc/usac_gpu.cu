@@ -80,7 +80,7 @@ struct usac_gpu_ctx {
     DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
     // scoring API buffers
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
-    DevBuf<int> d_q_cnt, d_q_ids, d_q_ids2, d_q_ok;
+    DevBuf<int> d_q_cnt, d_q_ids, d_q_ids2, d_q_ok, d_lo_ids_a, d_lo_ids_b, d_lo_small;
     DevBuf<float> d_q_model2;
     // exchange
     usac_allgather_fn allgather = nullptr;
@@ -162,7 +162,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
     c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release();
-    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release();
+    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -887,6 +887,155 @@ static void launch_winner_est(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
     c->last_launches++;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// LO-RANSAC: InnerLocalOptimization::GetModelScore + IterativeLocalOptimization (local_optimization/
+// inner_local_optimization.hpp:74-133, iterative_local_optimization.hpp:61-135), kinds InItLORsc (1) and InItFLORsc (2).
+// The control flow runs on the host inside the round replay; every fit / scoring step is a device call
+// (nonminimal_kernel, inliers_sum_kernel). Random subsets: Philox keyed by (seed, call counter) in place of mt19937
+// seeded from random_device (uniform_random_generator.hpp:11-47).
+// ------------------------------------------------------------------------------------------------------------------
+struct LoRunner {
+    usac_gpu_ctx* c;
+    int problem, kind, m, n, w, dim;
+    int sample_limit = 14, inner_iters = 20, iter_iters = 4, mult = 10;   // model.hpp:26-29
+    float theta, lo_thr, step;
+    uint64_t seed, calls = 0;
+    unsigned inner_done = 0, iterative_done = 0;
+    const float* aos;
+    int *A, *B, *d_sample, *d_pos, *d_stat, *d_ok;
+    float* d_model;
+
+    int init(usac_gpu_ctx* ctx, int problem_, int kind_, float threshold, uint64_t seed_) {
+        c = ctx; problem = problem_; kind = kind_; seed = seed_;
+        const ProblemDesc& d = c->h_prob[problem];
+        n = d.n; m = usac_sample_size(c->est); w = c->est == USAC_EST_LINE2D ? 3 : 9; dim = usac_point_dim(c->est);
+        theta = threshold; lo_thr = threshold;
+        step = (threshold * (unsigned)mult - threshold) / (unsigned)iter_iters;        // iterative_local_optimization.hpp:43
+        CUDA_TRY(c, c->d_lo_ids_a.ensure((size_t)n));
+        CUDA_TRY(c, c->d_lo_ids_b.ensure((size_t)n));
+        CUDA_TRY(c, c->d_lo_small.ensure(64));
+        CUDA_TRY(c, c->d_q_model2.ensure(9));
+        CUDA_TRY(c, c->d_q_models.ensure(9));
+        CUDA_TRY(c, c->d_q_recs.ensure(USAC_REC_STRIDE));
+        aos = c->d_aos.p + (size_t)d.aos_off * dim;
+        A = c->d_lo_ids_a.p; B = c->d_lo_ids_b.p;
+        d_sample = c->d_lo_small.p; d_pos = c->d_lo_small.p + 16; d_stat = c->d_lo_small.p + 32; d_ok = c->d_lo_small.p + 40;
+        d_model = c->d_q_model2.p;
+        return USAC_OK;
+    }
+    // Quality::getNumberInliers(.., thr, get_inliers = true, ids): device model -> ids, count, lane-summed errors
+    int score(const float* d_mod, float thr, int* ids, int& cnt, float& sum) {
+        prepare_models_kernel<<<1, 32, 0, c->stream>>>(c->est, d_mod, 1, w, thr, c->d_prob.p, problem, c->d_q_recs.p);
+        switch (c->est) {
+            case USAC_EST_HOMOGRAPHY: inliers_sum_kernel<USAC_EST_HOMOGRAPHY><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
+            case USAC_EST_FUNDAMENTAL: inliers_sum_kernel<USAC_EST_FUNDAMENTAL><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
+            case USAC_EST_ESSENTIAL: inliers_sum_kernel<USAC_EST_ESSENTIAL><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
+            default: inliers_sum_kernel<USAC_EST_LINE2D><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
+        }
+        c->last_launches += 2;
+        int st[2];
+        CUDA_TRY(c, cudaMemcpyAsync(st, d_stat, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        cnt = st[0]; memcpy(&sum, &st[1], 4);
+        return USAC_OK;
+    }
+    // Estimator::LeastSquaresFitting on device ids -> d_model; ok
+    int fit_ids(const int* ids, int count, bool& ok) {
+        launch_nonminimal(c, aos, ids, count, d_model, d_ok);
+        int h = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&h, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        ok = h != 0;
+        return USAC_OK;
+    }
+    // 14 distinct positions in [0, count): two Philox draws (8 + 6), the second mapped past the first
+    int fit_random_subset(const int* from, int count, bool& ok) {
+        int pos[16], a[8], b[8];
+        const int k = sample_limit;
+        philox_unique(seed, calls, 7, count, std::min(k, 8), a);
+        for (int i = 0; i < std::min(k, 8); i++) pos[i] = a[i];
+        if (k > 8) {
+            philox_unique(seed, calls, 8, count - 8, k - 8, b);
+            int sorted[8];
+            for (int i = 0; i < 8; i++) sorted[i] = a[i];
+            std::sort(sorted, sorted + 8);
+            for (int i = 0; i < k - 8; i++) {
+                int v = b[i];
+                for (int q = 0; q < 8; q++) if (v >= sorted[q]) v++;
+                pos[8 + i] = v;
+            }
+        }
+        calls++;
+        CUDA_TRY(c, cudaMemcpyAsync(d_pos, pos, sizeof(int) * k, cudaMemcpyHostToDevice, c->stream));
+        gather_ids_kernel<<<1, 32, 0, c->stream>>>(from, d_pos, k, d_sample);
+        c->last_launches++;
+        return fit_ids(d_sample, k, ok);
+    }
+    static bool bigger(int ia, float sa, int ib, float sb) { return ia > ib || (ia == ib && sa > sb); }
+
+    int iterative(int& lo_inl, float& lo_sum, int best_inl, float best_sum, bool& fail) {
+        for (int it = 0; it < iter_iters; it++) {
+            lo_thr -= step;
+            if (lo_inl <= m) break;
+            bool ok = false;
+            int rc;
+            if (kind == 2) {                                              // GetScoreLimited
+                if (lo_inl > sample_limit) {
+                    if ((rc = fit_random_subset(B, lo_inl, ok))) return rc;
+                    if (!ok) continue;
+                } else {
+                    if ((rc = fit_ids(B, lo_inl, ok))) return rc;
+                    if (!ok) break;
+                }
+                if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
+            } else {                                                      // GetScoreUnlimited
+                if ((rc = fit_ids(B, lo_inl, ok))) return rc;
+                if (!ok) break;
+                if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
+                if (bigger(best_inl, best_sum, lo_inl, lo_sum)) break;
+            }
+            iterative_done++;
+        }
+        fail = false;
+        if (fabsf(lo_thr - theta) > 0.00001) { fail = true; lo_thr = theta; }
+        return USAC_OK;
+    }
+
+    // InnerLocalOptimization::GetModelScore: model / score updated in place
+    int get_model_score(float* best_model, int& best_inl, float& best_sum) {
+        if (best_inl < 12) return USAC_OK;
+        int rc, cnt;
+        float sum;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, best_model, sizeof(float) * w, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = score(c->d_q_models.p, theta, A, cnt, sum))) return rc;      // quality->getInliers(best_model)
+        for (int it = 0; it < inner_iters; it++) {
+            bool ok = false;
+            if (best_inl > sample_limit) {
+                if ((rc = fit_random_subset(A, best_inl, ok))) return rc;
+                if (!ok) continue;
+            } else {
+                if ((rc = fit_ids(A, best_inl, ok))) return rc;
+                if (!ok) break;
+            }
+            lo_thr = (unsigned)mult * lo_thr;                                     // inner_local_optimization.hpp:101
+            int lo_inl;
+            float lo_sum;
+            if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
+            if (lo_inl <= m) continue;
+            bool fail = false;
+            if ((rc = iterative(lo_inl, lo_sum, best_inl, best_sum, fail))) return rc;
+            if (!fail && bigger(lo_inl, lo_sum, best_inl, best_sum)) {
+                CUDA_TRY(c, cudaMemcpyAsync(best_model, d_model, sizeof(float) * w, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(A, B, sizeof(int) * lo_inl, cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+                best_inl = lo_inl; best_sum = lo_sum;
+            }
+            inner_done++;
+        }
+        return USAC_OK;
+    }
+};
+
 // inlier mask of one model over the points in their given (quality-sorted) order: Quality::getInliers -> bytes
 static int fetch_mask(usac_gpu_ctx* c, int problem, const float* model, float thr, std::vector<unsigned char>& mask, std::vector<int>& ids) {
     const ProblemDesc& d = c->h_prob[problem];
@@ -949,6 +1098,8 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         ProsacTermHost pterm;
         if (is_sprt) sprt.init(c->est, n, (unsigned)m, cfg->max_iterations);
         if (is_prosac) { prosac_growth(n, (unsigned)m, growth); pterm.init(growth, n, (unsigned)m, cfg->confidence, cfg->max_iterations); }
+        LoRunner lo;
+        if (cfg->lo) { rc = lo.init(c, p, cfg->lo, cfg->threshold, cfg->sampler.seed); if (rc) return rc; }
         bool done = false;
         while (!done && hs.iters < hs.max_iters) {
             if (is_prosac) hs.prosac_term_len = pterm.termination_length;
@@ -1029,8 +1180,11 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                         inl = h_scores[q].x; memcpy(&score, &h_scores[q].y, 4);
                     }
                     if (inl > hs.best_cnt || (inl == hs.best_cnt && score > hs.best_sum)) {   // Score::bigger
+                        float cand[9] = {0};
+                        for (int k = 0; k < w; k++) cand[k] = h_models[(size_t)q * 9 + k];
+                        if (cfg->lo) { rc = lo.get_model_score(cand, inl, score); if (rc) return rc; }   // ransac.cpp:108-110
                         hs.best_cnt = inl; hs.best_sum = score; hs.best_hyp = (long long)(hyp0 + j); hs.best_midx = i;
-                        for (int k = 0; k < w; k++) hs.best_model[k] = h_models[(size_t)q * 9 + k];
+                        for (int k = 0; k < w; k++) hs.best_model[k] = cand[k];
                         if (is_prosac) {                                                 // ransac.cpp:123-125
                             rc = fetch_mask(c, p, hs.best_model, cfg->threshold, mask, ids);
                             if (rc) return rc;
@@ -1069,6 +1223,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         for (int i = 0; i < w; i++) r.model[i] = hs.best_model[i];
         r.inliers = hs.best_cnt; r.score = hs.best_sum; r.iterations = hs.iters; r.samples_drawn = hs.samples_drawn;
         r.best_hyp = hs.best_hyp; r.best_model_idx = hs.best_midx; r.rounds = hs.rounds; r.evals = hs.evals; r.useful_evals = hs.useful_evals;
+        if (cfg->lo) { r.lo_inner_iters = lo.inner_done; r.lo_iterative_iters = lo.iterative_done; }
     }
     return USAC_OK;
 }
@@ -1081,7 +1236,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     if (rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "fit: rank out of range");
     if (nranks > 1 && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_nccl_init or usac_gpu_set_allgather");
     if (cfg->sampler.rng == USAC_RNG_TABLE && (!cfg->sample_table || cfg->sample_table_rows == 0)) return fail(c, USAC_ERR_ARG, "fit: empty sample table");
-    const bool host_replay = cfg->sprt || cfg->sampler.sampler == USAC_SAMPLER_PROSAC;
+    if (cfg->lo != 0 && cfg->lo != 1 && cfg->lo != 2) return fail(c, USAC_ERR_ARG, "fit: lo must be 0 (none), 1 (InItLORsc) or 2 (InItFLORsc); GC / IRLS are not built");
+    if (cfg->lo && c->est == USAC_EST_LINE2D) return fail(c, USAC_ERR_ARG, "fit: local optimisation of line models is not built");
+    const bool host_replay = cfg->sprt || cfg->lo || cfg->sampler.sampler == USAC_SAMPLER_PROSAC;
     if (host_replay && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT / PROSAC termination with hypothesis sharding is not supported");
     cudaSetDevice(c->device);
     const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est);

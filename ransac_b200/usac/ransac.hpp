@@ -52,6 +52,8 @@ public:
         cfg.sampler = static_cast<GpuSampler*>(sampler)->config();
         cfg.threshold = model->threshold; cfg.confidence = model->desired_prob; cfg.max_iterations = model->max_iterations;
         cfg.sprt = model->sprt; cfg.round_size = model->gpu_round_size; cfg.rank = 0; cfg.nranks = 1;
+        if (model->lo == GC || model->lo == IRLS) throw std::runtime_error("Ransac: graph-cut / IRLS local optimisation is not part of the GPU layer");
+        cfg.lo = (int)model->lo;                                                         // NullLO 0, InItLORsc 1, InItFLORsc 2 (model.hpp:13)
         device->check(usac_gpu_fit(device->ctx, &cfg, &last_fit), "usac_gpu_fit");
         if (last_fit.inliers <= 0) throw std::runtime_error("Ransac: best score is 0");           // ransac.cpp:143-147
         usac_refit_result rf{};                                                                   // ransac.cpp:157-207 on the device

@@ -436,3 +436,25 @@ def test_nonminimal_and_refit_match_oracle(ctx, cfg):
     assert rf["inliers"] == ref["inliers"] and rf["accepted"] == ref["accepted"]
     assert np.array_equal(bits(rf["model"]), bits(ref["model"]))
     assert np.array_equal(ctx.get_inliers(rf["model"], thr), ref["ids"])
+
+
+# ---- LO-RANSAC (second "next" row) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,lo,sprt", [(2, 1, False), (2, 2, False), (3, 1, False), (3, 2, True), (4, 1, True)])
+def test_fit_with_local_optimisation_matches_oracle(ctx, cfg, lo, sprt):
+    """Inner + iterative LO (InItLORsc = 1, InItFLORsc = 2) on every new best model; config 4 is BASELINE's "SPRT + LO"."""
+    pts, gt, mask = gen.make(cfg, n=4000) if cfg != 4 else gen.essential(n=5000, inlier_ratio=0.3, seed=5)
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf, K, max_it = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"], 256, 2000
+    ctx.set_points(est, pts)
+    for seed in (1, 3):
+        if sprt:
+            ctx.set_sprt_pool(0, O.sprt_pool(seed, len(pts)))
+        r = ctx.fit(thr, conf, max_it, seed=seed, round_size=K, sprt=sprt, lo=lo)[0]
+        ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=max_it, seed=seed, sprt=sprt,
+                       batch=K if sprt else 0, lo=lo)
+        for key in ("inliers", "iterations", "best_hyp", "best_model_idx", "lo_inner", "lo_iterative"):
+            assert r[key] == ref[key], (key, r[key], ref[key], seed)
+        assert np.array_equal(bits(r["model"]), bits(ref["model"]))
+        assert r["score"] == ref["score"]                             # LO scores are lane sums: bit-identical
+        if cfg == 2:
+            assert r["inliers"] >= 0.97 * mask.sum()                  # LO lifts the minimal-sample model to (nearly) the full inlier set

@@ -369,3 +369,18 @@ def test_refit_loop_improves_or_keeps_the_minimal_model():
         assert rf["inliers"] >= r["inliers"] and 0 <= rf["accepted"] <= 4
         assert len(rf["ids"]) == O.score(O.EST_HOMOGRAPHY, pts, rf["model"], 2.0)[0]
         assert rf["inliers"] > 0.97 * mask.sum()                      # noise 0.5 px, threshold 2 px: essentially every true inlier
+
+
+def test_local_optimisation_lifts_minimal_models():
+    """LO-RANSAC in the oracle (inner_local_optimization.hpp:74-133): more inliers, not more iterations; counters as RansacOutput reports."""
+    from ransac_b200 import generator as gen
+    pts, H, mask = gen.homography(n=4000, seed=7)
+    base = O.ransac(pts, O.EST_HOMOGRAPHY, seed=3)
+    for lo in (1, 2):
+        r = O.ransac(pts, O.EST_HOMOGRAPHY, seed=3, lo=lo)
+        assert r["inliers"] >= base["inliers"] and r["inliers"] >= 0.97 * mask.sum()
+        assert r["iterations"] <= base["iterations"] and r["lo_inner"] >= 20 and r["lo_iterative"] >= r["lo_inner"]
+    pts, F, mask = gen.fundamental(n=4000, seed=7)
+    base = O.ransac(pts, O.EST_FUNDAMENTAL, seed=3, max_iterations=2000)
+    r = O.ransac(pts, O.EST_FUNDAMENTAL, seed=3, max_iterations=2000, lo=1)
+    assert r["inliers"] > base["inliers"]
