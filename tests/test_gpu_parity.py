@@ -458,3 +458,30 @@ def test_fit_with_local_optimisation_matches_oracle(ctx, cfg, lo, sprt):
         assert r["score"] == ref["score"]                             # LO scores are lane sums: bit-identical
         if cfg == 2:
             assert r["inliers"] >= 0.97 * mask.sum()                  # LO lifts the minimal-sample model to (nearly) the full inlier set
+
+
+# ---- the reference's own image pairs (points recovered into tests/golden/scoring_kat.npz from dataset/homography, dataset/EVD,
+# ---- dataset/fundamental): the complete run - main loop with LO, then the refit loop - against the oracle ------------------------
+def test_full_run_on_reference_datasets(ctx, golden_dir):
+    kat = np.load(os.path.join(golden_dir, "scoring_kat.npz"))
+    offs = kat["offsets"]
+    done = 0
+    for i, name in enumerate(kat["names"]):
+        pts = np.ascontiguousarray(kat["points"][offs[i]:offs[i + 1]])
+        est = O.EST_HOMOGRAPHY if kat["kind"][i] == 0 else O.EST_FUNDAMENTAL
+        thr, gt_inl = float(kat["threshold"][i]), int(kat["expected"][i])
+        if len(pts) < 30:
+            continue
+        ctx.set_points(est, pts)
+        r = ctx.fit(thr, 0.95, 2000, seed=1 + i, round_size=256, lo=1)[0]
+        ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95, max_iterations=2000, seed=1 + i, lo=1)
+        for key in ("inliers", "iterations", "best_hyp", "lo_inner", "lo_iterative"):
+            assert r[key] == ref[key], (name, key, r[key], ref[key])
+        assert np.array_equal(bits(r["model"]), bits(ref["model"])), name
+        if r["inliers"] > 0:
+            rf, rr = ctx.refit(r["model"], r["inliers"], thr), O.refit(est, pts, ref["model"], ref["inliers"], thr)
+            assert rf["inliers"] == rr["inliers"] and np.array_equal(bits(rf["model"]), bits(rr["model"])), name
+            if est == O.EST_HOMOGRAPHY and gt_inl >= 100:
+                assert rf["inliers"] >= 0.8 * gt_inl, (name, rf["inliers"], gt_inl)    # the reference's "GT Inl" column
+        done += 1
+    assert done >= 35
