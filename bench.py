@@ -9,8 +9,11 @@ all run to their own adaptive termination through usac_gpu_fit (sample -> solve 
 
   value : useful evaluations/s with the point sets resident in HBM. "Useful" = the evaluations the sequential loop of
           ransac.cpp:58-139 executes for the same sample stream (speculative tail of the last round is NOT counted).
+          The step's image pairs are split over --pipe contexts/streams (one host thread each): while one part waits for
+          the host sync of its round the kernels of the others run. (`config.value_single_stream`: one context.)
   e2e   : the same with HOST buffers: every step copies the step's point sets host->device (pinned memory) through
-          usac_gpu_set_points, fits, and reads the results (model, inliers, score, iterations) back.
+          usac_gpu_set_points, fits, and reads the results (model, inliers, score, iterations) back; every part is
+          double-buffered (two contexts) so that the upload of step k+1 overlaps the fit of step k.
   roofline : the scoring kernel, FP32 bound (BASELINE.json: "the roofline is FP32 FMA throughput plus HBM point
           streaming"); algorithmic 42 flop per homography evaluation.
   cpu_baseline / --impl reference : the CPU oracle (a restatement - the reference needs OpenCV-contrib/Eigen/nanoflann
@@ -213,8 +216,8 @@ def run_native(args):
         return (int(res["useful_evals"].sum()), int(res["evals"].sum()), t["launches"], t["score_launches"], t["score_ms"],
                 int(res["iterations"].sum()), int(res["rounds"].max()))
 
-    # e2e: the public API with HOST buffers. Two contexts (two streams, two host threads) each own half of the step's image
-    # pairs, so that the host->device copy of one half overlaps the fit of the other (the copy engine and the SMs run
+    # e2e: the public API with HOST buffers. n_pipe contexts (streams, host threads) each own a share of the step's image pairs,
+    # so that the host->device copy of one share overlaps the fits of the others (the copy engine and the SMs run
     # concurrently); every step still uploads every point set and reads every result back.
     n_pipe = max(1, min(args.pipe, B))
     halves = [(i * B // n_pipe, (i + 1) * B // n_pipe) for i in range(n_pipe)]
@@ -226,46 +229,96 @@ def run_native(args):
         pipe_ctx.append(c2)
         pipe_streams.append(s2)
 
-    def e2e_part(i, out):
+    # second buffer set for the e2e arm: part i owns contexts pipe_ctx[i] and pipe_ctx2[i]; one is being uploaded into while
+    # the other one is being fitted (a lock per part keeps the two fits of a part from running at once)
+    pipe_ctx2 = []
+    for _ in range(n_pipe):
+        c2 = GpuContext(local)
+        s2 = torch.cuda.Stream()
+        c2.set_stream(s2.cuda_stream)
+        pipe_ctx2.append(c2)
+        pipe_streams.append(s2)
+    part_locks = [threading.Lock() for _ in range(n_pipe)]
+
+    def e2e_part(cx, i, out, k):
         torch.cuda.set_device(local)
         lo, hi = halves[i]
-        pipe_ctx[i].set_points(capi.EST_HOMOGRAPHY, host[lo * N_POINTS:hi * N_POINTS], sizes[lo:hi])
+        cx.set_points(capi.EST_HOMOGRAPHY, host[lo * N_POINTS:hi * N_POINTS], sizes[lo:hi])      # H2D of this step's points + re-layout
+        with part_locks[i]:
+            res = cx.fit_records(**fit_kw)
+            t = cx.last_timing()
+        out[k] = (int(res["useful_evals"].sum()), int(res["evals"].sum()), t["launches"], t["score_launches"], t["score_ms"],
+                  int(res["iterations"].sum()), int(res["rounds"].max()))
+
+    def timed_e2e(steps):
+        """2 x n_pipe worker threads: part i of every step (1/n_pipe of the image pairs) is handled alternately by two threads
+        with their own context/stream, each doing upload -> fit -> read back; while one of them fits step k the other uploads
+        step k+1. The bracket is a pair of events on an idle timing stream recorded after a full device sync on each side, so
+        all the work of the `steps` steps (every upload, every fit, every result read-back) lies between them."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        outs = [[None] * steps for _ in range(n_pipe)]
+
+        def worker(i, j):
+            cx = (pipe_ctx, pipe_ctx2)[j][i]
+            for k in range(j, steps, 2):
+                e2e_part(cx, i, outs[i], k)
+        barrier()
+        ev0.record(stream)
+        threads = [threading.Thread(target=worker, args=(i, j)) for i in range(n_pipe) for j in range(2)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize()
+        ev1.record(stream)
+        barrier()
+        stats = [tuple(sum(outs[i][k][f] for i in range(n_pipe)) if f != 6 else max(outs[i][k][f] for i in range(n_pipe)) for f in range(7))
+                 for k in range(steps)]
+        return ev0.elapsed_time(ev1), stats
+
+    def resident_part(i, out):
+        torch.cuda.set_device(local)
         res = pipe_ctx[i].fit_records(**fit_kw)
         t = pipe_ctx[i].last_timing()
         out[i] = (int(res["useful_evals"].sum()), int(res["evals"].sum()), t["launches"], t["score_launches"], t["score_ms"],
                   int(res["iterations"].sum()), int(res["rounds"].max()))
 
-    def step_e2e():
+    def step_resident_pipelined():
         out = [None] * n_pipe
-        threads = [threading.Thread(target=e2e_part, args=(i, out)) for i in range(n_pipe)]
+        threads = [threading.Thread(target=resident_part, args=(i, out)) for i in range(n_pipe)]
         for th in threads:
             th.start()
         for th in threads:
             th.join()
         return tuple(sum(o[k] for o in out) if k != 6 else max(o[k] for o in out) for k in range(7))
 
-    def timed_e2e(steps):
-        """The e2e work runs on the contexts' own streams from worker threads; the bracket is a pair of events on an idle
-        timing stream recorded after a full device sync on each side (all work of the region lies between them)."""
+    def timed_threads(step_fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stats = []
         barrier()
         ev0.record(stream)
         for _ in range(steps):
-            stats.append(step_e2e())
+            stats.append(step_fn())
         torch.cuda.synchronize()
         ev1.record(stream)
         barrier()
         return ev0.elapsed_time(ev1), stats
 
     # ---- device-resident arm ----
+    # (a) one context, one stream: the per-launch CUDA-event times of the scoring kernel (roofline) are taken here, where no
+    #     other stream runs; (b) the same step split over the two contexts of the e2e arm (points already resident): while one
+    #     half waits for its round's host sync the other half's kernels run - this is the reported `value`.
     ctx.set_points(capi.EST_HOMOGRAPHY, host, sizes)
     timed(step_resident, args.warmup)
+    ms_single, stats = timed(step_resident, args.steps)
+    for i, (lo_, hi_) in enumerate(halves):
+        pipe_ctx[i].set_points(capi.EST_HOMOGRAPHY, host[lo_ * N_POINTS:hi_ * N_POINTS], sizes[lo_:hi_])
+    timed_threads(step_resident_pipelined, args.warmup)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, stats = timed(step_resident, args.steps)
+    ms, stats_p = timed_threads(step_resident_pipelined, args.steps)
     clk = clocks.stop()
-    useful = sum(s[0] for s in stats)
+    useful = sum(s[0] for s in stats_p)
     executed = sum(s[1] for s in stats)
     launches = sum(s[2] for s in stats)
     score_launches = sum(s[3] for s in stats)
@@ -310,7 +363,7 @@ def run_native(args):
                     "peak_source": "2*128 lanes*SMs*max SM clock from the device (no FP32 figure in MEASURED_PEAKS.json); "
                                    f"register-resident FFMA loop measured in this run: {measured_ffma:.1f} TFLOP/s",
                     "flops_per_eval": 42, "evals_per_launch": executed / max(score_launches, 1),
-                    "avg_launch_ms": score_ms / max(score_launches, 1), "score_share_of_step": score_ms / ms,
+                    "avg_launch_ms": score_ms / max(score_launches, 1), "score_share_of_step": score_ms / ms_single,
                     "hbm": {"algorithmic_bytes_per_launch": alg_bytes_launch,
                             "achieved_gbs": alg_bytes_launch / (score_ms / max(score_launches, 1) * 1e-3) / 1e9,
                             "peak_gbs": hbm_peak, "peak_source": "measured" if peaks else "fallback"}}
@@ -320,6 +373,7 @@ def run_native(args):
                 "config": {"workload": workload_name(B), "problems_per_gpu": B, "round_size": args.round_size,
                            "l2": f"inputs larger than L2: {B * N_POINTS * 32 / 1e6:.0f} MB of points per GPU (AoS + pair layout) vs 126 MB",
                            "ms_per_fit": ms_all / args.steps / B, "avg_iterations_per_fit": iters / (args.steps * B),
+                           "value_single_stream": sum(s[0] for s in stats) / (ms_single * 1e-3), "streams": n_pipe,
                            "evals_executed_per_s": executed_all / (ms_all * 1e-3), "useful_fraction": useful / max(executed, 1)},
                 "clocks": clk, "gpu_launches": int(launches_all),
                 "e2e": {"value": useful_e2e_all / (ms_e2e_all * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": B * N_POINTS * 16,
@@ -331,7 +385,7 @@ def run_native(args):
             line["config"]["single_fit_latency_ms"] = single_fit_latency(ctx, problems[0], timed)
         print(json.dumps(line))
     ctx.close()
-    for c2 in pipe_ctx:
+    for c2 in pipe_ctx + pipe_ctx2:
         c2.close()
     if world > 1:
         dist.destroy_process_group()
@@ -451,7 +505,7 @@ def main():
     ap.add_argument("--round-size", type=int, default=128, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
-    ap.add_argument("--pipe", type=int, default=2, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
+    ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
     ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 workload (0 = max(2048, 1024 x ranks))")

@@ -19,6 +19,8 @@ CASES = [
     ("C3 fundamental N=10000 25% PROSAC+SPRT", 3, {}, dict(est=O.EST_FUNDAMENTAL, thr=2.0, conf=0.95),
      dict(sampler="prosac", sprt=True, K=512)),
     ("C4 essential N=20000 20% uniform+SPRT (no LO)", 4, {}, dict(est=O.EST_ESSENTIAL, thr=2.5e-3, conf=0.95), dict(sprt=True, K=512)),
+    ("C4 essential N=20000 20% uniform+SPRT+LO", 4, {}, dict(est=O.EST_ESSENTIAL, thr=2.5e-3, conf=0.95), dict(sprt=True, K=512, lo=1)),
+    ("C2 homography N=4000 30% uniform+LO", 2, {}, dict(est=O.EST_HOMOGRAPHY, thr=2.0, conf=0.95), dict(lo=1)),
     ("C5 homography N=1M 10% NAPSAC grid", 5, {}, dict(est=O.EST_HOMOGRAPHY, thr=2.0, conf=0.95), dict(sampler="napsac", K=2048, oracle_iters=64)),
 ]
 ctx = GpuContext(0)
@@ -36,6 +38,8 @@ for name, cfg, genkw, p, mode in CASES:
     if mode.get("sprt"):
         ctx.set_sprt_pool(0, O.sprt_pool(1, len(pts)))
         kw["sprt"] = True; okw["sprt"] = True
+    if mode.get("lo"):
+        kw["lo"] = mode["lo"]; okw["lo"] = mode["lo"]
     if "K" in mode:
         kw["round_size"] = mode["K"]
         if mode.get("sprt") or mode.get("sampler") == "prosac":
