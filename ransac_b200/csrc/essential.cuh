@@ -142,9 +142,18 @@ __device__ bool null_space5(double* A, double* basis) {
 
 }  // namespace e5
 
-__device__ __noinline__ int solve_essential5(const float* __restrict__ pts, const int* s, float* out) {
-    using namespace e5;
-    double x1[5], y1[5], x2[5], y2[5], A[45];
+// ---------------------------------------------------------------------------------------------------------------
+// The solver in stages. The one-thread form (solve_essential5) runs them in sequence; the one-warp form
+// (solve_essential5_warp) spreads the independent pieces over the lanes - 22 determinants, the root brackets of every
+// derivative level, the candidate roots - each piece still evaluated by ONE lane with the same operations in the same
+// order, so both forms (and the host restatement of the parity tests) return bit-identical models.
+// ---------------------------------------------------------------------------------------------------------------
+namespace e5 {
+
+// stage 1: points -> X = [x1[5] y1[5] x2[5] y2[5]], L[9][4] (E_ij as linear forms), C[10][20] (the ten cubic constraints)
+__device__ bool stage_constraints(const float* __restrict__ pts, const int* s, double* X, double (*L)[4], double (*C)[20]) {
+    double A[45];
+    double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
     for (int i = 0; i < 5; i++) {
         const float4 p = reinterpret_cast<const float4*>(pts)[s[i]];
         x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w;
@@ -153,7 +162,7 @@ __device__ __noinline__ int solve_essential5(const float* __restrict__ pts, cons
         r[6] = x1[i]; r[7] = y1[i]; r[8] = 1.0;
     }
     double Bs[36];
-    if (!null_space5(A, Bs)) return 0;
+    if (!null_space5(A, Bs)) return false;
     for (int a = 3; a >= 0; a--) {                                        // modified Gram-Schmidt, last vector first
         double* v = Bs + 9 * a;
         for (int b = 3; b > a; b--) {
@@ -164,71 +173,75 @@ __device__ __noinline__ int solve_essential5(const float* __restrict__ pts, cons
         }
         double nn = 0.0;
         for (int e = 0; e < 9; e++) nn = add(nn, mul(v[e], v[e]));
-        if (!(nn > 0.0)) return 0;
+        if (!(nn > 0.0)) return false;
         const double inv = dvd(1.0, __dsqrt_rn(nn));
         for (int e = 0; e < 9; e++) v[e] = mul(v[e], inv);
     }
-    double L[9][4];
     for (int e = 0; e < 9; e++) for (int q = 0; q < 4; q++) L[e][q] = Bs[q * 9 + e];
-    double C[10][20];
     for (int r = 0; r < 10; r++) for (int m = 0; m < 20; m++) C[r][m] = 0.0;
-    {
-        double Q[3][3][10];
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int m = 0; m < 10; m++) Q[i][j][m] = 0.0;
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++)
-                for (int k = 0; k < 3; k++) acc_ll(Q[i][j], L[3 * i + k], L[3 * j + k], 1.0);
-        double tr[10];
-        for (int m = 0; m < 10; m++) tr[m] = add(add(Q[0][0][m], Q[1][1][m]), Q[2][2][m]);
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                double* c = C[3 * i + j];
-                for (int k = 0; k < 3; k++) acc_ql(c, Q[i][k], L[3 * k + j], 2.0);
-                acc_ql(c, tr, L[3 * i + j], -1.0);
-            }
-        double m0[10], m1[10], m2[10];
-        for (int m = 0; m < 10; m++) { m0[m] = 0.0; m1[m] = 0.0; m2[m] = 0.0; }
-        acc_ll(m0, L[4], L[8], 1.0); acc_ll(m0, L[5], L[7], -1.0);
-        acc_ll(m1, L[3], L[8], 1.0); acc_ll(m1, L[5], L[6], -1.0);
-        acc_ll(m2, L[3], L[7], 1.0); acc_ll(m2, L[4], L[6], -1.0);
-        acc_ql(C[9], m0, L[0], 1.0); acc_ql(C[9], m1, L[1], -1.0); acc_ql(C[9], m2, L[2], 1.0);
-    }
-    double roots[20];
-    int nroots = 0;
+    double Q[3][3][10];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int m = 0; m < 10; m++) Q[i][j][m] = 0.0;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) acc_ll(Q[i][j], L[3 * i + k], L[3 * j + k], 1.0);
+    double tr[10];
+    for (int m = 0; m < 10; m++) tr[m] = add(add(Q[0][0][m], Q[1][1][m]), Q[2][2][m]);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double* c = C[3 * i + j];
+            for (int k = 0; k < 3; k++) acc_ql(c, Q[i][k], L[3 * k + j], 2.0);
+            acc_ql(c, tr, L[3 * i + j], -1.0);
+        }
+    double m0[10], m1[10], m2[10];
+    for (int m = 0; m < 10; m++) { m0[m] = 0.0; m1[m] = 0.0; m2[m] = 0.0; }
+    acc_ll(m0, L[4], L[8], 1.0); acc_ll(m0, L[5], L[7], -1.0);
+    acc_ll(m1, L[3], L[8], 1.0); acc_ll(m1, L[5], L[6], -1.0);
+    acc_ll(m2, L[3], L[7], 1.0); acc_ll(m2, L[4], L[6], -1.0);
+    acc_ql(C[9], m0, L[0], 1.0); acc_ql(C[9], m1, L[1], -1.0); acc_ql(C[9], m2, L[2], 1.0);
+    return true;
+}
+
+// stage 2: det M(z) (pass 0) or det(M(1/w) diag(w^deg)) (pass 1) at node t of the 11 equispaced nodes in [-1, 1]
+__device__ double stage_det(const double (*C)[20], int pass, int t) {
     double Mz[100];
-    for (int pass = 0; pass < 2; pass++) {
-        double zs[11], dd[11];
-        for (int t = 0; t < 11; t++) {
-            const double z = dvd((double)(t - 5), 5.0);
-            for (int r = 0; r < 10; r++)
-                for (int c = 0; c < 10; c++)
-                    Mz[r * 10 + c] = pass == 0 ? horner(&C[r][COL_FIRST[c]], COL_DEG[c], z) : horner_rev(&C[r][COL_FIRST[c]], COL_DEG[c], z);
-            zs[t] = z;
-            dd[t] = det_lu(Mz, 10);
-        }
-        for (int lev = 1; lev < 11; lev++)
-            for (int t = 10; t >= lev; t--) dd[t] = dvd(sub(dd[t], dd[t - 1]), sub(zs[t], zs[t - lev]));
-        double coef[11];
-        for (int i = 0; i < 11; i++) coef[i] = 0.0;
-        coef[0] = dd[10];
-        for (int t = 9; t >= 0; t--) {
-            for (int i = 10; i >= 1; i--) coef[i] = sub(coef[i - 1], mul(coef[i], zs[t]));
-            coef[0] = sub(dd[t], mul(coef[0], zs[t]));
-        }
-        int deg = 10;
-        double cmax = 0.0;
-        bool finite = true;
-        for (int i = 0; i <= 10; i++) { if (!dfinite(coef[i])) finite = false; if (fabs(coef[i]) > cmax) cmax = fabs(coef[i]); }
-        if (!finite) return 0;
-        while (deg > 0 && !(fabs(coef[deg]) > mul(1e-13, cmax))) deg--;
-        if (deg < 1) continue;
-        double rr[10];
-        const int nr = real_roots(coef, deg, rr);
-        for (int i = 0; i < nr; i++) {
-            if (pass == 0) { if (fabs(rr[i]) <= 1.05) roots[nroots++] = rr[i]; }
-            else if (fabs(rr[i]) < dvd(1.0, 1.05) && rr[i] != 0.0) roots[nroots++] = dvd(1.0, rr[i]);
-        }
+    const double z = dvd((double)(t - 5), 5.0);
+    for (int r = 0; r < 10; r++)
+        for (int c = 0; c < 10; c++)
+            Mz[r * 10 + c] = pass == 0 ? horner(&C[r][COL_FIRST[c]], COL_DEG[c], z) : horner_rev(&C[r][COL_FIRST[c]], COL_DEG[c], z);
+    return det_lu(Mz, 10);
+}
+
+// stage 3: 11 determinant values -> monomial coefficients (Newton divided differences); returns the degree after trimming,
+// 0 when there is nothing to solve, -1 when a coefficient is not finite (the solver then returns no model)
+__device__ int stage_coefficients(double* dd, double* coef) {
+    double zs[11];
+    for (int t = 0; t < 11; t++) zs[t] = dvd((double)(t - 5), 5.0);
+    for (int lev = 1; lev < 11; lev++)
+        for (int t = 10; t >= lev; t--) dd[t] = dvd(sub(dd[t], dd[t - 1]), sub(zs[t], zs[t - lev]));
+    for (int i = 0; i < 11; i++) coef[i] = 0.0;
+    coef[0] = dd[10];
+    for (int t = 9; t >= 0; t--) {
+        for (int i = 10; i >= 1; i--) coef[i] = sub(coef[i - 1], mul(coef[i], zs[t]));
+        coef[0] = sub(dd[t], mul(coef[0], zs[t]));
     }
+    int deg = 10;
+    double cmax = 0.0;
+    bool finite = true;
+    for (int i = 0; i <= 10; i++) { if (!dfinite(coef[i])) finite = false; if (fabs(coef[i]) > cmax) cmax = fabs(coef[i]); }
+    if (!finite) return -1;
+    while (deg > 0 && !(fabs(coef[deg]) > mul(1e-13, cmax))) deg--;
+    return deg;
+}
+
+// stage 4 helper: keep the roots of pass 0 with |z| <= 1.05 and the reciprocals of the roots of pass 1 with |w| < 1/1.05
+__device__ int stage_collect(int pass, const double* rr, int nr, double* roots, int nroots) {
+    for (int i = 0; i < nr; i++) {
+        if (pass == 0) { if (fabs(rr[i]) <= 1.05) roots[nroots++] = rr[i]; }
+        else if (fabs(rr[i]) < dvd(1.0, 1.05) && rr[i] != 0.0) roots[nroots++] = dvd(1.0, rr[i]);
+    }
+    return nroots;
+}
+__device__ void stage_sort(double* roots, int& nroots) {                 // ascending |z|, stable
     if (nroots > 10) nroots = 10;
     for (int i = 1; i < nroots; i++) {
         const double v = roots[i];
@@ -236,122 +249,237 @@ __device__ __noinline__ int solve_essential5(const float* __restrict__ pts, cons
         while (j >= 0 && fabs(roots[j]) > fabs(v)) { roots[j + 1] = roots[j]; j--; }
         roots[j + 1] = v;
     }
-    for (int ri = 0; ri < nroots; ri++) {
-        const double z = roots[ri];
-        for (int r = 0; r < 10; r++)
-            for (int c = 0; c < 10; c++) Mz[r * 10 + c] = horner(&C[r][COL_FIRST[c]], COL_DEG[c], z);
-        bool ok = true;
-        for (int k = 0; k < 9 && ok; k++) {
-            int piv = k;
-            double best = fabs(Mz[k * 10 + k]);
-            for (int r = k + 1; r < 10; r++) { const double v = fabs(Mz[r * 10 + k]); if (v > best) { best = v; piv = r; } }
-            if (!(best > 0.0) || !dfinite(best)) { ok = false; break; }
-            if (piv != k) for (int j = 0; j < 10; j++) { const double t = Mz[k * 10 + j]; Mz[k * 10 + j] = Mz[piv * 10 + j]; Mz[piv * 10 + j] = t; }
-            const double inv = dvd(1.0, Mz[k * 10 + k]);
-            for (int j = k + 1; j < 10; j++) Mz[k * 10 + j] = mul(Mz[k * 10 + j], inv);
-            for (int r = 0; r < 10; r++) {
-                if (r == k) continue;
-                const double f = Mz[r * 10 + k];
-                for (int j = k + 1; j < 10; j++) Mz[r * 10 + j] = sub(Mz[r * 10 + j], mul(f, Mz[k * 10 + j]));
-            }
+}
+
+// stage 5: one root z -> x, y (Gauss-Jordan on [M(z) | last column]), eight Gauss-Newton steps, E, cheirality vote
+__device__ bool stage_root(const double (*C)[20], const double (*L)[4], const double* X, double z, double* E) {
+    const double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
+    double Mz[100];
+    for (int r = 0; r < 10; r++)
+        for (int c = 0; c < 10; c++) Mz[r * 10 + c] = horner(&C[r][COL_FIRST[c]], COL_DEG[c], z);
+    for (int k = 0; k < 9; k++) {
+        int piv = k;
+        double best = fabs(Mz[k * 10 + k]);
+        for (int r = k + 1; r < 10; r++) { const double v = fabs(Mz[r * 10 + k]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0) || !dfinite(best)) return false;
+        if (piv != k) for (int j = 0; j < 10; j++) { const double t = Mz[k * 10 + j]; Mz[k * 10 + j] = Mz[piv * 10 + j]; Mz[piv * 10 + j] = t; }
+        const double inv = dvd(1.0, Mz[k * 10 + k]);
+        for (int j = k + 1; j < 10; j++) Mz[k * 10 + j] = mul(Mz[k * 10 + j], inv);
+        for (int r = 0; r < 10; r++) {
+            if (r == k) continue;
+            const double f = Mz[r * 10 + k];
+            for (int j = k + 1; j < 10; j++) Mz[r * 10 + j] = sub(Mz[r * 10 + j], mul(f, Mz[k * 10 + j]));
         }
-        if (!ok) continue;
-        double u[3] = {-Mz[7 * 10 + 9], -Mz[8 * 10 + 9], z};
-        for (int it = 0; it < 8; it++) {                                  // Gauss-Newton on the ten constraints
-            double pw[3][4];
-            for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
-            double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
-            for (int r = 0; r < 10; r++) {
-                double val = 0.0, g[3] = {0, 0, 0};
-                for (int m = 0; m < 20; m++) {
-                    const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
-                    const double c = C[r][m];
-                    val = add(val, mul(c, mul(mul(pw[0][e[0]], pw[1][e[1]]), pw[2][e[2]])));
-                    for (int a = 0; a < 3; a++) {
-                        if (e[a] == 0) continue;
-                        double t = (double)e[a];
-                        for (int b = 0; b < 3; b++) t = mul(t, pw[b][b == a ? e[b] - 1 : e[b]]);
-                        g[a] = add(g[a], mul(c, t));
-                    }
+    }
+    double u[3] = {-Mz[7 * 10 + 9], -Mz[8 * 10 + 9], z};
+    for (int it = 0; it < 8; it++) {                                  // Gauss-Newton on the ten constraints
+        double pw[3][4];
+        for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
+        double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
+        for (int r = 0; r < 10; r++) {
+            double val = 0.0, g[3] = {0, 0, 0};
+            for (int m = 0; m < 20; m++) {
+                const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
+                const double c = C[r][m];
+                val = add(val, mul(c, mul(mul(pw[0][e[0]], pw[1][e[1]]), pw[2][e[2]])));
+                for (int a = 0; a < 3; a++) {
+                    if (e[a] == 0) continue;
+                    double t = (double)e[a];
+                    for (int b = 0; b < 3; b++) t = mul(t, pw[b][b == a ? e[b] - 1 : e[b]]);
+                    g[a] = add(g[a], mul(c, t));
                 }
-                JtJ[0] = add(JtJ[0], mul(g[0], g[0])); JtJ[1] = add(JtJ[1], mul(g[0], g[1])); JtJ[2] = add(JtJ[2], mul(g[0], g[2]));
-                JtJ[3] = add(JtJ[3], mul(g[1], g[1])); JtJ[4] = add(JtJ[4], mul(g[1], g[2])); JtJ[5] = add(JtJ[5], mul(g[2], g[2]));
-                Jtr[0] = add(Jtr[0], mul(g[0], val)); Jtr[1] = add(Jtr[1], mul(g[1], val)); Jtr[2] = add(Jtr[2], mul(g[2], val));
             }
-            const double a = JtJ[0], b = JtJ[1], c = JtJ[2], d = JtJ[3], e = JtJ[4], f = JtJ[5];
-            const double c00 = sub(mul(d, f), mul(e, e)), c01 = sub(mul(c, e), mul(b, f)), c02 = sub(mul(b, e), mul(c, d));
-            const double c11 = sub(mul(a, f), mul(c, c)), c12 = sub(mul(b, c), mul(a, e)), c22 = sub(mul(a, d), mul(b, b));
-            const double det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
-            if (!(fabs(det) > 0.0) || !dfinite(det)) break;
-            const double dx = dvd(add(add(mul(c00, Jtr[0]), mul(c01, Jtr[1])), mul(c02, Jtr[2])), det);
-            const double dy = dvd(add(add(mul(c01, Jtr[0]), mul(c11, Jtr[1])), mul(c12, Jtr[2])), det);
-            const double dz = dvd(add(add(mul(c02, Jtr[0]), mul(c12, Jtr[1])), mul(c22, Jtr[2])), det);
-            if (!dfinite(dx) || !dfinite(dy) || !dfinite(dz)) break;
-            u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
+            JtJ[0] = add(JtJ[0], mul(g[0], g[0])); JtJ[1] = add(JtJ[1], mul(g[0], g[1])); JtJ[2] = add(JtJ[2], mul(g[0], g[2]));
+            JtJ[3] = add(JtJ[3], mul(g[1], g[1])); JtJ[4] = add(JtJ[4], mul(g[1], g[2])); JtJ[5] = add(JtJ[5], mul(g[2], g[2]));
+            Jtr[0] = add(Jtr[0], mul(g[0], val)); Jtr[1] = add(Jtr[1], mul(g[1], val)); Jtr[2] = add(Jtr[2], mul(g[2], val));
         }
+        const double a = JtJ[0], b = JtJ[1], c = JtJ[2], d = JtJ[3], e = JtJ[4], f = JtJ[5];
+        const double c00 = sub(mul(d, f), mul(e, e)), c01 = sub(mul(c, e), mul(b, f)), c02 = sub(mul(b, e), mul(c, d));
+        const double c11 = sub(mul(a, f), mul(c, c)), c12 = sub(mul(b, c), mul(a, e)), c22 = sub(mul(a, d), mul(b, b));
+        const double det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
+        if (!(fabs(det) > 0.0) || !dfinite(det)) break;
+        const double dx = dvd(add(add(mul(c00, Jtr[0]), mul(c01, Jtr[1])), mul(c02, Jtr[2])), det);
+        const double dy = dvd(add(add(mul(c01, Jtr[0]), mul(c11, Jtr[1])), mul(c12, Jtr[2])), det);
+        const double dz = dvd(add(add(mul(c02, Jtr[0]), mul(c12, Jtr[1])), mul(c22, Jtr[2])), det);
+        if (!dfinite(dx) || !dfinite(dy) || !dfinite(dz)) break;
+        u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
+    }
+    bool finite = true;
+    for (int e = 0; e < 9; e++) {
+        double v = mul(L[e][0], u[0]);
+        v = add(v, mul(L[e][1], u[1]));
+        v = add(v, mul(L[e][2], u[2]));
+        v = add(v, L[e][3]);
+        E[e] = v;
+        if (!dfinite(v)) finite = false;
+    }
+    if (!finite) return false;
+    double n2 = 0.0;
+    for (int e = 0; e < 9; e++) n2 = add(n2, mul(E[e], E[e]));
+    const double sc = __dsqrt_rn(mul(0.5, n2));
+    if (!(sc > 0.0)) return false;
+    double En[9];
+    for (int e = 0; e < 9; e++) En[e] = dvd(E[e], sc);
+    double tv[3] = {0, 0, 0}, tbest = -1.0;
+    for (int a = 0; a < 3; a++) {
+        const int b = (a + 1) % 3;
+        const double cx = sub(mul(En[3 + a], En[6 + b]), mul(En[6 + a], En[3 + b]));
+        const double cy = sub(mul(En[6 + a], En[0 + b]), mul(En[0 + a], En[6 + b]));
+        const double cz = sub(mul(En[0 + a], En[3 + b]), mul(En[3 + a], En[0 + b]));
+        const double nn = add(add(mul(cx, cx), mul(cy, cy)), mul(cz, cz));
+        if (nn > tbest) { tbest = nn; tv[0] = cx; tv[1] = cy; tv[2] = cz; }
+    }
+    if (!(tbest > 0.0)) return false;
+    { const double inv = dvd(1.0, __dsqrt_rn(tbest)); tv[0] = mul(tv[0], inv); tv[1] = mul(tv[1], inv); tv[2] = mul(tv[2], inv); }
+    double cof[9], tE[9];
+    cof[0] = sub(mul(En[4], En[8]), mul(En[5], En[7])); cof[1] = sub(mul(En[5], En[6]), mul(En[3], En[8])); cof[2] = sub(mul(En[3], En[7]), mul(En[4], En[6]));
+    cof[3] = sub(mul(En[2], En[7]), mul(En[1], En[8])); cof[4] = sub(mul(En[0], En[8]), mul(En[2], En[6])); cof[5] = sub(mul(En[1], En[6]), mul(En[0], En[7]));
+    cof[6] = sub(mul(En[1], En[5]), mul(En[2], En[4])); cof[7] = sub(mul(En[2], En[3]), mul(En[0], En[5])); cof[8] = sub(mul(En[0], En[4]), mul(En[1], En[3]));
+    for (int c = 0; c < 3; c++) {
+        tE[0 + c] = sub(mul(tv[1], En[6 + c]), mul(tv[2], En[3 + c]));
+        tE[3 + c] = sub(mul(tv[2], En[0 + c]), mul(tv[0], En[6 + c]));
+        tE[6 + c] = sub(mul(tv[0], En[3 + c]), mul(tv[1], En[0 + c]));
+    }
+    for (int cam = 0; cam < 4; cam++) {
+        double R[9], t[3];
+        const double rs = (cam < 2) ? -1.0 : 1.0, ts = (cam & 1) ? -1.0 : 1.0;
+        for (int e = 0; e < 9; e++) R[e] = add(cof[e], mul(rs, tE[e]));
+        for (int e = 0; e < 3; e++) t[e] = mul(ts, tv[e]);
+        int infront = 0;
+        for (int k = 0; k < 5; k++) {
+            const double a0 = add(add(mul(R[0], x1[k]), mul(R[1], y1[k])), R[2]);
+            const double a1 = add(add(mul(R[3], x1[k]), mul(R[4], y1[k])), R[5]);
+            const double a2 = add(add(mul(R[6], x1[k]), mul(R[7], y1[k])), R[8]);
+            const double b0 = x2[k], b1 = y2[k], b2 = 1.0;
+            const double aa = add(add(mul(a0, a0), mul(a1, a1)), mul(a2, a2)), bb = add(add(mul(b0, b0), mul(b1, b1)), mul(b2, b2));
+            const double ab = add(add(mul(a0, b0), mul(a1, b1)), mul(a2, b2));
+            const double at = add(add(mul(a0, t[0]), mul(a1, t[1])), mul(a2, t[2])), bt = add(add(mul(b0, t[0]), mul(b1, t[1])), mul(b2, t[2]));
+            const double det = sub(mul(aa, bb), mul(ab, ab));
+            const double l1 = dvd(sub(mul(ab, bt), mul(bb, at)), det), l2 = dvd(sub(mul(aa, bt), mul(ab, at)), det);
+            if (l1 > 0.0 && l2 > 0.0) infront++; else break;
+        }
+        if (infront == 5) return true;
+    }
+    return false;
+}
+
+}  // namespace e5
+
+// one thread per sample
+__device__ __noinline__ int solve_essential5(const float* __restrict__ pts, const int* s, float* out) {
+    using namespace e5;
+    double X[20], L[9][4], C[10][20];
+    if (!stage_constraints(pts, s, X, L, C)) return 0;
+    double roots[20];
+    int nroots = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        double dd[11], coef[11], rr[10];
+        for (int t = 0; t < 11; t++) dd[t] = stage_det(C, pass, t);
+        const int deg = stage_coefficients(dd, coef);
+        if (deg < 0) return 0;
+        if (deg < 1) continue;
+        const int nr = real_roots(coef, deg, rr);
+        nroots = stage_collect(pass, rr, nr, roots, nroots);
+    }
+    stage_sort(roots, nroots);
+    for (int ri = 0; ri < nroots; ri++) {
         double E[9];
-        bool finite = true;
-        for (int e = 0; e < 9; e++) {
-            double v = mul(L[e][0], u[0]);
-            v = add(v, mul(L[e][1], u[1]));
-            v = add(v, mul(L[e][2], u[2]));
-            v = add(v, L[e][3]);
-            E[e] = v;
-            if (!dfinite(v)) finite = false;
-        }
-        if (!finite) continue;
-        double n2 = 0.0;
-        for (int e = 0; e < 9; e++) n2 = add(n2, mul(E[e], E[e]));
-        const double sc = __dsqrt_rn(mul(0.5, n2));
-        if (!(sc > 0.0)) continue;
-        double En[9];
-        for (int e = 0; e < 9; e++) En[e] = dvd(E[e], sc);
-        double tv[3] = {0, 0, 0}, tbest = -1.0;
-        for (int a = 0; a < 3; a++) {
-            const int b = (a + 1) % 3;
-            // columns a and b of En: col[c][r] = En[3r + c]
-            const double cx = sub(mul(En[3 + a], En[6 + b]), mul(En[6 + a], En[3 + b]));
-            const double cy = sub(mul(En[6 + a], En[0 + b]), mul(En[0 + a], En[6 + b]));
-            const double cz = sub(mul(En[0 + a], En[3 + b]), mul(En[3 + a], En[0 + b]));
-            const double nn = add(add(mul(cx, cx), mul(cy, cy)), mul(cz, cz));
-            if (nn > tbest) { tbest = nn; tv[0] = cx; tv[1] = cy; tv[2] = cz; }
-        }
-        if (!(tbest > 0.0)) continue;
-        { const double inv = dvd(1.0, __dsqrt_rn(tbest)); tv[0] = mul(tv[0], inv); tv[1] = mul(tv[1], inv); tv[2] = mul(tv[2], inv); }
-        double cof[9], tE[9];
-        cof[0] = sub(mul(En[4], En[8]), mul(En[5], En[7])); cof[1] = sub(mul(En[5], En[6]), mul(En[3], En[8])); cof[2] = sub(mul(En[3], En[7]), mul(En[4], En[6]));
-        cof[3] = sub(mul(En[2], En[7]), mul(En[1], En[8])); cof[4] = sub(mul(En[0], En[8]), mul(En[2], En[6])); cof[5] = sub(mul(En[1], En[6]), mul(En[0], En[7]));
-        cof[6] = sub(mul(En[1], En[5]), mul(En[2], En[4])); cof[7] = sub(mul(En[2], En[3]), mul(En[0], En[5])); cof[8] = sub(mul(En[0], En[4]), mul(En[1], En[3]));
-        for (int c = 0; c < 3; c++) {
-            tE[0 + c] = sub(mul(tv[1], En[6 + c]), mul(tv[2], En[3 + c]));
-            tE[3 + c] = sub(mul(tv[2], En[0 + c]), mul(tv[0], En[6 + c]));
-            tE[6 + c] = sub(mul(tv[0], En[3 + c]), mul(tv[1], En[0 + c]));
-        }
-        bool pass = false;
-        for (int cam = 0; cam < 4 && !pass; cam++) {
-            double R[9], t[3];
-            const double rs = (cam < 2) ? -1.0 : 1.0, ts = (cam & 1) ? -1.0 : 1.0;
-            for (int e = 0; e < 9; e++) R[e] = add(cof[e], mul(rs, tE[e]));
-            for (int e = 0; e < 3; e++) t[e] = mul(ts, tv[e]);
-            int infront = 0;
-            for (int k = 0; k < 5; k++) {
-                const double a0 = add(add(mul(R[0], x1[k]), mul(R[1], y1[k])), R[2]);
-                const double a1 = add(add(mul(R[3], x1[k]), mul(R[4], y1[k])), R[5]);
-                const double a2 = add(add(mul(R[6], x1[k]), mul(R[7], y1[k])), R[8]);
-                const double b0 = x2[k], b1 = y2[k], b2 = 1.0;
-                const double aa = add(add(mul(a0, a0), mul(a1, a1)), mul(a2, a2)), bb = add(add(mul(b0, b0), mul(b1, b1)), mul(b2, b2));
-                const double ab = add(add(mul(a0, b0), mul(a1, b1)), mul(a2, b2));
-                const double at = add(add(mul(a0, t[0]), mul(a1, t[1])), mul(a2, t[2])), bt = add(add(mul(b0, t[0]), mul(b1, t[1])), mul(b2, t[2]));
-                const double det = sub(mul(aa, bb), mul(ab, ab));
-                const double l1 = dvd(sub(mul(ab, bt), mul(bb, at)), det), l2 = dvd(sub(mul(aa, bt), mul(ab, at)), det);
-                if (l1 > 0.0 && l2 > 0.0) infront++; else break;
-            }
-            if (infront == 5) pass = true;
-        }
-        if (pass) {
+        if (stage_root(C, L, X, roots[ri], E)) {
             for (int e = 0; e < 9; e++) out[e] = (float)E[e];
             return 1;
         }
     }
     return 0;
+}
+
+// one warp per sample: `sm` points to E5_WARP_DOUBLES doubles of shared memory owned by this warp. Every lane returns the
+// model count; lane 0 .. (the lane that owns the winning root) writes `out`.
+#define E5_WARP_DOUBLES (20 + 36 + 200 + 22 + 22 + 242 + 24 + 24 + 20)
+__device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s, float* out, double* sm) {
+    using namespace e5;
+    const int lane = threadIdx.x & 31;
+    double* X = sm;                                                    // 20
+    double (*L)[4] = reinterpret_cast<double (*)[4]>(sm + 20);         // 36
+    double (*C)[20] = reinterpret_cast<double (*)[20]>(sm + 56);       // 200
+    double* dd = sm + 256;                                             // 2 x 11
+    double* coef = sm + 278;                                           // 2 x 11
+    double* der = sm + 300;                                            // 2 x 11 x 11 derivative tables
+    double* prev = sm + 542;                                           // 2 x 12 roots of the previous level
+    double* cur = sm + 566;                                            // 2 x 12
+    double* roots = sm + 590;                                          // 20
+    __shared__ int sh_i[8][8];                                         // per warp: ok, deg0, deg1, nprev0, nprev1, nroots
+    int* si = sh_i[(threadIdx.x >> 5) & 7];
+    if (lane == 0) si[0] = stage_constraints(pts, s, X, L, C) ? 1 : 0;
+    __syncwarp();
+    if (!si[0]) return 0;
+    if (lane < 22) dd[lane] = stage_det(C, lane / 11, lane % 11);
+    __syncwarp();
+    if (lane < 2) {
+        const int deg = stage_coefficients(dd + 11 * lane, coef + 11 * lane);
+        si[1 + lane] = deg;
+        if (deg >= 1) {                                                // derivative tables + the root of the linear one (real_roots)
+            double* D = der + 121 * lane;
+            const double* c = coef + 11 * lane;
+            double bound = 0.0;
+            for (int i = 0; i < deg; i++) { const double v = fabs(dvd(c[i], c[deg])); if (v > bound) bound = v; }
+            bound = add(bound, 1.0);
+            for (int i = 0; i <= deg; i++) D[deg * 11 + i] = c[i];
+            for (int d = deg; d > 1; d--)
+                for (int i = 0; i < d; i++) D[(d - 1) * 11 + i] = mul(D[d * 11 + i + 1], (double)(i + 1));
+            double* P = prev + 12 * lane;
+            P[11] = bound;
+            int np = 1;
+            P[0] = -dvd(D[1 * 11 + 0], D[1 * 11 + 1]);
+            if (!(fabs(P[0]) <= bound)) np = 0;
+            if (!(bound < 1e300)) { np = 0; si[1 + lane] = 0; }         // real_roots returns no roots
+            si[3 + lane] = np;
+        }
+    }
+    __syncwarp();
+    if (si[1] < 0 || si[2] < 0) return 0;
+    // derivative levels 2..deg of both polynomials: lane (16*pass + k) owns bracket k of the level
+    const int pass = lane >> 4, k = lane & 15;
+    const int deg = si[1 + pass];
+    const int maxdeg = max(si[1], si[2]);
+    for (int d = 2; d <= maxdeg; d++) {
+        bool has = false;
+        double val = 0.0;
+        const int np = (d <= deg) ? si[3 + pass] : 0;
+        if (d <= deg && k <= np + 1) {
+            const double* p = der + 121 * pass + 11 * d;
+            const double* P = prev + 12 * pass;
+            const double bound = P[11];
+            if (k <= np) {
+                const double left = k == 0 ? -bound : P[k - 1], right = k < np ? P[k] : bound;
+                const double pl = horner(p, d, left), pr = horner(p, d, right);
+                if (pl == 0.0) { has = true; val = left; }
+                else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { has = true; val = bisect(p, d, left, right, pl); }
+            } else if (horner(p, d, bound) == 0.0) { has = true; val = bound; }   // the closing `if (pl == 0.0)` of real_roots
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        const unsigned mine = (bal >> (16 * pass)) & 0xffffu;
+        if (has) cur[12 * pass + __popc(mine & ((1u << k) - 1))] = val;
+        __syncwarp();
+        if (d <= deg) {
+            const int nc = __popc(mine);
+            if (k < nc) prev[12 * pass + k] = cur[12 * pass + k];
+            if (k == 0) si[3 + pass] = nc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        int nroots = 0;
+        for (int ps = 0; ps < 2; ps++)
+            if (si[1 + ps] >= 1) nroots = stage_collect(ps, prev + 12 * ps, si[3 + ps], roots, nroots);
+        stage_sort(roots, nroots);
+        si[5] = nroots;
+    }
+    __syncwarp();
+    const int nroots = si[5];
+    double E[9];
+    const bool ok = lane < nroots && stage_root(C, L, X, roots[lane], E);
+    const unsigned win = __ballot_sync(0xffffffffu, ok);
+    if (!win) return 0;
+    if (lane == __ffs(win) - 1) for (int e = 0; e < 9; e++) out[e] = (float)E[e];
+    return 1;
 }

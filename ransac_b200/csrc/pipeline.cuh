@@ -244,6 +244,41 @@ __global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
     *nm = k;
 }
 
+// Essential matrices: one WARP per sample (essential.cuh, solve_essential5_warp) - the one-thread form of the five-point solver
+// is latency bound at ~3 ms per sample, the warp form spreads its independent pieces over the lanes (bit-identical results).
+#define E5_WARPS_PER_CTA 4
+__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) solve_kernel_e5_warp(const RoundArgs a) {
+    __shared__ double sm[E5_WARPS_PER_CTA][E5_WARP_DOUBLES];
+    const int slot = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * E5_WARPS_PER_CTA + w;
+    if (j >= a.K) return;                                               // whole warps leave together
+    int* nm = a.nmodels + (size_t)slot * a.K + j;
+    if (a.nranks > 1 && (j % a.nranks) != a.rank) { if (lane == 0) *nm = 0; return; }
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const float* pts = a.aos + (size_t)pd.aos_off * 4;
+    int s[8];
+    const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
+    for (int i = 0; i < a.m; i++) s[i] = src[i];
+    float* dst = a.models_raw + ((size_t)slot * a.K + j) * a.S * 9;
+    const int k = solve_essential5_warp(pts, s, dst, sm[w]);
+    if (lane == 0) *nm = k;
+}
+__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) estimate_kernel_e5_warp(const float* __restrict__ pts, const int* __restrict__ samples, int K,
+                                                                                float* __restrict__ models, int* __restrict__ nmodels) {
+    __shared__ double sm[E5_WARPS_PER_CTA][E5_WARP_DOUBLES];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * E5_WARPS_PER_CTA + w;
+    if (j >= K) return;
+    int s[8];
+    for (int i = 0; i < 5; i++) s[i] = samples[(size_t)j * 5 + i];
+    float* dst = models + (size_t)j * 9;
+    if (lane < 9) dst[lane] = 0.f;
+    __syncwarp();
+    const int k = solve_essential5_warp(pts, s, dst, sm[w]);
+    if (lane == 0) nmodels[j] = k;
+}
+
 // standalone Estimator API (usac_gpu_estimate)
 template <int EST>
 __global__ void __launch_bounds__(64) estimate_kernel(const float* __restrict__ pts, const int* __restrict__ samples, int K, int m, int S,

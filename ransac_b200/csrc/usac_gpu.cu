@@ -872,7 +872,7 @@ extern "C" int usac_gpu_estimate(usac_gpu_ctx* c, int problem, const int* sample
         case USAC_EST_LINE2D: estimate_kernel<USAC_EST_LINE2D><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
         case USAC_EST_HOMOGRAPHY: estimate_kernel<USAC_EST_HOMOGRAPHY><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
         case USAC_EST_FUNDAMENTAL: estimate_kernel<USAC_EST_FUNDAMENTAL><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
-        default: estimate_kernel<USAC_EST_ESSENTIAL><<<g, 64, 0, c->stream>>>(aos, c->d_samples.p, K, m, S, c->d_models_raw.p, c->d_nmodels.p); break;
+        default: estimate_kernel_e5_warp<<<(K + E5_WARPS_PER_CTA - 1) / E5_WARPS_PER_CTA, 32 * E5_WARPS_PER_CTA, 0, c->stream>>>(aos, c->d_samples.p, K, c->d_models_raw.p, c->d_nmodels.p); break;
     }
     CUDA_TRY(c, cudaMemcpyAsync(models_out, c->d_models_raw.p, sizeof(float) * K * S * 9, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(nmodels_out, c->d_nmodels.p, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
@@ -892,8 +892,13 @@ extern "C" int usac_gpu_set_allgather(usac_gpu_ctx* c, usac_allgather_fn fn, voi
 
 template <int EST>
 static void launch_round_est(usac_gpu_ctx* c, const RoundArgs& a, int slots, bool sprt) {
-    dim3 gs((a.K + 63) / 64, slots);
-    solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    if (EST == USAC_EST_ESSENTIAL) {
+        dim3 gw((a.K + E5_WARPS_PER_CTA - 1) / E5_WARPS_PER_CTA, slots);
+        solve_kernel_e5_warp<<<gw, 32 * E5_WARPS_PER_CTA, 0, c->stream>>>(a);
+    } else {
+        dim3 gs((a.K + 63) / 64, slots);
+        solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    }
     c->last_launches++;
 }
 template <int EST>
@@ -1077,8 +1082,13 @@ static int fetch_mask(usac_gpu_ctx* c, int problem, const float* model, float th
 
 template <int EST>
 static void launch_solve(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
-    dim3 gs((a.K + 63) / 64, slots);
-    solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    if (EST == USAC_EST_ESSENTIAL) {
+        dim3 gw((a.K + E5_WARPS_PER_CTA - 1) / E5_WARPS_PER_CTA, slots);
+        solve_kernel_e5_warp<<<gw, 32 * E5_WARPS_PER_CTA, 0, c->stream>>>(a);
+    } else {
+        dim3 gs((a.K + 63) / 64, slots);
+        solve_kernel<EST><<<gs, 64, 0, c->stream>>>(a);
+    }
     c->last_launches++;
 }
 template <int EST>
