@@ -97,7 +97,7 @@ struct ProsacTermHost {
         std::vector<double> pn(n);
         for (size_t nn = (size_t)m + 1; nn <= n; ++nn) {
             if (nn - 1 > 1000) { non_random_inliers[nn - 1] = non_random_inliers[nn - 2]; continue; }
-            std::fill(pn.begin(), pn.end(), 0.0);
+            std::fill(pn.begin(), pn.begin() + nn, 0.0);              // entries [m, nn) are the only ones read below
             pn[m] = (beta) * std::pow((double)1 - beta, (double)nn - m - 1) * (nn - m);
             double cur = pn[m];
             for (size_t i = (size_t)m + 2; i <= nn; ++i) {

@@ -41,37 +41,44 @@ __device__ __forceinline__ double refit_tree_d(double v, double* sm) {
     return r;
 }
 
-__device__ void refit_smallest_eigenvector(double* S, int n, double* vec, double* V) {     // S, V: n x n
-    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+// Eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (n <= 9; S, V in shared memory): 12 cyclic Jacobi
+// sweeps, executed by the first warp - lane k owns index k of every rotation update (row/column element k), which are
+// independent of each other, so the arithmetic per element is exactly that of the sequential loops of the host restatement.
+__device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, double* V) {
+    const int k = threadIdx.x & 31;
+    for (int i = k; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    __syncwarp();
     for (int sweep = 0; sweep < 12; sweep++)
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const sd apq(S[p * n + q]);
-                if (apq.v == 0.0) continue;
+                if (apq.v == 0.0) continue;                              // uniform: every lane reads the same element
                 const sd theta = (sd(S[q * n + q]) - sd(S[p * n + p])) / (sd(2.0) * apq);
                 const sd tt = sd(1.0) / (sd(fabs(theta.v)) + dsqrt(theta * theta + sd(1.0)));
                 const sd t = theta.v < 0.0 ? -tt : tt;
                 const sd c = sd(1.0) / dsqrt(t * t + sd(1.0)), s = t * c;
+                __syncwarp();                                            // everyone has read S[p][q], S[p][p], S[q][q]
                 if (!dfinite(c.v) || !dfinite(s.v)) continue;
-                for (int k = 0; k < n; k++) {
+                if (k < n) {
                     const sd a(S[k * n + p]), b(S[k * n + q]);
                     S[k * n + p] = (c * a - s * b).v;
                     S[k * n + q] = (s * a + c * b).v;
                 }
-                for (int k = 0; k < n; k++) {
+                __syncwarp();
+                if (k < n) {
                     const sd a(S[p * n + k]), b(S[q * n + k]);
                     S[p * n + k] = (c * a - s * b).v;
                     S[q * n + k] = (s * a + c * b).v;
+                    const sd va(V[k * n + p]), vb(V[k * n + q]);
+                    V[k * n + p] = (c * va - s * vb).v;
+                    V[k * n + q] = (s * va + c * vb).v;
                 }
-                for (int k = 0; k < n; k++) {
-                    const sd a(V[k * n + p]), b(V[k * n + q]);
-                    V[k * n + p] = (c * a - s * b).v;
-                    V[k * n + q] = (s * a + c * b).v;
-                }
+                __syncwarp();
             }
     int best = 0;
     for (int i = 1; i < n; i++) if (S[i * n + i] < S[best * n + best]) best = i;
-    for (int k = 0; k < n; k++) vec[k] = V[k * n + best];
+    if (k < n) vec[k] = V[k * n + best];
+    __syncwarp();
 }
 
 // ok_out: 1 when a model was written. ids: point ids (within the problem), n of them.
@@ -164,8 +171,9 @@ __global__ void __launch_bounds__(REFIT_THREADS) nonminimal_kernel(const float* 
             if (t == 0) { S[i * 9 + j] = v; S[j * 9 + i] = v; }
         }
     __syncthreads();
+    if (t >= 32) return;
+    refit_smallest_eigenvector_warp(S, 9, h, V);
     if (t != 0) return;
-    refit_smallest_eigenvector(S, 9, h, V);
     sd M[9], R[9];
     const sd S1((double)s1), T1x((double)t1x), T1y((double)t1y), S2((double)s2), T2x((double)t2x), T2y((double)t2y);
     for (int i = 0; i < 3; i++) {
