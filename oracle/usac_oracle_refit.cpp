@@ -179,7 +179,7 @@ extern "C" int orc_refit(int est, const float* pts, int n_points, float thr, flo
     int cnt = 0;
     float sum = 0;
     orc_score(est, pts, n_points, model_io, thr, &cnt, &sum, cur.data(), 0, nullptr);          /* quality->getInliers, :163 */
-    int prev = 0, accepted = 0, best = best_inliers;
+    int prev = 0, accepted = 0, best = best_inliers < cnt ? best_inliers : cnt;   /* never read past the list */
     for (int norm = 0; norm < 4; norm++) {
         float m[9];
         if (!orc_nonminimal(est, pts, cur.data(), best, m)) break;                               /* :173 uses best_score->inlier_number ids */
@@ -318,11 +318,12 @@ extern "C" void orc_lo_get_model_score(orc_lo* o, float* best_model, int* best_i
     lo_score(L, best_model, L.theta, cnt, sum, L.max_inliers);                       /* quality->getInliers(best_model), :79 */
     float lo_model[9];
     int sample[16];
+    int avail = best_inl < cnt ? best_inl : cnt;                                      /* ids present in max_inliers */
     for (int it = 0; it < L.inner_iters; it++) {
-        if (best_inl > L.sample_limit) {
-            lo_random_subset(L, best_inl, L.max_inliers, sample);
+        if (avail > L.sample_limit) {
+            lo_random_subset(L, avail, L.max_inliers, sample);
             if (!orc_nonminimal(L.est, L.pts, sample, L.sample_limit, lo_model)) continue;
-        } else if (!orc_nonminimal(L.est, L.pts, L.max_inliers.data(), best_inl, lo_model)) {
+        } else if (!orc_nonminimal(L.est, L.pts, L.max_inliers.data(), avail, lo_model)) {
             break;
         }
         L.lo_thr = (unsigned)L.mult * L.lo_thr;                                      /* :101 */
@@ -333,7 +334,7 @@ extern "C" void orc_lo_get_model_score(orc_lo* o, float* best_model, int* best_i
         const bool fail = lo_iterative(L, lo_inl, lo_sum, lo_model, best_inl, best_sum);
         if (!fail && bigger2(lo_inl, lo_sum, best_inl, best_sum)) {
             memcpy(best_model, lo_model, sizeof(float) * w);
-            best_inl = lo_inl; best_sum = lo_sum;
+            best_inl = lo_inl; best_sum = lo_sum; avail = lo_inl;
             L.max_inliers.resize((size_t)L.n);
             for (int i = 0; i < lo_inl; i++) L.max_inliers[i] = L.lo_inliers[i];
         }

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const 
     const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
     const double eps = st.sprt_eps, delta = st.sprt_delta, A = st.sprt_A;
     const double r_in = __ddiv_rn(delta, eps), r_out = __ddiv_rn(__dsub_rn(1.0, delta), __dsub_rn(1.0, eps));
-    auto wrap = [n](int v) { return v >= n ? v - n : v; };
+    auto wrap = [n](int v) { while (v >= n) v -= n; return v; };      // n may be as small as the minimal sample
     int idx = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q) % (unsigned long long)n);
     double lambda = 1.0;
     int tp = 0, tin = 0;

@@ -683,7 +683,10 @@ extern "C" int usac_gpu_refit(usac_gpu_ctx* c, int problem, const float* model_i
     launch_inliers(c, aos, d.n, c->d_q_recs.p, threshold, cur, cur + d.n);                 // quality->getInliers(best_model), ransac.cpp:163
     memset(out, 0, sizeof(*out));
     for (int i = 0; i < w; i++) out->model[i] = model_in[i];
-    int best = std::min(best_inliers, d.n), prev = 0;
+    int avail = 0;                                                                         // ids actually present in the list
+    CUDA_TRY(c, cudaMemcpyAsync(&avail, cur + d.n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int best = std::min(best_inliers, avail), prev = 0;                                     // never read past the list (the reference would)
     for (int norm = 0; norm < 4; norm++) {
         float m2[9];
         int ok = 0, c2 = 0;
@@ -1028,13 +1031,14 @@ struct LoRunner {
         float sum;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, best_model, sizeof(float) * w, cudaMemcpyHostToDevice, c->stream));
         if ((rc = score(c->d_q_models.p, theta, A, cnt, sum))) return rc;      // quality->getInliers(best_model)
+        int avail = std::min(best_inl, cnt);                                      // ids present in A (never index past the list)
         for (int it = 0; it < inner_iters; it++) {
             bool ok = false;
-            if (best_inl > sample_limit) {
-                if ((rc = fit_random_subset(A, best_inl, ok))) return rc;
+            if (avail > sample_limit) {
+                if ((rc = fit_random_subset(A, avail, ok))) return rc;
                 if (!ok) continue;
             } else {
-                if ((rc = fit_ids(A, best_inl, ok))) return rc;
+                if ((rc = fit_ids(A, avail, ok))) return rc;
                 if (!ok) break;
             }
             lo_thr = (unsigned)mult * lo_thr;                                     // inner_local_optimization.hpp:101
@@ -1048,7 +1052,7 @@ struct LoRunner {
                 CUDA_TRY(c, cudaMemcpyAsync(best_model, d_model, sizeof(float) * w, cudaMemcpyDeviceToHost, c->stream));
                 CUDA_TRY(c, cudaMemcpyAsync(A, B, sizeof(int) * lo_inl, cudaMemcpyDeviceToDevice, c->stream));
                 CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-                best_inl = lo_inl; best_sum = lo_sum;
+                best_inl = lo_inl; best_sum = lo_sum; avail = lo_inl;
             }
             inner_done++;
         }
@@ -1311,6 +1315,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     rc = push_desc(c);
     if (rc) return rc;
     if (cfg->sampler.rng == USAC_RNG_TABLE) {
+        const int n0 = c->h_prob[0].n;
+        for (size_t i = 0; i < (size_t)cfg->sample_table_rows * m; i++)
+            if (cfg->sample_table[i] < 0 || cfg->sample_table[i] >= n0) return fail(c, USAC_ERR_ARG, "fit: sample table index out of range");
         CUDA_TRY(c, c->d_table.ensure((size_t)cfg->sample_table_rows * m));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_table.p, cfg->sample_table, sizeof(int) * (size_t)cfg->sample_table_rows * m, cudaMemcpyHostToDevice, c->stream));
     }
