@@ -58,7 +58,7 @@ public:
         if (last_fit.inliers <= 0) throw std::runtime_error("Ransac: best score is 0");           // ransac.cpp:143-147
         usac_refit_result rf{};                                                                   // ransac.cpp:157-207 on the device
         device->check(usac_gpu_refit(device->ctx, 0, last_fit.model, last_fit.inliers, model->threshold, &rf), "usac_gpu_refit");
-        finish(rf.model, rf.inliers, last_fit.iterations, t0);
+        finish(rf.model, rf.inliers, last_fit.iterations, t0, last_fit.lo_inner_iters, last_fit.lo_iterative_iters);
     }
 
     void run_sequential() {
@@ -110,7 +110,8 @@ public:
     }
 
 private:
-    void finish(const float* params, int inlier_number, unsigned int iters, std::chrono::steady_clock::time_point t0) {
+    void finish(const float* params, int inlier_number, unsigned int iters, std::chrono::steady_clock::time_point t0,
+                unsigned int lo_inner = 0, unsigned int lo_iterative = 0) {
         if (inlier_number <= 0) throw std::runtime_error("Ransac: best score is 0");
         const bool line = model->estimator == Line2d;
         cv::Mat d = line ? cv::Mat(1, 3) : cv::Mat(3, 3);
@@ -121,6 +122,6 @@ private:
         quality->getInliers(d, inliers.data());                                       // ransac.cpp:210
         const long us = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
         delete ransac_output;
-        ransac_output = new RansacOutput(&best, inliers.data(), us, (unsigned int)inlier_number, iters, 0, 0, 0);
+        ransac_output = new RansacOutput(&best, inliers.data(), us, (unsigned int)inlier_number, iters, lo_inner, lo_iterative, 0);
     }
 };

@@ -89,3 +89,24 @@ def test_fused_equals_sequential_equals_oracle(harness, tmp_path, cfg, est_name,
     assert f["iterations"] == ref["iterations"] and f["inliers"] == fin["inliers"]
     assert np.array_equal(f["model"], np.asarray(fin["model"], np.float32).view(np.uint32))
     assert f["hash"] == fnv(fin["ids"][:fin["inliers"]])
+
+
+@pytest.mark.gpu
+def test_harness_report_and_statistics_csv(harness, tmp_path):
+    """The reference's human-readable block (test/test.cpp:38-53) and one statistics row in its CSV layout (helper/Logging.h:47-97)."""
+    from ransac_b200 import generator as gen
+    pts, H, mask = gen.homography(n=1500, seed=3)
+    p, csv = tmp_path / "p.txt", tmp_path / "out.csv"
+    write_points(p, pts)
+    r = subprocess.run([harness, str(p), "homography", "uniform", "2", "0.95", "1", "--lo", "1", "--report"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for token in ("uniform_homography", "Main iterations:", "LO iterations:", "points under threshold:", "Best model = ..."):
+        assert token in r.stdout
+    r = subprocess.run([harness, str(p), "homography", "uniform", "2", "0.95", "1", "--runs", "5", "--csv", str(csv), "--gt-inliers", str(int(mask.sum()))],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(csv).read().splitlines()
+    head = next(ln for ln in lines if ln.startswith("Filename,GT Inl"))
+    row = lines[lines.index(head) + 1].split(",")
+    assert len(row) == len(head.split(",")) == 22
+    assert float(row[2]) > 0.95 * mask.sum() and row[19:] == ["0", "0", "0"]    # every run found the structure
