@@ -72,25 +72,46 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
         b11 = -r[9]; b12 = -r[10]; b13 = -r[11]; b21 = -r[12]; b22 = -r[13]; b23 = -r[14]; g31 = r[15]; g32 = r[16]; g33 = r[17];
         negT = -2.f * r[REC_THR]; k1 = r[REC_BAND]; k2 = r[REC_BAND + 1];
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+    // Two phases. The symmetric transfer error is (d1 + d2)/2 with d1, d2 >= 0, so a point whose FORWARD distance alone
+    // exceeds 2*thr by more than the forward guard band is an outlier whatever the backward distance is (also when the
+    // backward term is NaN: the reference's sum is then NaN and fails `err < thr` as well). phase1 computes d1 and that
+    // verdict; the kernel runs phase2 (the backward half, 60 % of the arithmetic) only for the pairs of points on which some
+    // lane of the warp still needs it - for the random-sample hypotheses of a RANSAC round that is a small minority.
+    static constexpr bool TWO_PHASE = true;
+    struct P1 { float2 u, p1; };                                           // u = d1 - 2*thr, p1 = k1/nz (forward band)
+    __device__ __forceinline__ void phase1(const float4 A, const float4 B, P1& s) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 nz = __ffma2_rn(dup(h31), X1, __ffma2_rn(dup(h32), Y1, dup(h33)));
         const float2 nx = __ffma2_rn(dup(a11), X1, __ffma2_rn(dup(a12), Y1, dup(a13)));   // -(h11 x1 + h12 y1 + h13)
         const float2 ny = __ffma2_rn(dup(a21), X1, __ffma2_rn(dup(a22), Y1, dup(a23)));
+        const float2 r1 = make_float2(fast_rcp(nz.x), fast_rcp(nz.y));
+        const float2 dx = __ffma2_rn(nx, r1, X2), dy = __ffma2_rn(ny, r1, Y2);
+        const float2 sa = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+        const float2 d1 = make_float2(fast_sqrt(sa.x), fast_sqrt(sa.y));
+        s.u = __fadd2_rn(d1, dup(negT));
+        s.p1 = __fmul2_rn(dup(k1), r1);
+    }
+    static __device__ __forceinline__ bool sure_outlier(float u, float p1) { return u > fabsf(p1); }      // false for NaN
+    __device__ __forceinline__ void phase2(const float4 A, const float4 B, const P1& s, float2& t, float2& band) const {
+        const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 mz = __ffma2_rn(dup(g31), X2, __ffma2_rn(dup(g32), Y2, dup(g33)));
         const float2 mx = __ffma2_rn(dup(b11), X2, __ffma2_rn(dup(b12), Y2, dup(b13)));
         const float2 my = __ffma2_rn(dup(b21), X2, __ffma2_rn(dup(b22), Y2, dup(b23)));
-        const float2 q = __fmul2_rn(nz, mz);
-        const float2 r = make_float2(fast_rcp(q.x), fast_rcp(q.y));        // one reciprocal serves both projections
-        const float2 r1 = __fmul2_rn(r, mz), r2 = __fmul2_rn(r, nz);       // 1/nz, 1/mz
-        const float2 dx = __ffma2_rn(nx, r1, X2), dy = __ffma2_rn(ny, r1, Y2);
+        const float2 r2 = make_float2(fast_rcp(mz.x), fast_rcp(mz.y));
         const float2 ex = __ffma2_rn(mx, r2, X1), ey = __ffma2_rn(my, r2, Y1);
-        const float2 sa = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
         const float2 sb = __ffma2_rn(ey, ey, __fmul2_rn(ex, ex));
-        const float2 d1 = make_float2(fast_sqrt(sa.x), fast_sqrt(sa.y)), d2 = make_float2(fast_sqrt(sb.x), fast_sqrt(sb.y));
-        t = __fadd2_rn(__fadd2_rn(d1, dup(negT)), d2);                     // 2*err - 2*thr
-        const float2 p1 = __fmul2_rn(dup(k1), r1), p2 = __fmul2_rn(dup(k2), r2);
-        s = make_float2(fabsf(p1.x) + fabsf(p2.x), fabsf(p1.y) + fabsf(p2.y));
+        const float2 d2 = make_float2(fast_sqrt(sb.x), fast_sqrt(sb.y));
+        t = __fadd2_rn(s.u, d2);                                           // 2*err - 2*thr
+        const float2 p2 = __fmul2_rn(dup(k2), r2);
+        band = make_float2(fabsf(s.p1.x) + fabsf(p2.x), fabsf(s.p1.y) + fabsf(p2.y));
+    }
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+        P1 st;
+        phase1(A, B, st);
+        phase2(A, B, st, t, s);
+        // a lane that phase1 already proves an outlier is decided, whatever the backward half says (it may be NaN)
+        if (sure_outlier(st.u.x, st.p1.x)) { t.x = st.u.x; s.x = 0.f; }
+        if (sure_outlier(st.u.y, st.p1.y)) { t.y = st.u.y; s.y = 0.f; }
         w = t;
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
@@ -98,6 +119,7 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
 };
 
 template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
+    static constexpr bool TWO_PHASE = false;
     float f11, f12, f13, f21, f22, f23, f31, f32, f33, negthr, b1, b0;
     __device__ __forceinline__ void load(const float* r) {
         f11 = r[0]; f12 = r[1]; f13 = r[2]; f21 = r[3]; f22 = r[4]; f23 = r[5]; f31 = r[6]; f32 = r[7]; f33 = r[8];
@@ -121,6 +143,7 @@ template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
 };
 
 template <> struct FastModel<USAC_EST_ESSENTIAL> {
+    static constexpr bool TWO_PHASE = false;
     float e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0;
     __device__ __forceinline__ void load(const float* r) {
         e11 = r[0]; e12 = r[1]; e13 = r[2]; e21 = r[3]; e22 = r[4]; e23 = r[5]; e31 = r[6]; e32 = r[7]; e33 = r[8];
@@ -149,6 +172,7 @@ template <> struct FastModel<USAC_EST_ESSENTIAL> {
 };
 
 template <> struct FastModel<USAC_EST_LINE2D> {
+    static constexpr bool TWO_PHASE = false;
     float a, b, c, negthr, band;
     __device__ __forceinline__ void load(const float* r) { a = r[0]; b = r[1]; c = r[2]; negthr = -r[REC_THR]; band = r[REC_BAND]; }
     // line pairs are [xa xb ya yb]: one float4 per pair (B unused)
@@ -279,15 +303,41 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                 for (; j + USAC_PPI <= np; j += USAC_PPI) {
                     float2 em[USAC_PPI];
                     bool unsure = false;
+                    if constexpr (FastModel<EST>::TWO_PHASE) {
+                        typename FastModel<EST>::P1 st[USAC_PPI];
+                        bool need[USAC_PPI];
 #pragma unroll
-                    for (int q = 0; q < USAC_PPI; q++) {
-                        float4 A, B;
-                        load_pair(j + q, A, B);
-                        float2 t, sb, w;
-                        fm.eval(A, B, t, sb, w);
-                        em[q] = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
-                        if (EST == USAC_EST_FUNDAMENTAL) em[q] = __fmul2_rn(em[q], w);
-                        unsure = unsure || !(fabsf(t.x) > sb.x) || !(fabsf(t.y) > sb.y);   // also catches NaN
+                        for (int q = 0; q < USAC_PPI; q++) {                                    // forward halves, independent streams
+                            float4 A, B;
+                            load_pair(j + q, A, B);
+                            fm.phase1(A, B, st[q]);
+                            need[q] = __any_sync(0xffffffffu, !FastModel<EST>::sure_outlier(st[q].u.x, st[q].p1.x) ||
+                                                                  !FastModel<EST>::sure_outlier(st[q].u.y, st[q].p1.y));
+                        }
+#pragma unroll
+                        for (int q = 0; q < USAC_PPI; q++) {
+                            em[q] = make_float2(0.f, 0.f);
+                            if (need[q]) {                                                      // warp-uniform
+                                float4 A, B;
+                                load_pair(j + q, A, B);
+                                float2 t, sb;
+                                fm.phase2(A, B, st[q], t, sb);
+                                const bool ox = FastModel<EST>::sure_outlier(st[q].u.x, st[q].p1.x), oy = FastModel<EST>::sure_outlier(st[q].u.y, st[q].p1.y);
+                                em[q] = make_float2(ox ? 0.f : fminf(t.x, 0.f), oy ? 0.f : fminf(t.y, 0.f));
+                                unsure = unsure || (!ox && !(fabsf(t.x) > sb.x)) || (!oy && !(fabsf(t.y) > sb.y));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < USAC_PPI; q++) {
+                            float4 A, B;
+                            load_pair(j + q, A, B);
+                            float2 t, sb, w;
+                            fm.eval(A, B, t, sb, w);
+                            em[q] = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
+                            if (EST == USAC_EST_FUNDAMENTAL) em[q] = __fmul2_rn(em[q], w);
+                            unsure = unsure || !(fabsf(t.x) > sb.x) || !(fabsf(t.y) > sb.y);   // also catches NaN
+                        }
                     }
                     if (__any_sync(0xffffffffu, unsure)) break;
 #pragma unroll
