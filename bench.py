@@ -214,7 +214,7 @@ def run_native(args):
         res = ctx.fit_records(**fit_kw)
         t = ctx.last_timing()
         return (int(res["useful_evals"].sum()), int(res["evals"].sum()), t["launches"], t["score_launches"], t["score_ms"],
-                int(res["iterations"].sum()), int(res["rounds"].max()))
+                int(res["iterations"].sum()), int(res["rounds"].max()), int(res["rounds"].sum()))
 
     # e2e: the public API with HOST buffers. n_pipe contexts (streams, host threads) each own a share of the step's image pairs,
     # so that the host->device copy of one share overlaps the fits of the others (the copy engine and the SMs run
@@ -351,7 +351,10 @@ def run_native(args):
         except Exception:   # noqa: BLE001
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes_launch = (16.0 * N_POINTS * B + 128.0 * executed / N_POINTS) / 1.0       # every point once per pass + the model records
+        # HBM side of one launch: the points of every image pair still active in that round once (16 B per point) + one
+        # 128-byte record per model scored; sum(rounds) over the fits = number of (image pair, launch) incidences
+        pair_launches = sum(s[7] for s in stats)
+        alg_bytes_launch = (16.0 * N_POINTS * pair_launches + 128.0 * executed / N_POINTS) / max(score_launches, 1)
         traffic, traffic_note = None, None
         try:   # DRAM bytes of one ncu --set full capture of this kernel (profiles/): a full-size launch, not this run's average
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))

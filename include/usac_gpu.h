@@ -49,6 +49,12 @@ int usac_gpu_set_points(usac_gpu_ctx* ctx, int estimator, const float* points, c
 /* PROSAC assumes rows sorted by descending quality (prosac_sampler.hpp:75); nothing to upload. NAPSAC neighbourhoods: */
 int usac_gpu_set_neighbors_grid(usac_gpu_ctx* ctx, int problem, int cell_size);              /* nearest_neighbors.cpp:160-201 */
 int usac_gpu_set_neighbors_knn(usac_gpu_ctx* ctx, int problem, const int* neighbors, int k); /* nearest_neighbors.cpp:69-128 output */
+/* NearestNeighbors::getNearestNeighbors_nanoflann (nearest_neighbors.cpp:69-128) on the device: exact k nearest neighbours
+ * of every point (squared L2 over all columns, ascending, the query itself dropped; equidistant points in ascending index
+ * order), installed as the problem's kNN table. 1 <= k <= 31, n >= k + 1. */
+int usac_gpu_build_neighbors_knn(usac_gpu_ctx* ctx, int problem, int k);
+/* copy the installed kNN table (n x k) back to the host; k_out receives k */
+int usac_gpu_get_neighbors_knn(usac_gpu_ctx* ctx, int problem, int* neighbors_out, int* k_out);
 /* SPRT's shuffled point pool (sprt.hpp:93-107); host-generated so that it can replay the reference's random() stream */
 int usac_gpu_set_sprt_pool(usac_gpu_ctx* ctx, int problem, const int* pool);
 

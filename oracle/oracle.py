@@ -84,6 +84,8 @@ def lib():
         L.orc_standard_termination.argtypes = [C.c_uint, C.c_uint, C.c_int, C.c_float, C.c_uint]
         L.orc_standard_termination.restype = C.c_uint
         L.orc_grid_cells.argtypes = [fp, C.c_int, C.c_int, ip, ip, ip, ip]
+        L.orc_knn_build.argtypes = [fp, C.c_int, C.c_int, C.c_int, ip]
+        L.orc_knn_build.restype = C.c_int
         L.orc_ransac.argtypes = [C.POINTER(Config), fp, C.c_int, C.POINTER(Result)]
         L.orc_ransac.restype = C.c_int
         L.orc_essential5_candidates.argtypes = [fp, ip, dp, ip]
@@ -207,6 +209,15 @@ def grid_cells(points, cell_size):
     nc = C.c_int()
     lib().orc_grid_cells(_f(p), n, cell_size, _i(cell), _i(members), _i(start), C.byref(nc))
     return cell, members, start[:nc.value + 1].copy()
+
+
+def knn_build(points, k):
+    """n x k table of nearest_neighbors.cpp:69-128 (brute force; ties by ascending index)."""
+    p, n = _pts(points)
+    out = np.empty((n, k), np.int32)
+    if lib().orc_knn_build(_f(p), n, p.shape[1], k, _i(out)) != 0:
+        raise ValueError("knn_build: needs n >= k + 1")
+    return out
 
 
 class Sampler:

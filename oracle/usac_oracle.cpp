@@ -439,6 +439,42 @@ extern "C" int orc_solve_minimal(int estimator, const float* points, const int* 
 }
 
 /* ======================================================================================================
+ * k nearest neighbours, nearest_neighbors.cpp:69-128
+ * ====================================================================================================== */
+
+/* For every point the k+1 closest points by squared L2 distance over all columns (the nanoflann result set, ascending),
+ * minus the first one (the query itself). Brute force with the total order (distance bits, point index), so that the
+ * result is defined for equidistant points too. */
+extern "C" int orc_knn_build(const float* points, int n, int dim, int k, int* table_out) {
+    if (n < k + 1 || k < 1) return -1;
+    std::vector<uint64_t> best((size_t)k + 1);
+    for (int q = 0; q < n; q++) {
+        int have = 0;
+        const float* pq = points + (size_t)q * dim;
+        for (int p = 0; p < n; p++) {
+            const float* pp = points + (size_t)p * dim;
+            float d = 0.f;
+            for (int c = 0; c < dim; c++) {
+                const float diff = pq[c] - pp[c];
+                const float sq = diff * diff;
+                d = c == 0 ? sq : d + sq;
+            }
+            uint32_t bits;
+            std::memcpy(&bits, &d, 4);
+            bits &= 0x7fffffffu;                       /* d >= 0 or NaN: the bit pattern orders like the value, NaN last */
+            if (d != d) bits = 0x7fc00000u;            /* one NaN pattern, whatever payload the hardware produced */
+            uint64_t key = ((uint64_t)bits << 32) | (uint32_t)p;
+            if (have == k + 1 && key >= best[k]) continue;
+            int j = have < k + 1 ? have++ : k;
+            while (j > 0 && best[j - 1] > key) { best[j] = best[j - 1]; j--; }
+            best[j] = key;
+        }
+        for (int j = 0; j < k; j++) table_out[(size_t)q * k + j] = (int)(uint32_t)best[j + 1];
+    }
+    return 0;
+}
+
+/* ======================================================================================================
  * Neighbourhood grid, nearest_neighbors.cpp:160-201
  * ====================================================================================================== */
 

@@ -75,6 +75,14 @@ void orc_philox_unique(uint64_t seed, uint64_t hyp_id, uint32_t stream, int n, i
 /* ---- termination ---- */
 unsigned orc_standard_termination(unsigned inliers, unsigned n, int m, float confidence, unsigned max_iterations);
 
+/* ---- k nearest neighbours (usac/utils/nearest_neighbors.cpp:69-128, nanoflann KD-tree, L2_Simple metric over all `dim`
+ * columns, k+1 results of which the first - the query itself - is dropped; ascending distance). Brute force here.
+ * nanoflann is not in /root/reference (un-vendored, un-pinned): "parity unpinned" for the order of exactly equidistant
+ * neighbours, which in the KD-tree depends on the traversal; the oracle breaks such ties by ascending point index.
+ * Distance: float32, sum of squared differences accumulated in column order, one rounding per operator.
+ * table_out: n x k; returns 0, or -1 when n < k + 1. */
+int orc_knn_build(const float* points, int n, int dim, int k, int* table_out);
+
 /* ---- grid neighbours (usac/utils/nearest_neighbors.cpp:160-201) as CSR: cell id per point, members sorted ---- */
 void orc_grid_cells(const float* points, int n, int cell_size, int* cell_of_point, int* members, int* cell_start,
                     int* ncells_out);

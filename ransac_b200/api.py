@@ -81,6 +81,18 @@ class GpuContext:
         t = np.ascontiguousarray(table, dtype=np.int32)
         self._check(self.L.usac_gpu_set_neighbors_knn(self.h, problem, _ptr(t, C.c_int), t.shape[1]), "set_neighbors_knn")
 
+    def build_neighbors_knn(self, problem, k):
+        """nearest_neighbors.cpp:69-128 on the device; installs the table and returns nothing (see get_neighbors_knn)."""
+        self._check(self.L.usac_gpu_build_neighbors_knn(self.h, problem, int(k)), "build_neighbors_knn")
+        self._knn_k = getattr(self, "_knn_k", {})
+        self._knn_k[problem] = int(k)
+
+    def get_neighbors_knn(self, problem, k_max=31):
+        out = np.empty((int(self.n[problem]), k_max), np.int32)
+        k = C.c_int()
+        self._check(self.L.usac_gpu_get_neighbors_knn(self.h, problem, _ptr(out, C.c_int), C.byref(k)), "get_neighbors_knn")
+        return out.reshape(-1)[:int(self.n[problem]) * k.value].reshape(int(self.n[problem]), k.value).copy()
+
     def set_sprt_pool(self, problem, pool):
         t = np.ascontiguousarray(pool, dtype=np.int32)
         assert t.shape[0] == self.n[problem]

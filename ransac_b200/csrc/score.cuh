@@ -143,28 +143,46 @@ template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
 };
 
 template <> struct FastModel<USAC_EST_ESSENTIAL> {
-    static constexpr bool TWO_PHASE = false;
     float e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0;
     __device__ __forceinline__ void load(const float* r) {
         e11 = r[0]; e12 = r[1]; e13 = r[2]; e21 = r[3]; e22 = r[4]; e23 = r[5]; e31 = r[6]; e32 = r[7]; e33 = r[8];
         negT = -2.f * r[REC_THR]; ka = r[REC_BAND]; kb = r[REC_BAND + 1]; k0 = r[REC_BAND + 2];
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+    // Two phases, as for the homography: err = (da + db)/2 with da = |p1.l|/|l12| (l = E^T p2) and db >= 0, so da alone
+    // beyond 2*thr + (its band + the band of the final sum) proves the outlier; phase2 adds the other epipolar distance.
+    static constexpr bool TWO_PHASE = true;
+    struct P1 { float2 u, p1; };                                           // u = da - 2*thr, p1 = ka/|l12| + k0 (>= 0)
+    __device__ __forceinline__ void phase1(const float4 A, const float4 B, P1& s) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 l1 = __ffma2_rn(dup(e11), X2, __ffma2_rn(dup(e21), Y2, dup(e31)));
         const float2 l2 = __ffma2_rn(dup(e12), X2, __ffma2_rn(dup(e22), Y2, dup(e32)));
         const float2 l3 = __ffma2_rn(dup(e13), X2, __ffma2_rn(dup(e23), Y2, dup(e33)));
+        const float2 a1 = __ffma2_rn(l1, X1, __ffma2_rn(l2, Y1, l3));
+        const float2 a2 = __ffma2_rn(l2, l2, __fmul2_rn(l1, l1));
+        const float2 ra = make_float2(fast_rsqrt(a2.x), fast_rsqrt(a2.y));
+        const float2 pa = __fmul2_rn(a1, ra);
+        s.u = make_float2(fabsf(pa.x) + negT, fabsf(pa.y) + negT);
+        s.p1 = __ffma2_rn(dup(ka), ra, dup(k0));
+    }
+    static __device__ __forceinline__ bool sure_outlier(float u, float p1) { return u > fabsf(p1); }      // false for NaN
+    __device__ __forceinline__ void phase2(const float4 A, const float4 B, const P1& s, float2& t, float2& band) const {
+        const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 t1 = __ffma2_rn(dup(e11), X1, __ffma2_rn(dup(e12), Y1, dup(e13)));
         const float2 t2 = __ffma2_rn(dup(e21), X1, __ffma2_rn(dup(e22), Y1, dup(e23)));
         const float2 t3 = __ffma2_rn(dup(e31), X1, __ffma2_rn(dup(e32), Y1, dup(e33)));
-        const float2 a1 = __ffma2_rn(l1, X1, __ffma2_rn(l2, Y1, l3));
         const float2 b1 = __ffma2_rn(t1, X2, __ffma2_rn(t2, Y2, t3));
-        const float2 a2 = __ffma2_rn(l2, l2, __fmul2_rn(l1, l1));
         const float2 b2 = __ffma2_rn(t2, t2, __fmul2_rn(t1, t1));
-        const float2 ra = make_float2(fast_rsqrt(a2.x), fast_rsqrt(a2.y)), rb = make_float2(fast_rsqrt(b2.x), fast_rsqrt(b2.y));
-        const float2 pa = __fmul2_rn(a1, ra), pb = __fmul2_rn(b1, rb);
-        t = make_float2((fabsf(pa.x) + negT) + fabsf(pb.x), (fabsf(pa.y) + negT) + fabsf(pb.y));   // 2*err - 2*thr
-        s = __ffma2_rn(dup(ka), ra, __ffma2_rn(dup(kb), rb, dup(k0)));
+        const float2 rb = make_float2(fast_rsqrt(b2.x), fast_rsqrt(b2.y));
+        const float2 pb = __fmul2_rn(b1, rb);
+        t = make_float2(s.u.x + fabsf(pb.x), s.u.y + fabsf(pb.y));        // 2*err - 2*thr
+        band = __ffma2_rn(dup(kb), rb, s.p1);
+    }
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+        P1 st;
+        phase1(A, B, st);
+        phase2(A, B, st, t, s);
+        if (sure_outlier(st.u.x, st.p1.x)) { t.x = st.u.x; s.x = 0.f; }
+        if (sure_outlier(st.u.y, st.p1.y)) { t.y = st.u.y; s.y = 0.f; }
         w = t;
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }

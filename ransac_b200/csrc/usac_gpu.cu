@@ -21,6 +21,7 @@
 #include "score.cuh"
 #include "sprt.cuh"
 #include "refit.cuh"
+#include "knn.cuh"
 #include "host_replay.hpp"
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -78,6 +79,8 @@ struct usac_gpu_ctx {
     DevBuf<unsigned long long> d_grid_keys;   // grid build scratch: 2n keys
     DevBuf<int> d_grid_ints;                  // grid build scratch: 4n ints + 1
     DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
+    DevBuf<int> d_knn_cells;                  // kNN build scratch: cell_start of the search grid
+    DevBuf<float4> d_knn_pts;                 // kNN build scratch: points in cell order
     // scoring API buffers
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
     DevBuf<int> d_q_cnt, d_q_ids, d_q_ids2, d_q_ok, d_lo_ids_a, d_lo_ids_b, d_lo_small;
@@ -161,7 +164,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -393,6 +396,72 @@ static cudaError_t reserve_segment(DevBuf<T>& buf, size_t used, size_t count, cu
     buf.release();
     buf = nb;
     return cudaSuccess;
+}
+
+// ---- device-side kNN build (nearest_neighbors.cpp:69-128), kernels in knn.cuh
+template <int DIM>
+static void launch_knn_query(int cap, int blocks, cudaStream_t st, const float4* spts, const int* sidx, const unsigned* skeys, const int* cell_start,
+                             const knn::GridDesc* gd, int G, int n, int k, int* table) {
+    if (cap <= 8) knn::query_kernel<DIM, 8><<<blocks, 128, 0, st>>>(spts, sidx, skeys, cell_start, gd, G, n, k, table);
+    else if (cap <= 16) knn::query_kernel<DIM, 16><<<blocks, 128, 0, st>>>(spts, sidx, skeys, cell_start, gd, G, n, k, table);
+    else knn::query_kernel<DIM, 32><<<blocks, 128, 0, st>>>(spts, sidx, skeys, cell_start, gd, G, n, k, table);
+}
+
+extern "C" int usac_gpu_build_neighbors_knn(usac_gpu_ctx* c, int problem, int k) {
+    if (!c || problem < 0 || problem >= c->P || k < 1 || k > 31) return fail(c, USAC_ERR_ARG, "build_neighbors_knn: bad arguments (1 <= k <= 31)");
+    cudaSetDevice(c->device);
+    ProblemDesc& d = c->h_prob[problem];
+    const int n = d.n, dim = usac_point_dim(c->est);
+    if (n < k + 1) return fail(c, USAC_ERR_ARG, "build_neighbors_knn: needs at least k + 1 points");
+    SideUsed& u = c->side;
+    CUDA_TRY(c, reserve_segment(c->d_knn, u.knn, (size_t)n * k, c->stream));
+    const int G = std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)n / 16.0))));
+    const int ncells = G * G;
+    CUDA_TRY(c, c->d_grid_keys.ensure((size_t)n + 8));                       // 2 x n unsigned keys + bbox + grid descriptor
+    CUDA_TRY(c, c->d_grid_ints.ensure(2 * (size_t)n + 16));
+    CUDA_TRY(c, c->d_knn_cells.ensure((size_t)ncells + 1));
+    CUDA_TRY(c, c->d_knn_pts.ensure((size_t)n));
+    unsigned* keys = reinterpret_cast<unsigned*>(c->d_grid_keys.p);
+    unsigned* skeys = keys + n;
+    int* idx = c->d_grid_ints.p;
+    int* sidx = idx + n;
+    int* bbox = sidx + n;
+    knn::GridDesc* gd = reinterpret_cast<knn::GridDesc*>(bbox + 4);
+    const float* pts = c->d_aos.p + (size_t)d.aos_off * dim;
+    const int g = (n + 255) / 256;
+    knn::bbox_init_kernel<<<1, 1, 0, c->stream>>>(bbox);
+    knn::bbox_kernel<<<std::min(g, 4 * c->prop.multiProcessorCount), 256, 0, c->stream>>>(pts, n, dim, bbox);
+    knn::grid_desc_kernel<<<1, 1, 0, c->stream>>>(bbox, G, gd);
+    knn::cell_keys_kernel<<<g, 256, 0, c->stream>>>(pts, n, dim, gd, G, keys, idx);
+    int bits = 1;
+    while ((1 << bits) < ncells) bits++;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, skeys, idx, sidx, n, 0, bits, c->stream);
+    CUDA_TRY(c, c->d_grid_temp.ensure(tb));
+    CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_grid_temp.p, tb, keys, skeys, idx, sidx, n, 0, bits, c->stream));
+    knn::cell_start_kernel<<<(ncells + 1 + 255) / 256, 256, 0, c->stream>>>(skeys, n, ncells, c->d_knn_cells.p);
+    knn::gather_kernel<<<g, 256, 0, c->stream>>>(pts, n, dim, sidx, c->d_knn_pts.p);
+    int* table = c->d_knn.p + u.knn;
+    if (dim == 4) launch_knn_query<4>(k + 1, (n + 127) / 128, c->stream, c->d_knn_pts.p, sidx, skeys, c->d_knn_cells.p, gd, G, n, k, table);
+    else launch_knn_query<2>(k + 1, (n + 127) / 128, c->stream, c->d_knn_pts.p, sidx, skeys, c->d_knn_cells.p, gd, G, n, k, table);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    d.knn_off = (long long)u.knn;
+    u.knn += (size_t)n * k;
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)n, &d.cursor_off, c->stream));
+    d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
+    return push_desc(c);
+}
+
+extern "C" int usac_gpu_get_neighbors_knn(usac_gpu_ctx* c, int problem, int* neighbors_out, int* k_out) {
+    if (!c || problem < 0 || problem >= c->P || !neighbors_out || !k_out) return fail(c, USAC_ERR_ARG, "get_neighbors_knn: bad arguments");
+    const ProblemDesc& d = c->h_prob[problem];
+    if (d.neigh_type != USAC_NEIGH_KNN || d.knn_off < 0) return fail(c, USAC_ERR_ARG, "get_neighbors_knn: no kNN table installed for this problem");
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(neighbors_out, c->d_knn.p + d.knn_off, (size_t)d.n * d.knn * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *k_out = d.knn;
+    return USAC_OK;
 }
 
 extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cell_size) {

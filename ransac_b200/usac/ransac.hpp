@@ -29,7 +29,8 @@ public:
         estimator = new GpuEstimator(device);
         if (model->sampler == Napsac) {                                               // ransac.hpp:61-78
             if (model->neighborsType == Grid) device->check(usac_gpu_set_neighbors_grid(device->ctx, 0, model->cell_size), "usac_gpu_set_neighbors_grid");
-            else throw std::runtime_error("Ransac: kNN neighbourhoods are supplied with setNeighbors (nanoflann is not part of this layer)");
+            else device->check(usac_gpu_build_neighbors_knn(device->ctx, 0, (int)model->k_nearest_neighbors),      // getNearestNeighbors_nanoflann
+                               "usac_gpu_build_neighbors_knn");
         }
         sampler = new GpuSampler(device, model);                                       // initSampler, init.cpp:23-50
         quality = new GpuQuality(device);

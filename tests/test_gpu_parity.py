@@ -226,6 +226,90 @@ def test_napsac_sampler_matches_oracle(ctx):
     assert np.array_equal(got, ref)
 
 
+def knn_rows_bruteforce(pts, rows, k):
+    """numpy restatement of orc_knn_build for a subset of query rows (float32, column order, (distance, index) ties)."""
+    out = np.empty((len(rows), k), np.int32)
+    p = np.asarray(pts, np.float32)
+    for i, q in enumerate(rows):
+        diff = p[q] - p
+        d = diff[:, 0] * diff[:, 0]
+        for c in range(1, p.shape[1]):
+            d = d + diff[:, c] * diff[:, c]
+        key = (np.where(np.isnan(d), np.float32(np.nan), d).astype(np.float32).view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(len(p), dtype=np.uint64)
+        out[i] = (np.sort(key)[1:k + 1] & np.uint64(0xffffffff)).astype(np.int32)
+    return out
+
+
+@pytest.mark.parametrize("est,n,k", [("homography", 4000, 5), ("homography", 20000, 8), ("homography", 777, 16), ("line2d", 1000, 7),
+                                     ("fundamental", 3000, 31), ("homography", 9, 8)])
+def test_knn_build_matches_oracle(ctx, est, n, k):
+    """usac_gpu_build_neighbors_knn against the oracle's brute force (nearest_neighbors.cpp:69-128): identical tables."""
+    if est == "line2d":
+        pts, _, _ = gen.line2d(n=n, seed=3)
+    elif est == "fundamental":
+        pts, _, _ = gen.fundamental(n=n, seed=3)
+    else:
+        pts, _, _ = gen.homography(n=n, clustered=(n == 20000), seed=3)
+    ctx.set_points(EST[est], pts)
+    ctx.build_neighbors_knn(0, k)
+    got = ctx.get_neighbors_knn(0)
+    assert got.shape == (n, k)
+    assert np.array_equal(got, O.knn_build(pts, k))
+
+
+def test_knn_build_degenerate_inputs(ctx):
+    """Duplicates (ties by index), every point in one spot, a single column of points, non-finite coordinates, k + 1 > n."""
+    g = np.random.default_rng(5)
+    base = g.uniform(0, 100, (300, 4)).astype(np.float32)
+    dup = np.concatenate([base, base[:120], base[:50]])               # exact duplicates: distance 0 ties
+    same = np.tile(np.float32([3, 4, 5, 6]), (200, 1))
+    column = np.stack([np.full(500, 7.0), g.uniform(0, 1000, 500), g.uniform(0, 1000, 500), g.uniform(0, 1000, 500)], 1).astype(np.float32)
+    lattice = np.stack(np.meshgrid(np.arange(20.0), np.arange(20.0), [0.0], [0.0]), -1).reshape(-1, 4).astype(np.float32)   # many equidistant neighbours
+    bad = g.uniform(0, 1000, (400, 4)).astype(np.float32)
+    bad[3, 0] = np.nan; bad[17, 2] = np.inf; bad[40, 1] = -np.inf; bad[41] = np.nan
+    for pts in (dup, same, column, lattice, bad):
+        ctx.set_points(O.EST_HOMOGRAPHY, pts)
+        ctx.build_neighbors_knn(0, 6)
+        assert np.array_equal(ctx.get_neighbors_knn(0), O.knn_build(pts, 6))
+    ctx.set_points(O.EST_HOMOGRAPHY, base[:5])
+    with pytest.raises(RuntimeError):
+        ctx.build_neighbors_knn(0, 5)
+    with pytest.raises(RuntimeError):
+        ctx.build_neighbors_knn(0, 32)
+
+
+def test_knn_build_full_size_1m(ctx):
+    """BASELINE config 5 size (1M correspondences, clustered inliers): 600 random rows against a brute-force restatement,
+    every row free of self-references and duplicates; then a NAPSAC fit over the device-built table against the oracle
+    given the same table."""
+    from ransac_b200.api import NEIGH_KNN, SAMPLER_NAPSAC
+    pts, _, _ = gen.make(5)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    ctx.build_neighbors_knn(0, 6)
+    table = ctx.get_neighbors_knn(0)
+    rows = np.random.default_rng(2).choice(len(pts), 600, replace=False)
+    assert np.array_equal(table[rows], knn_rows_bruteforce(pts, rows, 6))
+    assert (table != np.arange(len(pts))[:, None]).all()
+    srt = np.sort(table, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    r = ctx.fit(2.0, 0.95, 1000, sampler=SAMPLER_NAPSAC, neighbors=NEIGH_KNN, seed=4, round_size=256)[0]
+    ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_KNN, knn_table=table,
+                   threshold=2.0, confidence=0.95, max_iterations=1000, seed=4)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+
+
+def test_fit_napsac_knn_matches_oracle(ctx):
+    """NAPSAC over nearest-neighbour tables built on each side independently (device build vs oracle brute force)."""
+    from ransac_b200.api import NEIGH_KNN, SAMPLER_NAPSAC
+    pts, _, _ = gen.homography(n=6000, inlier_ratio=0.2, clustered=True, seed=33)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    ctx.build_neighbors_knn(0, 7)
+    r = ctx.fit(2.0, 0.95, 3000, sampler=SAMPLER_NAPSAC, neighbors=NEIGH_KNN, seed=9, round_size=128)[0]
+    ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_KNN, knn_table=O.knn_build(pts, 7),
+                   threshold=2.0, confidence=0.95, max_iterations=3000, seed=9)
+    assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
+
+
 def assert_fit_equal(r, ref, est):
     for key in ("inliers", "iterations", "best_hyp", "best_model_idx"):
         assert r[key] == ref[key], (key, r[key], ref[key])

@@ -233,6 +233,26 @@ def test_napsac_knn_cursor():
         uses[p] = c + m - 1
 
 
+def test_knn_build_vs_kdtree_and_ties():
+    """orc_knn_build (nearest_neighbors.cpp:69-128): the k+1 nearest minus the first. Pinned against an independent exact
+    KD-tree (scipy cKDTree, float64 - nanoflann itself is not available) on tie-free data; tie rule = ascending index."""
+    from scipy.spatial import cKDTree
+    g = np.random.default_rng(4)
+    for dim, n, k in ((4, 3000, 5), (2, 1200, 9), (4, 64, 8)):
+        pts = g.uniform(0, 1000, (n, dim)).astype(np.float32)
+        table = O.knn_build(pts, k)
+        _, ref = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=k + 1)
+        assert np.array_equal(table, ref[:, 1:].astype(np.int32))
+    lattice = np.stack(np.meshgrid(np.arange(6.0), np.arange(6.0), [0.0], [0.0]), -1).reshape(-1, 4).astype(np.float32)
+    t = O.knn_build(lattice, 4)
+    assert t[0].tolist() == [1, 6, 7, 2]                     # d^2 = 1, 1, 2, 4 (tie 2 vs 12 -> lower index)
+    dup = np.concatenate([lattice, lattice[:3]])
+    t = O.knn_build(dup, 2)
+    assert t[36].tolist() == [36, 1]                         # its duplicate (point 0) takes rank 0; the query itself is kept
+    with pytest.raises(ValueError):
+        O.knn_build(lattice[:4], 4)
+
+
 def test_standard_termination():
     """standard_termination_criteria.hpp:52-62 (float32 power by repeated multiply, truncation)."""
     assert O.standard_termination(1200, 4000, 4, 0.95, 10000) == int(np.log(np.float32(0.05)) / np.log(1 - np.float32(0.3) ** 4))
