@@ -7,7 +7,9 @@
 
 #define USAC_REC_STRIDE 32          // floats per prepared-model record (128 B)
 #define USAC_TILE_PAIRS 128         // point pairs per shared-memory tile (256 points)
-#define USAC_STAGES 4               // bulk-copy pipeline depth of the scoring kernel
+#ifndef USAC_WARP_STAGES
+#define USAC_WARP_STAGES 2          // bulk-copy pipeline depth of each warp of the scoring kernel
+#endif
 #define USAC_SCORE_THREADS 128      // models per scoring CTA
 #ifndef USAC_SCORE_MIN_CTAS
 #define USAC_SCORE_MIN_CTAS 5        // resident scoring CTAs per SM (5 -> <= 102 registers per thread; measured best with USAC_PPI 4)

@@ -69,7 +69,7 @@ __device__ __forceinline__ void make_record(int est, const float* model, float t
         const float g8 = 8.f * u;
         const float K1 = g8 * ((bx1 + by1) + (pd.mx2 + pd.my2 + 2.1f * T2) * bz1);
         const float K2 = g8 * ((bx2 + by2) + (pd.mx1 + pd.my1 + 2.1f * T2) * bz2);
-        const float c0 = g8 * (pd.mx1 + pd.my1 + pd.mx2 + pd.my2 + 4.2f * T2) + 16.f * u * T2;
+        const float c0 = g8 * (pd.mx1 + pd.my1 + pd.mx2 + pd.my2 + 4.2f * T2) + 32.f * u * T2;
         rec[REC_BAND] = 1.001f * (K1 + c0 * bz1);
         rec[REC_BAND + 1] = 1.001f * K2;
     } else if (est == USAC_EST_FUNDAMENTAL) {

@@ -2,10 +2,9 @@
 //
 // Replaces Quality::getNumberInliers (quality.hpp:60-101) looping the virtual Estimator::GetError.
 //
-// Mapping: one thread owns one model (register resident, every parameter duplicated into both halves of a 64-bit
-// register pair); a CTA of USAC_SCORE_THREADS models walks a chunk of the point set that is staged through shared memory
-// in tiles of USAC_TILE_PAIRS point pairs by 1-D bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier),
-// USAC_STAGES deep. Points are stored pair-interleaved ([x1a x1b y1a y1b x2a x2b y2a y2b] per pair) so that one broadcast
+// Mapping: one thread owns one model (register resident); a warp of 32 models walks a chunk of the point set that is
+// staged through the warp's own shared-memory ring in tiles of USAC_TILE_PAIRS point pairs by 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier), USAC_WARP_STAGES deep. Points are stored pair-interleaved ([x1a x1b y1a y1b x2a x2b y2a y2b] per pair) so that one broadcast
 // LDS.128 feeds two points straight into the packed FP32x2 pipe (FFMA2/FMUL2/FADD2, sm_100): the residual costs ~28
 // packed instructions per pair for a homography, which makes the kernel FMA-pipe bound rather than issue bound.
 //
@@ -71,29 +70,40 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
         a11 = -r[0]; a12 = -r[1]; a13 = -r[2]; a21 = -r[3]; a22 = -r[4]; a23 = -r[5]; h31 = r[6]; h32 = r[7]; h33 = r[8];
         b11 = -r[9]; b12 = -r[10]; b13 = -r[11]; b21 = -r[12]; b22 = -r[13]; b23 = -r[14]; g31 = r[15]; g32 = r[16]; g33 = r[17];
         negT = -2.f * r[REC_THR]; k1 = r[REC_BAND]; k2 = r[REC_BAND + 1];
+        T2p = 2.f * r[REC_THR] * 1.0000019f;
     }
     // Two phases. The symmetric transfer error is (d1 + d2)/2 with d1, d2 >= 0, so a point whose FORWARD distance alone
     // exceeds 2*thr by more than the forward guard band is an outlier whatever the backward distance is (also when the
-    // backward term is NaN: the reference's sum is then NaN and fails `err < thr` as well). phase1 computes d1 and that
-    // verdict; the kernel runs phase2 (the backward half, 60 % of the arithmetic) only for the pairs of points on which some
-    // lane of the warp still needs it - for the random-sample hypotheses of a RANSAC round that is a small minority.
+    // backward term is NaN: the reference's sum is then NaN and fails `err < thr` as well). phase1 decides that without a
+    // division or a square root, on the distance scaled by nz:
+    //     d1 > 2 thr + k1/|nz|   <=>   (x2 nz - nx)^2 + (y2 nz - ny)^2 > (2 thr |nz| + k1)^2
+    // (12 packed FMA-pipe instructions, no MUFU). The rounding error of the left-hand side is smaller than that of the
+    // quotient form the band k1 was derived for (one rounding of x2*nz - nx instead of product, rcp.approx, product), and
+    // T2p = 2 thr (1 + 2^-19) absorbs the roundings of the comparison itself. The kernel runs phase2 (d1 itself and the
+    // backward half, all 8 MUFU) only for the pairs of points on which some lane of the warp still needs it - for the
+    // random-sample hypotheses of a RANSAC round that is a small minority.
     static constexpr bool TWO_PHASE = true;
-    struct P1 { float2 u, p1; };                                           // u = d1 - 2*thr, p1 = k1/nz (forward band)
+    float T2p;
+    struct P1 { float2 sa, nz; };                                          // sa = (d1 nz)^2
     __device__ __forceinline__ void phase1(const float4 A, const float4 B, P1& s) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 nz = __ffma2_rn(dup(h31), X1, __ffma2_rn(dup(h32), Y1, dup(h33)));
         const float2 nx = __ffma2_rn(dup(a11), X1, __ffma2_rn(dup(a12), Y1, dup(a13)));   // -(h11 x1 + h12 y1 + h13)
         const float2 ny = __ffma2_rn(dup(a21), X1, __ffma2_rn(dup(a22), Y1, dup(a23)));
-        const float2 r1 = make_float2(fast_rcp(nz.x), fast_rcp(nz.y));
-        const float2 dx = __ffma2_rn(nx, r1, X2), dy = __ffma2_rn(ny, r1, Y2);
-        const float2 sa = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
-        const float2 d1 = make_float2(fast_sqrt(sa.x), fast_sqrt(sa.y));
-        s.u = __fadd2_rn(d1, dup(negT));
-        s.p1 = __fmul2_rn(dup(k1), r1);
+        const float2 ax = __ffma2_rn(X2, nz, nx), ay = __ffma2_rn(Y2, nz, ny);           // nz * (x2 - nx/nz)
+        s.sa = __ffma2_rn(ay, ay, __fmul2_rn(ax, ax));
+        s.nz = nz;
     }
-    static __device__ __forceinline__ bool sure_outlier(float u, float p1) { return u > fabsf(p1); }      // false for NaN
+    __device__ __forceinline__ void sure(const P1& s, bool& ox, bool& oy) const {       // false for NaN
+        const float2 az = make_float2(fabsf(s.nz.x), fabsf(s.nz.y));
+        const float2 c = __ffma2_rn(dup(T2p), az, dup(k1));
+        const float2 c2 = __fmul2_rn(c, c);
+        ox = s.sa.x > c2.x; oy = s.sa.y > c2.y;
+    }
     __device__ __forceinline__ void phase2(const float4 A, const float4 B, const P1& s, float2& t, float2& band) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
+        const float2 r1 = make_float2(fabsf(fast_rcp(s.nz.x)), fabsf(fast_rcp(s.nz.y)));
+        const float2 d1 = __fmul2_rn(make_float2(fast_sqrt(s.sa.x), fast_sqrt(s.sa.y)), r1);
         const float2 mz = __ffma2_rn(dup(g31), X2, __ffma2_rn(dup(g32), Y2, dup(g33)));
         const float2 mx = __ffma2_rn(dup(b11), X2, __ffma2_rn(dup(b12), Y2, dup(b13)));
         const float2 my = __ffma2_rn(dup(b21), X2, __ffma2_rn(dup(b22), Y2, dup(b23)));
@@ -101,17 +111,19 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
         const float2 ex = __ffma2_rn(mx, r2, X1), ey = __ffma2_rn(my, r2, Y1);
         const float2 sb = __ffma2_rn(ey, ey, __fmul2_rn(ex, ex));
         const float2 d2 = make_float2(fast_sqrt(sb.x), fast_sqrt(sb.y));
-        t = __fadd2_rn(s.u, d2);                                           // 2*err - 2*thr
+        t = __fadd2_rn(__fadd2_rn(d1, dup(negT)), d2);                     // 2*err - 2*thr
         const float2 p2 = __fmul2_rn(dup(k2), r2);
-        band = make_float2(fabsf(s.p1.x) + fabsf(p2.x), fabsf(s.p1.y) + fabsf(p2.y));
+        band = __ffma2_rn(dup(k1), r1, make_float2(fabsf(p2.x), fabsf(p2.y)));
     }
     __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
         P1 st;
+        bool ox, oy;
         phase1(A, B, st);
+        sure(st, ox, oy);
         phase2(A, B, st, t, s);
         // a lane that phase1 already proves an outlier is decided, whatever the backward half says (it may be NaN)
-        if (sure_outlier(st.u.x, st.p1.x)) { t.x = st.u.x; s.x = 0.f; }
-        if (sure_outlier(st.u.y, st.p1.y)) { t.y = st.u.y; s.y = 0.f; }
+        if (ox) { t.x = 1.f; s.x = 0.f; }
+        if (oy) { t.y = 1.f; s.y = 0.f; }
         w = t;
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
@@ -164,7 +176,9 @@ template <> struct FastModel<USAC_EST_ESSENTIAL> {
         s.u = make_float2(fabsf(pa.x) + negT, fabsf(pa.y) + negT);
         s.p1 = __ffma2_rn(dup(ka), ra, dup(k0));
     }
-    static __device__ __forceinline__ bool sure_outlier(float u, float p1) { return u > fabsf(p1); }      // false for NaN
+    __device__ __forceinline__ void sure(const P1& s, bool& ox, bool& oy) const {       // false for NaN
+        ox = s.u.x > fabsf(s.p1.x); oy = s.u.y > fabsf(s.p1.y);
+    }
     __device__ __forceinline__ void phase2(const float4 A, const float4 B, const P1& s, float2& t, float2& band) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 t1 = __ffma2_rn(dup(e11), X1, __ffma2_rn(dup(e12), Y1, dup(e13)));
@@ -179,10 +193,12 @@ template <> struct FastModel<USAC_EST_ESSENTIAL> {
     }
     __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
         P1 st;
+        bool ox, oy;
         phase1(A, B, st);
+        sure(st, ox, oy);
         phase2(A, B, st, t, s);
-        if (sure_outlier(st.u.x, st.p1.x)) { t.x = st.u.x; s.x = 0.f; }
-        if (sure_outlier(st.u.y, st.p1.y)) { t.y = st.u.y; s.y = 0.f; }
+        if (ox) { t.x = 1.f; s.x = 0.f; }
+        if (oy) { t.y = 1.f; s.y = 0.f; }
         w = t;
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
@@ -217,6 +233,8 @@ struct ScoreArgs {
     int mblocks, slots;          // work items = slots x nchunks x mblocks (model block fastest: neighbours share points)
     int* part_cnt;               // [slot][nchunks][mstride]
     float* part_sum;
+    unsigned* work;              // global work-item counter, never reset: this launch's items are work - work_base
+    unsigned work_base;
 };
 
 // Slow path of one lane: the reference's exact arithmetic for point `idx` of the problem. Returns the lane's `em`
@@ -238,38 +256,46 @@ __device__ __noinline__ float strict_em(const float* __restrict__ rec, const flo
     return (err < thr) ? FastModel<EST>::strict_to_em(err, thr) : 0.f;
 }
 
-// Persistent kernel: a CTA loops over work items (slot, point chunk, model block). The points of an item are streamed
-// through a USAC_STAGES-deep ring of shared-memory tiles filled by 1-D bulk async copies (completion on `full` mbarriers).
-// There is no CTA-wide barrier inside an item: the last warp to finish a tile (counted with a shared-memory atomic)
-// re-arms the stage and issues the copy of the tile USAC_STAGES ahead.
+// Persistent kernel of independent warps: every warp draws work items (slot, point chunk, group of 32 models) from a global
+// counter and streams the item's points through its OWN USAC_WARP_STAGES-deep ring of shared-memory tiles filled by 1-D bulk
+// async copies (completion on the warp's `full` mbarriers). Warps never wait for each other - no CTA barrier, no shared
+// counters: a warp whose models need the slow phases (good models, degenerate models) does not hold back its neighbours,
+// and the dynamic hand-out levels the tail. The four warps of a CTA mostly draw neighbouring items (the model group is the
+// fastest index), so their tile fetches hit the same L2 lines.
 template <int EST>
 __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a) {
     constexpr int PAIR_FLOATS = (EST == USAC_EST_LINE2D) ? 4 : 8;
     constexpr int NWARPS = USAC_SCORE_THREADS / 32;
-    __shared__ __align__(128) float tile[USAC_STAGES][USAC_TILE_PAIRS * PAIR_FLOATS];
-    __shared__ __align__(8) uint64_t full[USAC_STAGES];
-    __shared__ int done[USAC_STAGES];
+    __shared__ __align__(128) float tile_all[NWARPS][USAC_WARP_STAGES][USAC_TILE_PAIRS * PAIR_FLOATS];
+    __shared__ __align__(8) uint64_t full_all[NWARPS][USAC_WARP_STAGES];
 
-    if (threadIdx.x == 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*tile)[USAC_TILE_PAIRS * PAIR_FLOATS] = tile_all[warp];
+    uint64_t* full = full_all[warp];
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < USAC_STAGES; s++) { mbar_init(&full[s], 1); done[s] = 0; }
+        for (int s = 0; s < USAC_WARP_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
-    const int lane = threadIdx.x & 31;
-    const long long total = (long long)a.slots * a.nchunks * a.mblocks;
-    uint32_t g = 0;                                                  // tiles consumed so far by this CTA (uniform)
+    const int mgroups = a.mblocks * NWARPS;
+    const unsigned total = (unsigned)a.slots * (unsigned)a.nchunks * (unsigned)mgroups;
+    uint32_t g = 0;                                                  // tiles consumed so far by this warp (uniform)
 
-    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-        const int mblock = (int)(item % a.mblocks);
-        const long long rest = item / a.mblocks;
-        const int chunk = (int)(rest % a.nchunks), slot = (int)(rest / a.nchunks);
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(a.work, 1u) - a.work_base;   // every warp overdraws exactly once (accounted by the host)
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const int mgroup = (int)(item % (unsigned)mgroups);
+        const unsigned rest = item / (unsigned)mgroups;
+        const int chunk = (int)(rest % (unsigned)a.nchunks), slot = (int)(rest / (unsigned)a.nchunks);
         const int M = a.mvalid ? a.mvalid[slot] : a.M;
-        if (mblock * USAC_SCORE_THREADS >= M) continue;              // uniform per CTA
+        if (mgroup * 32 >= M) continue;                              // uniform per warp
         const ProblemDesc pd = a.prob[a.active ? a.active[slot] : slot];
-        const int m = mblock * USAC_SCORE_THREADS + threadIdx.x;
+        const int m = mgroup * 32 + lane;
         const bool live = m < M;
         const float* rec = a.recs + ((size_t)slot * a.mstride + (live ? m : 0)) * USAC_REC_STRIDE;
         const size_t out = ((size_t)slot * a.nchunks + chunk) * a.mstride + m;
@@ -283,9 +309,9 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
         const int ntiles = (npairs + USAC_TILE_PAIRS - 1) / USAC_TILE_PAIRS;
         const float* src = a.pairs + ((size_t)pd.pair_off + pair_begin) * PAIR_FLOATS;
 
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < USAC_STAGES && k < ntiles; k++) {
-                const int s = (g + k) % USAC_STAGES;
+        if (lane == 0) {
+            for (int k = 0; k < USAC_WARP_STAGES && k < ntiles; k++) {
+                const int s = (g + k) % USAC_WARP_STAGES;
                 const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - k * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
                 mbar_expect_tx(&full[s], bytes);
                 bulk_copy_g2s(tile[s], src + (size_t)k * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
@@ -301,8 +327,8 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
         for (int q = 0; q < USAC_PPI; q++) sum[q] = make_float2(0.f, 0.f);
 
         for (int k = 0; k < ntiles; k++) {
-            const int s = (g + k) % USAC_STAGES;
-            mbar_wait(&full[s], ((g + k) / USAC_STAGES) & 1);
+            const int s = (g + k) % USAC_WARP_STAGES;
+            mbar_wait(&full[s], ((g + k) / USAC_WARP_STAGES) & 1);
             const int np = min(USAC_TILE_PAIRS, npairs - k * USAC_TILE_PAIRS);
             const float4* tp = reinterpret_cast<const float4*>(tile[s]);
             const int idx0 = 2 * (pair_begin + k * USAC_TILE_PAIRS);
@@ -327,10 +353,18 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {                                    // forward halves, independent streams
                             float4 A, B;
+#ifdef USAC_ABLATE_LDS   /* tuning experiment only (tools/): one shared-memory read per trip; results are wrong */
+                            load_pair(j, A, B);          // the same data rotated per q: distinct arithmetic, one LDS pair per trip
+                            if (q == 1) { A = make_float4(A.y, A.z, A.w, A.x); B = make_float4(B.y, B.z, B.w, B.x); }
+                            if (q == 2) { A = make_float4(A.z, A.w, A.x, A.y); B = make_float4(B.z, B.w, B.x, B.y); }
+                            if (q == 3) { A = make_float4(A.w, A.x, A.y, A.z); B = make_float4(B.w, B.x, B.y, B.z); }
+#else
                             load_pair(j + q, A, B);
+#endif
                             fm.phase1(A, B, st[q]);
-                            need[q] = __any_sync(0xffffffffu, !FastModel<EST>::sure_outlier(st[q].u.x, st[q].p1.x) ||
-                                                                  !FastModel<EST>::sure_outlier(st[q].u.y, st[q].p1.y));
+                            bool ox, oy;
+                            fm.sure(st[q], ox, oy);
+                            need[q] = __any_sync(0xffffffffu, !ox || !oy);
                         }
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {
@@ -340,7 +374,8 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                                 load_pair(j + q, A, B);
                                 float2 t, sb;
                                 fm.phase2(A, B, st[q], t, sb);
-                                const bool ox = FastModel<EST>::sure_outlier(st[q].u.x, st[q].p1.x), oy = FastModel<EST>::sure_outlier(st[q].u.y, st[q].p1.y);
+                                bool ox, oy;
+                                fm.sure(st[q], ox, oy);
                                 em[q] = make_float2(ox ? 0.f : fminf(t.x, 0.f), oy ? 0.f : fminf(t.y, 0.f));
                                 unsure = unsure || (!ox && !(fabsf(t.x) > sb.x)) || (!oy && !(fabsf(t.y) > sb.y));
                             }
@@ -379,21 +414,14 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                     sum[0] = __fadd2_rn(sum[0], e1);
                 }
             }
-            // release the stage: the last warp to get here re-arms it and fetches the tile USAC_STAGES ahead
+            // every lane is done with the stage: re-arm it and fetch the tile USAC_WARP_STAGES ahead
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&done[s], 1) == NWARPS - 1) {
-                    done[s] = 0;
-                    if (k + USAC_STAGES < ntiles) {
-                        __threadfence_block();
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        const int nk = k + USAC_STAGES;
-                        const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - nk * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
-                        mbar_expect_tx(&full[s], bytes);
-                        bulk_copy_g2s(tile[s], src + (size_t)nk * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
-                    }
-                }
+            if (lane == 0 && k + USAC_WARP_STAGES < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int nk = k + USAC_WARP_STAGES;
+                const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - nk * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_copy_g2s(tile[s], src + (size_t)nk * USAC_TILE_PAIRS * PAIR_FLOATS, bytes, &full[s]);
             }
         }
         g += (uint32_t)ntiles;
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
             for (int q = 0; q < USAC_PPI; q++) tot += sum[q].x + sum[q].y;
             a.part_sum[out] = FastModel<EST>::finish(tot, (int)cnt, rec[REC_THR]);
         }
-        __syncthreads();                                             // every warp left the item: its stages may be refilled
+        __syncwarp();                                                // all lanes left the item before its stages are refilled
     }
 }
 

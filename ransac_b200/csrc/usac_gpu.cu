@@ -79,6 +79,8 @@ struct usac_gpu_ctx {
     DevBuf<unsigned long long> d_grid_keys;   // grid build scratch: 2n keys
     DevBuf<int> d_grid_ints;                  // grid build scratch: 4n ints + 1
     DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
+    DevBuf<unsigned> d_work;                  // work-item counter of the scoring kernel (monotone; see launch_score)
+    unsigned work_next = 0;
     DevBuf<int> d_knn_cells;                  // kNN build scratch: cell_start of the search grid
     DevBuf<float4> d_knn_pts;                 // kNN build scratch: points in cell order
     // scoring API buffers
@@ -146,6 +148,11 @@ extern "C" int usac_gpu_create(usac_gpu_ctx** out, int device) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    if ((e = c->d_work.ensure(1)) != cudaSuccess || (e = cudaMemset(c->d_work.p, 0, sizeof(unsigned))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return USAC_ERR_CUDA;
+    }
     *out = c;
     return USAC_OK;
 }
@@ -164,7 +171,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -532,8 +539,14 @@ extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* p
 // ------------------------------------------------------------------------------------------------------------------
 static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     a.mblocks = mblocks; a.slots = slots;
-    const long long items = (long long)slots * a.nchunks * mblocks;
-    const unsigned grid = (unsigned)std::min<long long>(items, (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS);
+    constexpr int warps_per_cta = USAC_SCORE_THREADS / 32;
+    const long long items = (long long)slots * a.nchunks * mblocks * warps_per_cta;            // one item = 32 models x one point chunk
+    const unsigned grid = (unsigned)std::min<long long>((items + warps_per_cta - 1) / warps_per_cta,
+                                                        (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS);
+    // the kernel's warps draw items from a counter that is never reset: this launch owns [work_base, work_base + items),
+    // and every warp draws exactly one value beyond that before it exits
+    a.work = c->d_work.p; a.work_base = c->work_next;
+    c->work_next += (unsigned)items + grid * warps_per_cta;
     auto& ev = c->next_score_event();
     cudaEventRecord(ev.first, c->stream);
     switch (c->est) {
