@@ -12,7 +12,11 @@
 #endif
 #define USAC_SCORE_THREADS 128      // models per scoring CTA
 #ifndef USAC_SCORE_MIN_CTAS
-#define USAC_SCORE_MIN_CTAS 5        // resident scoring CTAs per SM (5 -> <= 102 registers per thread; measured best with USAC_PPI 4)
+#define USAC_SCORE_MIN_CTAS 4        // resident scoring CTAs per SM (4 -> 118 registers, no spills; 16 warps/SM sustain the same rate as 20
+                                     // and leave room for the small kernels of other streams: measured best, profiles/README.md)
+#endif
+#ifndef USAC_SCORE_GRID_CTAS
+#define USAC_SCORE_GRID_CTAS USAC_SCORE_MIN_CTAS   // scoring CTAs launched per SM (<= USAC_SCORE_MIN_CTAS; fewer leaves room for other streams' kernels)
 #endif
 #ifndef USAC_PPI
 #define USAC_PPI 4                  // point pairs per trip of the scoring loop (independent instruction streams)

@@ -384,9 +384,9 @@ struct SelKey { unsigned long long key; int j; };
 __device__ __forceinline__ SelKey sel_max(SelKey a, SelKey b) { return (b.key > a.key) ? b : a; }   // ties keep the earlier
 
 __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const uint2* __restrict__ scores_all) {
-    __shared__ unsigned long long s_key[256];
-    __shared__ int s_j[256];
-    __shared__ int s_stop[256];
+    __shared__ unsigned long long s_key[8];
+    __shared__ int s_j[8];
+    __shared__ int s_stop[8];
     __shared__ int s_T;
     __shared__ unsigned s_useful;
     const int slot = blockIdx.x;
@@ -412,11 +412,23 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
         SelKey c = {score_key((int)(v.x & 0x3fffffffu), __uint_as_float(v.y)), j};
         mine = sel_max(mine, c);
     }
-    s_key[threadIdx.x] = mine.key; s_j[threadIdx.x] = mine.j;
+    // exclusive prefix over threads of the "leftmost maximum" (associative): shuffle scan inside each warp, then the
+    // totals of the earlier warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SelKey inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const SelKey left = {__shfl_up_sync(0xffffffffu, inc.key, o), __shfl_up_sync(0xffffffffu, inc.j, o)};
+        if (lane >= o) inc = sel_max(left, inc);
+    }
+    if (lane == 31) { s_key[warp] = inc.key; s_j[warp] = inc.j; }
     __syncthreads();
-    // exclusive prefix over threads (256 entries: serial scan by each thread is cheap and branch-free enough)
     SelKey run = {carry_key, -1};
-    for (int t = 0; t < (int)threadIdx.x; t++) { SelKey c = {s_key[t], s_j[t]}; if (c.j >= 0) run = sel_max(run, c); }
+    for (int w = 0; w < warp; w++) { const SelKey c = {s_key[w], s_j[w]}; run = sel_max(run, c); }
+    {
+        const SelKey excl = {__shfl_up_sync(0xffffffffu, inc.key, 1), __shfl_up_sync(0xffffffffu, inc.j, 1)};
+        if (lane > 0) run = sel_max(run, excl);
+    }
     // walk own samples with the running prefix best; find the first sample at which the loop condition fails
     int stop = K;           // K = no stop in my range
     SelKey at_stop = run;
@@ -426,11 +438,16 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
         const unsigned mi = (run.j < 0) ? carry_max : table[(unsigned)(run.key >> 32)];
         if (iters0 + (unsigned)j + 1u >= mi) { stop = j; at_stop = run; break; }
     }
-    s_stop[threadIdx.x] = stop;
+    {
+        int wmin = stop;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        if (lane == 0) s_stop[warp] = wmin;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int T = K;
-        for (int t = 0; t < (int)blockDim.x; t++) T = min(T, s_stop[t]);
+        for (int t = 0; t < (int)(blockDim.x >> 5); t++) T = min(T, s_stop[t]);
         s_T = T;
         s_useful = 0;
     }

@@ -542,7 +542,7 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     constexpr int warps_per_cta = USAC_SCORE_THREADS / 32;
     const long long items = (long long)slots * a.nchunks * mblocks * warps_per_cta;            // one item = 32 models x one point chunk
     const unsigned grid = (unsigned)std::min<long long>((items + warps_per_cta - 1) / warps_per_cta,
-                                                        (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS);
+                                                        (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS);
     // the kernel's warps draw items from a counter that is never reset: this launch owns [work_base, work_base + items),
     // and every warp draws exactly one value beyond that before it exits
     a.work = c->d_work.p; a.work_base = c->work_next;
@@ -560,26 +560,17 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     c->last_score_launches++;
 }
 
-// Work items of the persistent scoring kernel = slots x mblocks x nchunks, all of about the same cost, handed to
-// SMs x USAC_SCORE_MIN_CTAS resident CTAs round-robin. The point axis is split (a) to fill the machine when the model
-// axis alone cannot and (b) so that the items divide evenly over the CTAs (2368 items on 740 CTAs would cost 4 item
-// times instead of 3.2; 5 chunks each make it 16 exactly).
+// Work items of the persistent scoring kernel = slots x nchunks x (mblocks x 4 groups of 32 models), drawn one at a time by
+// SMs x USAC_SCORE_GRID_CTAS x 4 resident warps. With the dynamic hand-out the kernel ends at most one item time after the
+// ideal, so the point axis is split until every warp gets ~16 items (a chunk stays >= 2 tiles: each item pays one exposed
+// tile-fetch latency and 128 B of model record per lane).
 static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_pairs, int* chunk_pairs, int* nchunks) {
-    const long long ctas = (long long)c->prop.multiProcessorCount * USAC_SCORE_MIN_CTAS;
-    const long long base = (long long)slots * mblocks;
-    const int max_chunks = std::max(1, max_pairs / USAC_TILE_PAIRS);
-    int nc;
-    if (base < ctas) {
-        nc = (int)std::min<long long>((2 * ctas + base - 1) / base, max_chunks);
-    } else {
-        nc = 1;
-        double best = 1e30;
-        for (int t = 1; t <= std::min(8, std::max(1, max_pairs / (4 * USAC_TILE_PAIRS))); t++) {
-            const long long items = base * t;
-            const double waste = (double)((items + ctas - 1) / ctas * ctas) / (double)items;
-            if (waste < best - 1e-3) { best = waste; nc = t; }
-        }
-    }
+    static const int per_warp = [] { const char* e = getenv("USAC_GPU_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    const long long warps = (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS * (USAC_SCORE_THREADS / 32);
+    const long long base = (long long)slots * mblocks * (USAC_SCORE_THREADS / 32);
+    const int max_chunks = std::max(1, max_pairs / (2 * USAC_TILE_PAIRS));
+    int nc = (int)std::min<long long>((per_warp * warps + base - 1) / base, max_chunks);
+    nc = std::max(nc, 1);
     int cp = (max_pairs + nc - 1) / nc;
     cp = ((cp + 1) / 2) * 2;
     nc = (max_pairs + cp - 1) / cp;
