@@ -9,11 +9,10 @@ all run to their own adaptive termination through usac_gpu_fit (sample -> solve 
 
   value : useful evaluations/s with the point sets resident in HBM. "Useful" = the evaluations the sequential loop of
           ransac.cpp:58-139 executes for the same sample stream (speculative tail of the last round is NOT counted).
-          The step's image pairs are split over --pipe contexts/streams (one host thread each): while one part waits for
-          the host sync of its round the kernels of the others run. (`config.value_single_stream`: one context.)
+          One context, one stream. (`config.value_pipelined`: the step split over --pipe contexts/streams, for information.)
   e2e   : the same with HOST buffers: every step copies the step's point sets host->device (pinned memory) through
-          usac_gpu_set_points, fits, and reads the results (model, inliers, score, iterations) back; every part is
-          double-buffered (two contexts) so that the upload of step k+1 overlaps the fit of step k.
+          usac_gpu_set_points, fits, and reads the results (model, inliers, score, iterations) back; the step is split
+          over --pipe parts, each double-buffered (two contexts), so that uploads overlap the fits of other parts/steps.
   roofline : the scoring kernel, FP32 bound (BASELINE.json: "the roofline is FP32 FMA throughput plus HBM point
           streaming"); algorithmic 42 flop per homography evaluation.
   cpu_baseline / --impl reference : the CPU oracle (a restatement - the reference needs OpenCV-contrib/Eigen/nanoflann
@@ -305,24 +304,26 @@ def run_native(args):
         return ev0.elapsed_time(ev1), stats
 
     # ---- device-resident arm ----
-    # (a) one context, one stream: the per-launch CUDA-event times of the scoring kernel (roofline) are taken here, where no
-    #     other stream runs; (b) the same step split over the two contexts of the e2e arm (points already resident): while one
-    #     half waits for its round's host sync the other half's kernels run - this is the reported `value`.
+    # (a) one context, one stream: the reported `value`, and the per-launch CUDA-event times of the scoring kernel (roofline);
+    # (b) for information, the same step split over --pipe contexts/streams (config.value_pipelined). The scoring kernel is
+    #     persistent and fills every SM, so the small kernels of another stream cannot run beside it: splitting the step only
+    #     makes the launches smaller. (Up to kernel v4 the static work split left long tails and (b) was the faster arm.)
     ctx.set_points(capi.EST_HOMOGRAPHY, host, sizes)
     timed(step_resident, args.warmup)
-    ms_single, stats = timed(step_resident, args.steps)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, stats = timed(step_resident, args.steps)
+    clk = clocks.stop()
+    ms_single = ms
     for i, (lo_, hi_) in enumerate(halves):
         pipe_ctx[i].set_points(capi.EST_HOMOGRAPHY, host[lo_ * N_POINTS:hi_ * N_POINTS], sizes[lo_:hi_])
     timed_threads(step_resident_pipelined, args.warmup)
-    clocks = ClockSampler(local)
-    clocks.start()
-    ms, stats_p = timed_threads(step_resident_pipelined, args.steps)
-    clk = clocks.stop()
-    useful = sum(s[0] for s in stats_p)
-    executed_p = sum(s[1] for s in stats_p)            # the reported arm (pipelined)
-    launches = sum(s[2] for s in stats_p)
-    iters = sum(s[5] for s in stats_p)
-    executed = sum(s[1] for s in stats)                # the single-stream arm: undisturbed per-launch event times for the roofline
+    ms_pipe, stats_p = timed_threads(step_resident_pipelined, args.steps)
+    useful = sum(s[0] for s in stats)
+    executed_p = sum(s[1] for s in stats)
+    launches = sum(s[2] for s in stats)
+    iters = sum(s[5] for s in stats)
+    executed = executed_p
     score_launches = sum(s[3] for s in stats)
     score_ms = sum(s[4] for s in stats)
     # ---- end-to-end arm (host buffers) ----
@@ -380,7 +381,7 @@ def run_native(args):
                 "config": {"workload": workload_name(B), "problems_per_gpu": B, "round_size": args.round_size,
                            "l2": f"inputs larger than L2: {B * N_POINTS * 32 / 1e6:.0f} MB of points per GPU (AoS + pair layout) vs 126 MB",
                            "ms_per_fit": ms_all / args.steps / B, "avg_iterations_per_fit": iters / (args.steps * B),
-                           "value_single_stream": sum(s[0] for s in stats) / (ms_single * 1e-3), "streams": n_pipe,
+                           "value_pipelined": sum(s[0] for s in stats_p) / (ms_pipe * 1e-3), "pipelined_streams": n_pipe,
                            "evals_executed_per_s": executed_all / (ms_all * 1e-3), "useful_fraction": useful / max(executed_p, 1)},
                 "clocks": clk, "gpu_launches": int(launches_all),
                 "e2e": {"value": useful_e2e_all / (ms_e2e_all * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": B * N_POINTS * 16,
@@ -509,7 +510,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--problems", type=int, default=2368, help="image pairs per GPU and step (2368 = 16 x 148 SMs)")
     ap.add_argument("--ref-problems", type=int, default=256, help="image pairs per step of the CPU reference arm")
-    ap.add_argument("--round-size", type=int, default=128, help="samples per round and problem")
+    ap.add_argument("--round-size", type=int, default=256, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
     ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")

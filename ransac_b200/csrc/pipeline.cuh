@@ -37,6 +37,8 @@ struct RoundArgs {
     const int* pool;             // shuffled point pools (ProblemDesc::pool_off)
     struct SprtModelResult* sprt_res;   // [slot][K*S]
     int* done_out;               // [slot] FitState::done after the round (the only thing the host reads per round)
+    int limit_remaining;         // 1: samples the sequential loop can no longer reach (index >= max_iters - iters at the start of
+                                 // the round; the bound never grows) are not solved or scored
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -232,6 +234,10 @@ __global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
     int* nm = a.nmodels + (size_t)slot * a.K + j;
     if (a.nranks > 1 && (j % a.nranks) != a.rank) { *nm = 0; return; }     // another rank's hypothesis
     const int pid = a.active[slot];
+    if (a.limit_remaining) {
+        const FitState& st = a.state[pid];
+        if (st.max_iters <= st.iters || (unsigned)j >= st.max_iters - st.iters) { *nm = 0; return; }
+    }
     const ProblemDesc pd = a.prob[pid];
     const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
     int s[8];
@@ -255,6 +261,10 @@ __global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) solve_kernel_e5_warp(co
     int* nm = a.nmodels + (size_t)slot * a.K + j;
     if (a.nranks > 1 && (j % a.nranks) != a.rank) { if (lane == 0) *nm = 0; return; }
     const int pid = a.active[slot];
+    if (a.limit_remaining) {
+        const FitState& st = a.state[pid];
+        if (st.max_iters <= st.iters || (unsigned)j >= st.max_iters - st.iters) { if (lane == 0) *nm = 0; return; }
+    }
     const ProblemDesc pd = a.prob[pid];
     const float* pts = a.aos + (size_t)pd.aos_off * 4;
     int s[8];

@@ -1414,7 +1414,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     // Without SPRT and PROSAC the result does not depend on the round size (prefix semantics of select_kernel), so the
     // round grows as problems finish: the tail of a batch then needs a few large rounds instead of many tiny ones.
     const char* growth_env = getenv("USAC_GPU_ROUND_GROWTH");      // tuning knob: 0 disables, N caps the growth factor
-    const int growth_cap = growth_env ? atoi(growth_env) : 2;     // measured on C2 x 2368: 2 is the sweet spot
+    const int growth_cap = growth_env ? atoi(growth_env) : 8;     // measured on C2 x 2368 (profiles/README.md): 8 is the sweet spot
     const bool k_free = growth_cap > 1 && !cfg->sprt && cfg->sampler.sampler != USAC_SAMPLER_PROSAC && cfg->sampler.rng != USAC_RNG_TABLE;
     const int K0 = K;
     while (!active.empty()) {
@@ -1441,6 +1441,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
         a.table_rows = cfg->sample_table_rows; a.rank = rank; a.nranks = nranks; a.nchunks = nchunks;
         a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
+        a.limit_remaining = 1;
 
         launch_sampler(c, a, slots);
         switch (c->est) {

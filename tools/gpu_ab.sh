@@ -8,6 +8,6 @@ for v in $VARIANTS; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_${i}_$v.json"))
-print("$v", "value %.1f G/s single %.1f e2e %.1f G/s frac %.3f launch_ms %.3f share %.2f" % (d["value"]/1e9, d["config"]["value_single_stream"]/1e9, d["e2e"]["value"]/1e9, d["roofline"]["frac"], d["roofline"]["avg_launch_ms"], d["roofline"]["score_share_of_step"]))
+print("$v", "value %.1f G/s pipelined %.1f e2e %.1f G/s frac %.3f launch_ms %.3f share %.2f" % (d["value"]/1e9, d["config"]["value_pipelined"]/1e9, d["e2e"]["value"]/1e9, d["roofline"]["frac"], d["roofline"]["avg_launch_ms"], d["roofline"]["score_share_of_step"]))
 PY
 done
