@@ -385,6 +385,45 @@ __global__ void reduce_kernel(const RoundArgs a) {
     a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
 }
 
+// The same for many point chunks (one large problem: hundreds of partials per model): a CTA of 8 warps owns 32 samples
+// (lane <-> sample, coalesced), warp w sums the chunks w, w+8, ... and the eight partial sums are added in warp order
+// (fixed order -> deterministic).
+__global__ void __launch_bounds__(256) reduce_chunks_kernel(const RoundArgs a) {
+    __shared__ int s_c[8][3][32];
+    __shared__ float s_s[8][3][32];
+    const int slot = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    const bool mine = j < a.K && !(a.nranks > 1 && (j % a.nranks) != a.rank);
+    const int k = mine ? a.nmodels[(size_t)slot * a.K + j] : 0;
+    const int off = mine ? a.offsets[(size_t)slot * a.K + j] : 0;
+    for (int i = 0; i < 3; i++) {
+        int c = 0;
+        float s = 0.f;
+        if (i < k)
+            for (int ch = warp; ch < a.nchunks; ch += 8) {
+                const size_t o = ((size_t)slot * a.nchunks + ch) * a.mstride + off + i;
+                c += a.part_cnt[o];
+                s += a.part_sum[o];
+            }
+        s_c[warp][i][lane] = c;
+        s_s[warp][i][lane] = s;
+    }
+    __syncthreads();
+    if (warp != 0 || !mine) return;
+    int bc = -1, bi = 0;
+    float bs = 0.f;
+    for (int i = 0; i < k; i++) {
+        int c = 0;
+        float s = 0.f;
+        for (int w = 0; w < 8; w++) { c += s_c[w][i][lane]; s += s_s[w][i][lane]; }
+        if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
+    }
+    if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }
+    const int per_rank = (a.K + a.nranks - 1) / a.nranks;
+    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + j / a.nranks) : ((size_t)slot * a.K + j);
+    a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // select: best-update and adaptive termination with the reference's sequential semantics (ransac.cpp:58-139):
 // the prefix best over the samples of the round, the first sample t at which iters reaches max_iters, the result

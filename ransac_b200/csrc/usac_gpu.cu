@@ -594,13 +594,23 @@ static void collect_timing(usac_gpu_ctx* c) {
 // ------------------------------------------------------------------------------------------------------------------
 // Quality API
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void final_reduce_kernel(const int* __restrict__ part_cnt, const float* __restrict__ part_sum, int M, int mstride, int nchunks,
-                                    int* __restrict__ cnt, float* __restrict__ sum) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= M) return;
+// 256 threads = 8 warps x 32 models: warp w sums the chunks w, w+8, ...; the eight partials are added in warp order
+__global__ void __launch_bounds__(256) final_reduce_kernel(const int* __restrict__ part_cnt, const float* __restrict__ part_sum, int M, int mstride,
+                                                           int nchunks, int* __restrict__ cnt, float* __restrict__ sum) {
+    __shared__ int s_c[8][32];
+    __shared__ float s_s[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
     int cc = 0;
     float s = 0.f;
-    for (int ch = 0; ch < nchunks; ch++) { cc += part_cnt[(size_t)ch * mstride + q]; s += part_sum[(size_t)ch * mstride + q]; }
+    if (q < M)
+        for (int ch = warp; ch < nchunks; ch += 8) { cc += part_cnt[(size_t)ch * mstride + q]; s += part_sum[(size_t)ch * mstride + q]; }
+    s_c[warp][lane] = cc;
+    s_s[warp][lane] = s;
+    __syncthreads();
+    if (warp != 0 || q >= M) return;
+    cc = 0; s = 0.f;
+    for (int w = 0; w < 8; w++) { cc += s_c[w][lane]; s += s_s[w][lane]; }
     cnt[q] = cc;
     sum[q] = s;
 }
@@ -631,7 +641,7 @@ extern "C" int usac_gpu_score(usac_gpu_ctx* c, int problem, const float* models,
     a.pairs = c->d_pairs.p; a.aos = c->d_aos.p; a.prob = c->d_prob.p; a.active = c->d_active.p; a.recs = c->d_q_recs.p; a.mvalid = nullptr;
     a.M = M; a.mstride = M; a.chunk_pairs = chunk_pairs; a.nchunks = nchunks; a.part_cnt = c->d_part_cnt.p; a.part_sum = c->d_part_sum.p;
     launch_score(c, a, 1, mblocks);
-    final_reduce_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(c->d_part_cnt.p, c->d_part_sum.p, M, M, nchunks, c->d_q_cnt.p, c->d_q_sum.p);
+    final_reduce_kernel<<<(M + 31) / 32, 256, 0, c->stream>>>(c->d_part_cnt.p, c->d_part_sum.p, M, M, nchunks, c->d_q_cnt.p, c->d_q_sum.p);
     c->last_launches++;
     if (inliers_out) CUDA_TRY(c, cudaMemcpyAsync(inliers_out, c->d_q_cnt.p, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream));
     if (sumerr_out) CUDA_TRY(c, cudaMemcpyAsync(sumerr_out, c->d_q_sum.p, sizeof(float) * M, cudaMemcpyDeviceToHost, c->stream));
@@ -1459,7 +1469,8 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
             sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
             launch_score(c, sa, slots, mblocks);
             dim3 gr((K + 127) / 128, slots);
-            reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
+            if (nchunks > 8) reduce_chunks_kernel<<<dim3((K + 31) / 32, slots), 256, 0, c->stream>>>(a);
+            else reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
             c->last_launches++;
             const uint2* scores = c->d_scores.p;
             if (nranks > 1) {
