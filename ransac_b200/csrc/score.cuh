@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                     bool unsure = false;
                     if constexpr (FastModel<EST>::TWO_PHASE) {
                         typename FastModel<EST>::P1 st[USAC_PPI];
-                        bool need[USAC_PPI];
+                        bool lane_need[USAC_PPI];
+                        bool lane_any = false;
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {                                    // forward halves, independent streams
                             float4 A, B;
@@ -364,12 +365,16 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                             fm.phase1(A, B, st[q]);
                             bool ox, oy;
                             fm.sure(st[q], ox, oy);
-                            need[q] = __any_sync(0xffffffffu, !ox || !oy);
+                            lane_need[q] = !ox || !oy;
+                            lane_any = lane_any || lane_need[q];
                         }
+                        // one vote for the whole trip: in most trips every point is a proven outlier for every model of the
+                        // warp - nothing to count, nothing to add
+                        if (!__any_sync(0xffffffffu, lane_any)) continue;
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {
                             em[q] = make_float2(0.f, 0.f);
-                            if (need[q]) {                                                      // warp-uniform
+                            if (__any_sync(0xffffffffu, lane_need[q])) {                        // warp-uniform
                                 float4 A, B;
                                 load_pair(j + q, A, B);
                                 float2 t, sb;
