@@ -349,7 +349,6 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                     bool unsure = false;
                     if constexpr (FastModel<EST>::TWO_PHASE) {
                         typename FastModel<EST>::P1 st[USAC_PPI];
-                        bool lane_need[USAC_PPI];
                         bool lane_any = false;
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {                                    // forward halves, independent streams
@@ -365,8 +364,7 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                             fm.phase1(A, B, st[q]);
                             bool ox, oy;
                             fm.sure(st[q], ox, oy);
-                            lane_need[q] = !ox || !oy;
-                            lane_any = lane_any || lane_need[q];
+                            lane_any = lane_any || !ox || !oy;
                         }
                         // one vote for the whole trip: in most trips every point is a proven outlier for every model of the
                         // warp - nothing to count, nothing to add
@@ -374,13 +372,13 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {
                             em[q] = make_float2(0.f, 0.f);
-                            if (__any_sync(0xffffffffu, lane_need[q])) {                        // warp-uniform
+                            bool ox, oy;
+                            fm.sure(st[q], ox, oy);
+                            if (__any_sync(0xffffffffu, !ox || !oy)) {                          // warp-uniform
                                 float4 A, B;
                                 load_pair(j + q, A, B);
                                 float2 t, sb;
                                 fm.phase2(A, B, st[q], t, sb);
-                                bool ox, oy;
-                                fm.sure(st[q], ox, oy);
                                 em[q] = make_float2(ox ? 0.f : fminf(t.x, 0.f), oy ? 0.f : fminf(t.y, 0.f));
                                 unsure = unsure || (!ox && !(fabsf(t.x) > sb.x)) || (!oy && !(fabsf(t.y) > sb.y));
                             }
