@@ -119,6 +119,46 @@ def test_score_matches_oracle(ctx, cfg):
     check_scores(ctx, est, pts, models[:40], thr * 10)               # LO thresholds (10x), quality.hpp:62-64
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_score_counts_exact_stress(ctx, seed):
+    """Inlier counts of thousands of hypotheses - random-sample models (mostly bad, many near-degenerate), all-inlier models
+    and perturbations of the ground truth that put many points next to the threshold - against the oracle: every count equal.
+    Exercises the forward-only outlier proof of the two-phase kernel (score.cuh) and its guard band far beyond the handful of
+    models of the other tests."""
+    g = np.random.default_rng(seed)
+    pts, H, mask = gen.homography(n=4000, seed=200 + seed)
+    inl = np.where(mask)[0]
+    models = []
+    while len(models) < 1500:                                        # random minimal samples
+        models.extend(O.solve_minimal(O.EST_HOMOGRAPHY, pts, g.choice(4000, 4, replace=False).astype(np.int32)))
+    while len(models) < 1800:                                        # all-inlier samples
+        models.extend(O.solve_minimal(O.EST_HOMOGRAPHY, pts, g.choice(inl, 4, replace=False).astype(np.int32)))
+    for _ in range(248):                                             # ground truth, perturbed at every scale
+        P = H.astype(np.float64) * (1 + g.normal(0, 10 ** g.uniform(-7, -2), (3, 3)))
+        P[:2, 2] += g.normal(0, 10 ** g.uniform(-3, 0.5), 2)
+        models.append((P / P[2, 2]).astype(np.float32).ravel())
+    models = np.stack(models[:2048]).astype(np.float32)
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    for thr in (2.0, 0.5, 20.0):
+        cnt, _ = ctx.score(models, thr)
+        ref = np.array([O.score(O.EST_HOMOGRAPHY, pts, m, thr)[0] for m in models])
+        bad = np.where(cnt != ref)[0]
+        assert len(bad) == 0, (thr, bad[:10], cnt[bad[:10]], ref[bad[:10]])
+    # essential metric (two-phase as well): calibrated coordinates, perturbed ground truth and random matrices
+    ptsE, E, _ = gen.essential(n=4000, seed=300 + seed)
+    mods = [E.ravel()]
+    for _ in range(400):
+        mods.append((E + g.normal(0, 10 ** g.uniform(-5, 0), (3, 3)).astype(np.float32)).ravel())
+    for _ in range(111):
+        mods.append(g.normal(0, 1, 9).astype(np.float32))
+    mods = np.stack(mods).astype(np.float32)
+    ctx.set_points(O.EST_ESSENTIAL, ptsE)
+    for thr in (2.5e-3, 2.5e-2):
+        cnt, _ = ctx.score(mods, thr)
+        ref = np.array([O.score(O.EST_ESSENTIAL, ptsE, m, thr)[0] for m in mods])
+        assert np.array_equal(cnt, ref), (thr, np.where(cnt != ref)[0][:10])
+
+
 def test_score_essential_metric(ctx):
     pts, E, mask = gen.essential(n=5000)
     g = np.random.default_rng(4)
