@@ -6,6 +6,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,8 @@ struct usac_gpu_ctx {
     // data
     int est = 0, P = 0;
     std::vector<ProblemDesc> h_prob;
+    std::vector<ProblemDesc> h_prob_pushed;   // what d_prob holds (push_desc skips the upload when nothing changed)
+    bool maxima_fetched = false;              // coordinate maxima (written by layout_kernel) copied into h_prob
     long long total_points = 0, total_pairs = 0;
     DevBuf<float> d_aos, d_pairs;
     DevBuf<ProblemDesc> d_prob;
@@ -262,6 +265,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     const int dim = usac_point_dim(estimator);
     c->est = estimator; c->P = P;
     c->h_prob.assign(P, ProblemDesc());
+    c->h_prob_pushed.clear(); c->maxima_fetched = false;
     std::vector<long long> pair_offs(P);
     long long aos = 0, pairs = 0;
     for (int p = 0; p < P; p++) {
@@ -310,15 +314,22 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
 
 // push host-side descriptor fields that the host owns (offsets) without clobbering the device-computed maxima
 static int push_desc(usac_gpu_ctx* c) {
-    std::vector<ProblemDesc> cur(c->P);
-    CUDA_TRY(c, cudaMemcpyAsync(cur.data(), c->d_prob.p, sizeof(ProblemDesc) * c->P, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int p = 0; p < c->P; p++) {
-        ProblemDesc& h = c->h_prob[p];
-        h.mx1 = cur[p].mx1; h.my1 = cur[p].my1; h.mx2 = cur[p].mx2; h.my2 = cur[p].my2;
+    if (!c->maxima_fetched) {                                   // once per point set: the maxima layout_kernel computed
+        std::vector<ProblemDesc> cur(c->P);
+        CUDA_TRY(c, cudaMemcpyAsync(cur.data(), c->d_prob.p, sizeof(ProblemDesc) * c->P, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int p = 0; p < c->P; p++) {
+            ProblemDesc& h = c->h_prob[p];
+            h.mx1 = cur[p].mx1; h.my1 = cur[p].my1; h.mx2 = cur[p].mx2; h.my2 = cur[p].my2;
+        }
+        c->maxima_fetched = true;
     }
+    if (c->h_prob_pushed.size() == c->h_prob.size() &&
+        memcmp(c->h_prob_pushed.data(), c->h_prob.data(), sizeof(ProblemDesc) * c->h_prob.size()) == 0)
+        return USAC_OK;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), sizeof(ProblemDesc) * c->P, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->h_prob_pushed = c->h_prob;
     return USAC_OK;
 }
 
@@ -1353,6 +1364,14 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     const bool host_replay = cfg->sprt || cfg->lo || cfg->sampler.sampler == USAC_SAMPLER_PROSAC;
     if (host_replay && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT / PROSAC termination with hypothesis sharding is not supported");
     cudaSetDevice(c->device);
+    // USAC_GPU_TRACE=1: host-side wall-clock split of one fit on stderr (setup / enqueue / waiting for the round's flags / read-back)
+    static const bool trace = getenv("USAC_GPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto t_begin = now();
+    double t_enqueue = 0, t_wait = 0;
+    int n_rounds = 0;
     const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est);
     int max_n = 0;
     for (int p = 0; p < P; p++) max_n = std::max(max_n, c->h_prob[p].n);
@@ -1427,7 +1446,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     const int growth_cap = growth_env ? atoi(growth_env) : 8;     // measured on C2 x 2368 (profiles/README.md): 8 is the sweet spot
     const bool k_free = growth_cap > 1 && !cfg->sprt && cfg->sampler.sampler != USAC_SAMPLER_PROSAC && cfg->sampler.rng != USAC_RNG_TABLE;
     const int K0 = K;
+    const auto t_setup = now();
     while (!active.empty()) {
+        const auto t_r0 = now();
         const int slots = (int)active.size();
         if (k_free && slots < P) {
             long long kr = std::min<long long>({2048LL, (long long)P * K0 / slots, (long long)K0 * growth_cap});
@@ -1490,8 +1511,10 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         }
         // the one host sync of the round: one `done` flag per active problem
         CUDA_TRY(c, cudaMemcpyAsync(c->h_done, c->d_done.p, sizeof(int) * slots, cudaMemcpyDeviceToHost, c->stream));
+        const auto t_r1 = now();
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaGetLastError());
+        t_enqueue += us(t_r0, t_r1); t_wait += us(t_r1, now()); n_rounds++;
         std::vector<int> next;
         for (int q = 0; q < slots; q++) if (!c->h_done[q]) next.push_back(active[q]);
         active.swap(next);
@@ -1510,6 +1533,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         r.best_hyp = s.best_hyp; r.best_model_idx = s.best_midx; r.rounds = s.rounds; r.evals = s.evals;
         r.useful_evals = s.useful_evals;
     }
+    if (trace)
+        fprintf(stderr, "usac_gpu_fit trace: %d problems, %d rounds: setup %.0f us, enqueue %.0f us, wait %.0f us, total %.0f us (GPU events: %.0f us, scoring %.0f us)\n",
+                P, n_rounds, us(t_begin, t_setup), t_enqueue, t_wait, us(t_begin, now()), c->last_total_ms * 1e3, c->last_score_ms * 1e3);
     return USAC_OK;
 }
 
