@@ -55,7 +55,7 @@ struct usac_gpu_ctx {
     void set_error(const char* what, const char* why) { err = std::string(what) + ": " + why; }
 
     // data
-    int est = 0, P = 0;
+    int est = 0, est_prev = 0, P = 0;
     std::vector<ProblemDesc> h_prob;
     std::vector<ProblemDesc> h_prob_pushed;   // what d_prob holds (push_desc skips the upload when nothing changed)
     bool maxima_fetched = false;              // coordinate maxima (written by layout_kernel) copied into h_prob
@@ -66,6 +66,9 @@ struct usac_gpu_ctx {
     DevBuf<FitState> d_state;
     FitState* h_state = nullptr; size_t h_state_cap = 0;     // pinned
     DevBuf<int> d_active, d_done;
+    DevBuf<int> d_active2;                    // second active list: the lists of consecutive rounds are compacted on the device
+    DevBuf<FitState> d_state_init;            // initial fit states of the current point sets (uploaded once, copied per fit)
+    std::vector<long long> state_init_sig;
     int* h_active = nullptr; size_t h_active_cap = 0;        // pinned
     int* h_done = nullptr;                                   // pinned, same capacity as h_active
     // side structures
@@ -169,7 +172,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
         destroy_fn f = (destroy_fn)dlsym(c->nccl_lib, "ncclCommDestroy");
         if (f) f(c->nccl_comm);
     }
-    c->d_aos.release(); c->d_pairs.release(); c->d_prob.release(); c->d_pair_offs.release(); c->d_state.release(); c->d_active.release();
+    c->d_aos.release(); c->d_pairs.release(); c->d_prob.release(); c->d_pair_offs.release(); c->d_state.release(); c->d_active.release(); c->d_active2.release(); c->d_state_init.release();
     c->d_knn.release(); c->d_cell_of_point.release(); c->d_members.release(); c->d_rank.release(); c->d_cell_start.release();
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
@@ -263,7 +266,9 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     if (estimator < USAC_EST_LINE2D || estimator > USAC_EST_ESSENTIAL) return fail(c, USAC_ERR_ARG, "set_points: unknown estimator");
     cudaSetDevice(c->device);
     const int dim = usac_point_dim(estimator);
+    c->est_prev = c->est;
     c->est = estimator; c->P = P;
+    const std::vector<ProblemDesc> old = std::move(c->h_prob);  // equally sized point sets keep their termination-table offsets
     c->h_prob.assign(P, ProblemDesc());
     c->h_prob_pushed.clear(); c->maxima_fetched = false;
     std::vector<long long> pair_offs(P);
@@ -275,6 +280,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
         memset(&d, 0, sizeof(d));
         d.n = n; d.n_pairs = (n + 1) / 2; d.aos_off = aos; d.pair_off = pairs;
         d.growth_off = d.term_off = d.pool_off = d.knn_off = d.grid_off = d.cell_start_off = d.cursor_off = -1;
+        if (old.size() == (size_t)P && old[p].n == n && estimator == c->est_prev) d.term_off = old[p].term_off;
         pair_offs[p] = pairs;
         aos += n; pairs += d.n_pairs;
     }
@@ -288,6 +294,11 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     CUDA_TRY(c, c->d_pair_offs.ensure(P));
     CUDA_TRY(c, c->d_state.ensure(P));
     CUDA_TRY(c, c->d_active.ensure(P));
+    CUDA_TRY(c, c->d_active2.ensure(P));
+    if (c->d_state_init.cap < (size_t)P) {                  // the template survives a new upload of equally sized point sets
+        CUDA_TRY(c, c->d_state_init.ensure(P));
+        c->state_init_sig.clear();
+    }
     CUDA_TRY(c, c->d_done.ensure(P));
     if (c->h_state_cap < (size_t)P) {
         if (c->h_state) cudaFreeHost(c->h_state);
@@ -301,7 +312,13 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
         CUDA_TRY(c, cudaMallocHost(&c->h_done, sizeof(int) * P));
         c->h_active_cap = P;
     }
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_aos.p, points, (size_t)aos * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    {   // the point upload goes in 4 MB pieces: the copy engine serves streams in submission order, and the few-KB uploads of
+        // another context's running fit (its per-round active list) must not wait behind one 100+ MB transfer
+        const size_t bytes = (size_t)aos * dim * sizeof(float), piece = (size_t)4 << 20;
+        for (size_t off = 0; off < bytes; off += piece)
+            CUDA_TRY(c, cudaMemcpyAsync(reinterpret_cast<char*>(c->d_aos.p) + off, reinterpret_cast<const char*>(points) + off,
+                                        std::min(piece, bytes - off), cudaMemcpyHostToDevice, c->stream));
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), sizeof(ProblemDesc) * P, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_pair_offs.p, pair_offs.data(), sizeof(long long) * P, cudaMemcpyHostToDevice, c->stream));
     const int threads = 256;
@@ -309,6 +326,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
                                                                                           c->d_pair_offs.p, pairs);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // pair_offs / h_prob staging are stack/heap temporaries
+    c->h_prob_pushed = c->h_prob;                    // d_prob = this + the coordinate maxima layout_kernel has just written
     return USAC_OK;
 }
 
@@ -321,6 +339,10 @@ static int push_desc(usac_gpu_ctx* c) {
         for (int p = 0; p < c->P; p++) {
             ProblemDesc& h = c->h_prob[p];
             h.mx1 = cur[p].mx1; h.my1 = cur[p].my1; h.mx2 = cur[p].mx2; h.my2 = cur[p].my2;
+            if (c->h_prob_pushed.size() == (size_t)c->P) {
+                ProblemDesc& q = c->h_prob_pushed[p];
+                q.mx1 = h.mx1; q.my1 = h.my1; q.mx2 = h.mx2; q.my2 = h.my2;
+            }
         }
         c->maxima_fetched = true;
     }
@@ -1351,6 +1373,37 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
     return USAC_OK;
 }
 
+// The fit loop keeps the host->device copy engine out of its way (an upload of the next point sets by another context would
+// otherwise delay every small copy of a running fit): initial states come from a device-resident template, the list of active
+// problems is compacted on the device from the round's `done` flags (same order as the host's bookkeeping).
+__global__ void copy_states_kernel(const FitState* __restrict__ src, FitState* __restrict__ dst, int P) {
+    const size_t words = (size_t)P * (sizeof(FitState) / 4);
+    const unsigned* s = reinterpret_cast<const unsigned*>(src);
+    unsigned* d = reinterpret_cast<unsigned*>(dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+__global__ void iota_kernel(int* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+__global__ void __launch_bounds__(1024) compact_active_kernel(const int* __restrict__ active, const int* __restrict__ done, int slots,
+                                                              int* __restrict__ next) {
+    __shared__ int sm[33];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int q0 = 0; q0 < slots; q0 += blockDim.x) {
+        const int q = q0 + threadIdx.x;
+        const int keep = (q < slots && !done[q]) ? 1 : 0;
+        int total;
+        const int off = block_exclusive_scan(keep, &total, sm);
+        if (keep) next[base + off] = active[q];
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+}
+
 extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results) {
     if (!c || !cfg || !results) return fail(c, USAC_ERR_ARG, "fit: bad arguments");
     if (c->P <= 0) return fail(c, USAC_ERR_STATE, "fit: no points uploaded");
@@ -1432,11 +1485,24 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         collect_timing(c);
         return rc;
     }
-    for (int p = 0; p < P; p++) init_state(c->h_state[p], c->h_prob[p], c->est, cfg->max_iterations, 0);
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof(FitState) * P, cudaMemcpyHostToDevice, c->stream));
+    {
+        std::vector<long long> sig = {(long long)c->est, (long long)cfg->max_iterations, (long long)P};
+        for (int p = 0; p < P; p++) sig.push_back(c->h_prob[p].n);
+        if (sig != c->state_init_sig) {
+            for (int p = 0; p < P; p++) init_state(c->h_state[p], c->h_prob[p], c->est, cfg->max_iterations, 0);
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_state_init.p, c->h_state, sizeof(FitState) * P, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            c->state_init_sig = sig;
+        }
+        copy_states_kernel<<<std::min(4 * c->prop.multiProcessorCount, (P * (int)(sizeof(FitState) / 4) + 255) / 256), 256, 0, c->stream>>>(
+            c->d_state_init.p, c->d_state.p, P);
+    }
 
     std::vector<int> active(P);
     for (int p = 0; p < P; p++) active[p] = p;
+    int* act_cur = c->d_active.p;
+    int* act_next = c->d_active2.p;
+    iota_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(act_cur, P);
     c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
     cudaEventRecord(c->ev0, c->stream);
 
@@ -1464,11 +1530,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         plan_chunks(c, slots, std::max(1, mblocks / nranks), max_pairs, &chunk_pairs, &nchunks);
         rc = ensure_round_buffers(c, slots, K, nchunks, nranks);
         if (rc) return rc;
-        memcpy(c->h_active, active.data(), sizeof(int) * slots);
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int) * slots, cudaMemcpyHostToDevice, c->stream));
-
         RoundArgs a;
         fill_round_args(c, a, cfg->sampler, K);
+        a.active = act_cur;
         a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
         a.table_rows = cfg->sample_table_rows; a.rank = rank; a.nranks = nranks; a.nchunks = nchunks;
         a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
@@ -1485,7 +1549,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         c->last_launches++;
         {
             ScoreArgs sa;
-            sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
+            sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = act_cur; sa.recs = c->d_recs.p;
             sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
             sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
             launch_score(c, sa, slots, mblocks);
@@ -1509,6 +1573,8 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
             case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
             default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
         }
+        compact_active_kernel<<<1, 1024, 0, c->stream>>>(act_cur, c->d_done.p, slots, act_next);
+        std::swap(act_cur, act_next);
         // the one host sync of the round: one `done` flag per active problem
         CUDA_TRY(c, cudaMemcpyAsync(c->h_done, c->d_done.p, sizeof(int) * slots, cudaMemcpyDeviceToHost, c->stream));
         const auto t_r1 = now();
