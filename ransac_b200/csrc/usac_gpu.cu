@@ -1503,7 +1503,8 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     int* act_cur = c->d_active.p;
     int* act_next = c->d_active2.p;
     iota_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(act_cur, P);
-    c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
+    int setup_launches = 2;                                      // copy_states_kernel + iota_kernel (counted below: the counters are reset next)
+    c->score_events_used = 0; c->last_launches = setup_launches; c->last_score_launches = 0;
     cudaEventRecord(c->ev0, c->stream);
 
     // Without SPRT and PROSAC the result does not depend on the round size (prefix semantics of select_kernel), so the
@@ -1574,6 +1575,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
             default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
         }
         compact_active_kernel<<<1, 1024, 0, c->stream>>>(act_cur, c->d_done.p, slots, act_next);
+        c->last_launches++;
         std::swap(act_cur, act_next);
         // the one host sync of the round: one `done` flag per active problem
         CUDA_TRY(c, cudaMemcpyAsync(c->h_done, c->d_done.p, sizeof(int) * slots, cudaMemcpyDeviceToHost, c->stream));
