@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
         const float* src = a.pairs + ((size_t)pd.pair_off + pair_begin) * PAIR_FLOATS;
 
         if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stages were last read through the generic proxy
             for (int k = 0; k < USAC_WARP_STAGES && k < ntiles; k++) {
                 const int s = (g + k) % USAC_WARP_STAGES;
                 const uint32_t bytes = min(USAC_TILE_PAIRS, npairs - k * USAC_TILE_PAIRS) * PAIR_FLOATS * 4;
