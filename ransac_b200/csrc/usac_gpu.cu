@@ -588,6 +588,7 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
         case USAC_EST_FUNDAMENTAL: score_kernel<USAC_EST_FUNDAMENTAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
         default: score_kernel<USAC_EST_ESSENTIAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
     }
+    if (cudaPeekAtLastError() != cudaSuccess) c->work_next = a.work_base;   // not launched: the counter did not move (callers report the error)
     cudaEventRecord(ev.second, c->stream);
     c->last_launches++;
     c->last_score_launches++;
