@@ -144,6 +144,24 @@ def test_score_counts_exact_stress(ctx, seed):
         ref = np.array([O.score(O.EST_HOMOGRAPHY, pts, m, thr)[0] for m in models])
         bad = np.where(cnt != ref)[0]
         assert len(bad) == 0, (thr, bad[:10], cnt[bad[:10]], ref[bad[:10]])
+    # Sampson metric: seven-point models of random and of all-inlier samples, perturbed ground truth, random matrices
+    ptsF, F, maskF = gen.fundamental(n=4000, seed=400 + seed)
+    inlF = np.where(maskF)[0]
+    modsF = [F.ravel()]
+    while len(modsF) < 700:
+        modsF.extend(O.solve_minimal(O.EST_FUNDAMENTAL, ptsF, g.choice(4000, 7, replace=False).astype(np.int32)))
+    while len(modsF) < 900:
+        modsF.extend(O.solve_minimal(O.EST_FUNDAMENTAL, ptsF, g.choice(inlF, 7, replace=False).astype(np.int32)))
+    for _ in range(100):
+        modsF.append((F.astype(np.float64) * (1 + g.normal(0, 10 ** g.uniform(-6, -1), (3, 3)))).astype(np.float32).ravel())
+    for _ in range(24):
+        modsF.append(g.normal(0, 1, 9).astype(np.float32))
+    modsF = np.stack(modsF[:1024]).astype(np.float32)
+    ctx.set_points(O.EST_FUNDAMENTAL, ptsF)
+    for thr in (2.0, 0.2, 30.0):
+        cnt, _ = ctx.score(modsF, thr)
+        ref = np.array([O.score(O.EST_FUNDAMENTAL, ptsF, m, thr)[0] for m in modsF])
+        assert np.array_equal(cnt, ref), (thr, np.where(cnt != ref)[0][:10])
     # essential metric (two-phase as well): calibrated coordinates, perturbed ground truth and random matrices
     ptsE, E, _ = gen.essential(n=4000, seed=300 + seed)
     mods = [E.ravel()]
