@@ -162,7 +162,11 @@ template <> struct FastModel<USAC_EST_ESSENTIAL> {
     }
     // Two phases, as for the homography: err = (da + db)/2 with da = |p1.l|/|l12| (l = E^T p2) and db >= 0, so da alone
     // beyond 2*thr + (its band + the band of the final sum) proves the outlier; phase2 adds the other epipolar distance.
+    #ifdef USAC_E_SINGLE_PHASE   /* tuning experiment (tools/): evaluate both halves for every pair */
+    static constexpr bool TWO_PHASE = false;
+#else
     static constexpr bool TWO_PHASE = true;
+#endif
     struct P1 { float2 u, p1; };                                           // u = da - 2*thr, p1 = ka/|l12| + k0 (>= 0)
     __device__ __forceinline__ void phase1(const float4 A, const float4 B, P1& s) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
