@@ -358,14 +358,7 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
 #pragma unroll
                         for (int q = 0; q < USAC_PPI; q++) {                                    // forward halves, independent streams
                             float4 A, B;
-#ifdef USAC_ABLATE_LDS   /* tuning experiment only (tools/): one shared-memory read per trip; results are wrong */
-                            load_pair(j, A, B);          // the same data rotated per q: distinct arithmetic, one LDS pair per trip
-                            if (q == 1) { A = make_float4(A.y, A.z, A.w, A.x); B = make_float4(B.y, B.z, B.w, B.x); }
-                            if (q == 2) { A = make_float4(A.z, A.w, A.x, A.y); B = make_float4(B.z, B.w, B.x, B.y); }
-                            if (q == 3) { A = make_float4(A.w, A.x, A.y, A.z); B = make_float4(B.w, B.x, B.y, B.z); }
-#else
                             load_pair(j + q, A, B);
-#endif
                             fm.phase1(A, B, st[q]);
                             bool ox, oy;
                             fm.sure(st[q], ox, oy);
