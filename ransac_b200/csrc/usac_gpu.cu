@@ -20,6 +20,7 @@
 #include "essential.cuh"
 #include "pipeline.cuh"
 #include "score.cuh"
+#include "score_queue.cuh"
 #include "sprt.cuh"
 #include "refit.cuh"
 #include "knn.cuh"
@@ -582,6 +583,12 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     c->work_next += (unsigned)items + grid * warps_per_cta;
     auto& ev = c->next_score_event();
     cudaEventRecord(ev.first, c->stream);
+    // USAC_GPU_SCORE_QUEUE=1: the experimental survivor-queue kernel (score_queue.cuh) for the two-phase evaluators
+    static const bool use_queue = getenv("USAC_GPU_SCORE_QUEUE") != nullptr;
+    if (use_queue && (c->est == USAC_EST_HOMOGRAPHY || c->est == USAC_EST_ESSENTIAL)) {
+        if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+        else score_queue_kernel<USAC_EST_ESSENTIAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+    } else
     switch (c->est) {
         case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
         case USAC_EST_HOMOGRAPHY: score_kernel<USAC_EST_HOMOGRAPHY><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
