@@ -13,7 +13,9 @@
 // Status (end of round 1): parity-green - tests/test_gpu_parity.py passes with USAC_GPU_SCORE_QUEUE=1 (58 tests: exact
 // counts, fits, stress) - and performance-NEUTRAL so far: C2 bench roofline.frac 0.775 vs 0.781 (value 9.9e11 vs 1.0e12),
 // outlier-only rounds 0.86 - 0.92 vs 0.91 - 0.94 (the shared copy of the records and the larger shared-memory footprint
-// cost what the dense batches save). Not the default; it needs an ncu pass before it is worth more work.
+// cost what the dense batches save). Not the default; it needs an ncu pass before it is worth more work. First suspect: code
+// size - `drain` is inlined at five call sites, the kernel is 2288 SASS instructions (36 KB, score_kernel: 1100), so the
+// instruction cache may be what limits it; make the drain a single out-of-line call site.
 #pragma once
 #include "score.cuh"
 
