@@ -1,6 +1,7 @@
 // score_queue.cuh - EXPERIMENTAL variant of the scoring kernel for the two-phase evaluators (homography, essential):
 // a per-warp SURVIVOR QUEUE instead of the warp-wide slow path. Selected at run time with USAC_GPU_SCORE_QUEUE=1
-// (launch_score in usac_gpu.cu); the default path is score_kernel<EST> in score.cuh and is not touched by this file.
+// (=2: the variant with an out-of-line drain) in launch_score (usac_gpu.cu); the default path is score_kernel<EST> in
+// score.cuh and is not touched by this file.
 //
 // Why: in score_kernel one evaluation out of the 64 of a pair of points x 32 models that the forward test cannot reject
 // sends the whole warp through the backward half for that pair (56 % of a launch on hard problems, profiles/README.md),
@@ -22,7 +23,46 @@
 #define USAC_Q_CAP 128           // queue entries per warp (a pair of points adds at most 64)
 #define USAC_Q_REC 23            // leading floats of a model record kept in shared memory (odd stride: conflict-free rows)
 
+// The dense batches as ONE out-of-line function (variant 2, USAC_GPU_SCORE_QUEUE=2): the inlined form below is instantiated
+// at five call sites. Written after the last GPU run of round 1: compiles, not yet run.
 template <int EST>
+__device__ __noinline__ void queue_drain_fn(const unsigned* qbuf, int qn, const float4* tp, const float* rec_s, const float* rec_group,
+                                            const float* aos, int idx0, int n, unsigned* cnt_io, float* sum_io) {
+    const int lane = threadIdx.x & 31;
+    unsigned cnt = *cnt_io;
+    float sum = *sum_io;
+    __syncwarp();
+    for (int base = 0; base < qn; base += 32) {
+        const int e = base + lane;
+        float em = 0.f;
+        int owner = -1;
+        if (e < qn) {
+            const unsigned ent = qbuf[e];
+            owner = (int)(ent >> 16);
+            const int pj = (int)((ent >> 1) & 0x7fffu), h = (int)(ent & 1u);
+            const float4 A = tp[2 * pj], B = tp[2 * pj + 1];
+            const float x1 = h ? A.y : A.x, y1 = h ? A.w : A.z, x2 = h ? B.y : B.x, y2 = h ? B.w : B.z;
+            FastModel<EST> fq;
+            fq.load(rec_s + owner * USAC_Q_REC);
+            float2 t, sb, w;
+            fq.eval(make_float4(x1, x1, y1, y1), make_float4(x2, x2, y2, y2), t, sb, w);
+            em = fminf(t.x, 0.f);
+            if (!(fabsf(t.x) > sb.x)) em = strict_em<EST>(rec_group + (size_t)owner * USAC_REC_STRIDE, aos, idx0 + 2 * pj + h, n);
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int l = 0; l < 32; l++) {
+            const int o = __shfl_sync(0xffffffffu, owner, l);
+            const float v = __shfl_sync(0xffffffffu, em, l);
+            if (o == lane) { cnt += __float_as_uint(v) >> 31; sum += v; }
+        }
+    }
+    __syncwarp();
+    *cnt_io = cnt;
+    *sum_io = sum;
+}
+
+template <int EST, bool OUTLINE>
 __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score_queue_kernel(const ScoreArgs a) {
     static_assert(FastModel<EST>::TWO_PHASE, "the survivor queue needs a forward-only outlier test");
     static_assert(REC_THR < USAC_Q_REC && REC_BAND + 2 < USAC_Q_REC, "FastModel::load must find its fields in the shared copy");
@@ -106,6 +146,11 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
 
             // one dense batch per 32 queued survivors; entries = lane << 16 | pair in tile << 1 | half
             auto drain = [&]() {
+                if constexpr (OUTLINE) {
+                    queue_drain_fn<EST>(qbuf, qn, tp, rec_s, rec_group, aos, idx0, pd.n, &cnt, &sum);
+                    qn = 0;
+                    return;
+                }
                 __syncwarp();                                         // queue stores visible to every lane
                 for (int base = 0; base < qn; base += 32) {
                     const int e = base + lane;

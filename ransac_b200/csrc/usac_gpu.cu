@@ -584,10 +584,15 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
     auto& ev = c->next_score_event();
     cudaEventRecord(ev.first, c->stream);
     // USAC_GPU_SCORE_QUEUE=1: the experimental survivor-queue kernel (score_queue.cuh) for the two-phase evaluators
-    static const bool use_queue = getenv("USAC_GPU_SCORE_QUEUE") != nullptr;
-    if (use_queue && (c->est == USAC_EST_HOMOGRAPHY || c->est == USAC_EST_ESSENTIAL)) {
-        if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
-        else score_queue_kernel<USAC_EST_ESSENTIAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+    static const int use_queue = [] { const char* e = getenv("USAC_GPU_SCORE_QUEUE"); return e ? atoi(e) : 0; }();
+    if (use_queue > 0 && (c->est == USAC_EST_HOMOGRAPHY || c->est == USAC_EST_ESSENTIAL)) {
+        if (use_queue == 2) {                                        // out-of-line drain (not yet run on a GPU)
+            if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY, true><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+            else score_queue_kernel<USAC_EST_ESSENTIAL, true><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+        } else {
+            if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY, false><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+            else score_queue_kernel<USAC_EST_ESSENTIAL, false><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+        }
     } else
     switch (c->est) {
         case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
