@@ -152,7 +152,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(per_step), "ms_per_fit": t / args.steps / per_step * 1e3},
+            "config": {"workload": workload_name(per_step), "problems_per_step": per_step, "ms_per_fit": t / args.steps / per_step * 1e3},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
                              "sample": f"{per_step} C2 image pairs per step, CPU oracle (restated reference; the reference needs "
                                        "OpenCV-contrib/Eigen/nanoflann and does not compile here), all host threads over independent fits"},
@@ -160,9 +160,11 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_name(problems):
+def workload_name(problems=None):
+    """Identical for the GPU arm and the reference arm (the driver compares the strings); the number of image pairs per step -
+    the full batch on the GPU, a bounded sample of it on the CPU - is `config.problems_per_step`."""
     return (f"C2 homography 4-pt normalized DLT, uniform sampler, N={N_POINTS}, {int(INLIER_RATIO * 100)}% inliers, thr {THR}, "
-            f"conf {CONF}, max_iter {MAX_IT}; step = {problems} independent image pairs per GPU, each run to adaptive termination")
+            f"conf {CONF}, max_iter {MAX_IT}; step = a batch of independent image pairs per GPU, each run to adaptive termination")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -333,6 +335,14 @@ def run_native(args):
     # results: one 168-byte FitState record per problem at the end + one `done` int per still-active problem per round
     d2h_step = B * 168 + sum(s[6] for s in stats_e2e) / args.steps * B * 4   # (upper bound: every problem active in every round)
 
+    # ---- second leg: the hypothesis-sharded 1M-point fit (config.c5) ----
+    c5 = None
+    if not args.no_c5:
+        for c2 in pipe_ctx + pipe_ctx2:
+            c2.close()
+        pipe_ctx, pipe_ctx2 = [], []
+        c5 = c5_leg(args, rank, world, local, max(5, args.steps), 3)
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([useful, useful_e2e, executed_p, launches], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -378,7 +388,7 @@ def run_native(args):
         line = {"metric": METRIC, "value": useful_all / (ms_all * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(B), "problems_per_gpu": B, "round_size": args.round_size,
+                "config": {"workload": workload_name(B), "problems_per_step": B, "problems_per_gpu": B, "round_size": args.round_size,
                            "l2": f"inputs larger than L2: {B * N_POINTS * 32 / 1e6:.0f} MB of points per GPU (AoS + pair layout) vs 126 MB",
                            "ms_per_fit": ms_all / args.steps / B, "avg_iterations_per_fit": iters / (args.steps * B),
                            "value_pipelined": sum(s[0] for s in stats_p) / (ms_pipe * 1e-3), "pipelined_streams": n_pipe,
@@ -387,6 +397,8 @@ def run_native(args):
                 "e2e": {"value": useful_e2e_all / (ms_e2e_all * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": B * N_POINTS * 16,
                         "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e_all / args.steps, "ms_per_fit": ms_e2e_all / args.steps / B},
                 "roofline": roofline}
+        if c5 is not None:
+            line["config"]["c5"] = c5
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         if args.latency:
@@ -401,23 +413,26 @@ def run_native(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# --workload c5: BASELINE.json configs[4] - ONE homography problem with 1M correspondences (10 % inliers, clustered),
-# NAPSAC over the device grid, 10 000 samples; the hypotheses of every round are sharded over the ranks and one NCCL
-# all-gather per round exchanges the per-sample scores (strong scaling: the job is fixed, more GPUs finish it sooner).
+# C5: BASELINE.json configs[4] - ONE homography problem with 1M correspondences (10 % inliers, clustered), NAPSAC over the
+# device grid, 10 000 samples; the hypotheses of every round are sharded over the ranks and one NCCL all-gather per round
+# exchanges the per-sample scores (strong scaling: the job is fixed, more GPUs finish it sooner). Runs as the second leg of
+# the default bench line (`config.c5`, so that the driver's --gpus N runs exercise usac_gpu_nccl_init / ncclAllGather) and
+# alone with `--workload c5`.
 # ---------------------------------------------------------------------------------------------------------------------
-def run_c5(args):
+C5_GOLDEN = os.path.join(ROOT, "tests", "golden", "c5_n1_oracle.json")   # the full 10 000-sample fit by the CPU oracle (committed)
+
+
+def c5_leg(args, rank, world, local, steps, warmup):
+    """-> dict for config.c5 (every rank returns it; identical on all ranks by construction and asserted so)."""
+    import zlib
+
     import torch
 
     from ransac_b200 import GpuContext, capi, nccl_unique_id
     from ransac_b200 import dist as D
     from ransac_b200 import generator as gen
-    local = env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    rank, world = D.init("nccl")
     n = args.c5_points
-    K = args.c5_round if args.c5_round > 0 else max(2048, 1024 * world)   # >= 1024 samples per rank and round (results do not depend on K)
+    K = args.c5_round if args.c5_round > 0 else 2048        # samples per round; NOT inflated with the rank count (results do not depend on K)
     pts = gen.make(5, n=n)[0]
     host = torch.from_numpy(pts).pin_memory()
     ctx = GpuContext(local)
@@ -425,18 +440,17 @@ def run_c5(args):
     ctx.set_stream(stream.cuda_stream)
     if world > 1:
         ctx.nccl_init(D.broadcast_bytes(nccl_unique_id() if rank == 0 else None), rank, world)
-    info = ctx.device_info()
     fit_kw = dict(threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=1, round_size=K, sampler=capi.SAMPLER_NAPSAC,
                   neighbors=capi.NEIGH_GRID, rank=rank, nranks=world)
     ctx.set_points(capi.EST_HOMOGRAPHY, host)
     ctx.set_neighbors_grid(0, 50)
 
-    def bracket(fn, steps):
+    def bracket(fn, nsteps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         D.barrier(); torch.cuda.synchronize()
         out = []
         ev0.record(stream)
-        for _ in range(steps):
+        for _ in range(nsteps):
             out.append(fn())
         ev1.record(stream)
         D.barrier(); torch.cuda.synchronize()
@@ -445,48 +459,70 @@ def run_c5(args):
     def step():
         r = ctx.fit_records(**fit_kw)[0]
         t = ctx.last_timing()
-        return int(r["useful_evals"]), int(r["evals"]), t["launches"], t["score_launches"], t["score_ms"], int(r["iterations"]), int(r["inliers"])
+        return (int(r["useful_evals"]), int(r["evals"]), t["launches"], t["score_launches"], t["score_ms"], int(r["iterations"]), int(r["inliers"]),
+                int(r["best_hyp"]), zlib.crc32(np.asarray(r["model"], np.float32).tobytes()), int(r["rounds"]))
 
     def step_e2e():
-        ctx.set_points(capi.EST_HOMOGRAPHY, host)          # H2D of the 16 MB point set; the neighbourhood grid (built on the host by
-        ctx.set_neighbors_grid(0, 50)                       # set_neighbors_grid, the reference times it separately: test/test.cpp:17-29) too
+        ctx.set_points(capi.EST_HOMOGRAPHY, host)          # H2D of the 16 MB point set + the device-side grid build (the reference
+        ctx.set_neighbors_grid(0, 50)                       # times its neighbourhood build separately: test/test.cpp:17-29)
         return step()
 
-    bracket(step, args.warmup)
+    bracket(step, warmup)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, st = bracket(step, args.steps)
+    ms, st = bracket(step, steps)
     clk = clocks.stop()
-    ms_e2e, st_e2e = bracket(step_e2e, max(1, min(args.steps, 3)))
-    t_all = D.reduce_max([ms, ms_e2e / max(1, min(args.steps, 3)) * args.steps])
-    sums = D.reduce_sum([sum(x[0] for x in st), sum(x[1] for x in st), sum(x[2] for x in st), sum(x[0] for x in st_e2e) / len(st_e2e) * args.steps])
-    if rank == 0:
-        peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
-        executed, launches, score_ms = sum(x[1] for x in st), sum(x[3] for x in st), sum(x[4] for x in st)
-        ach = 42.0 * executed / (score_ms * 1e-3) / 1e12
-        line = {"metric": METRIC, "value": sums[0] / (t_all[0] * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_all[0] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"C5 homography N={n}, 10% inliers (clustered), NAPSAC grid cell 50, max_iter {MAX_IT}, conf {CONF}; "
-                                       f"step = one robust fit, hypotheses sharded over {world} GPU(s), one NCCL all-gather per round of {K} samples",
-                           "ms_per_fit": t_all[0] / args.steps, "iterations": st[-1][5], "inliers": st[-1][6],
-                           "l2": "the 32 MB point set (AoS + pair layout) is L2 resident by design: it is re-read by every model block",
-                           "evals_executed_per_s": sums[1] / (t_all[0] * 1e-3)},
-                "clocks": clk, "gpu_launches": int(sums[2]),
-                "e2e": {"value": sums[3] / (t_all[1] * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 168 + 4 * st[-1][2],
-                        "ms_per_step": t_all[1] / args.steps, "note": "includes the host-side grid build of set_neighbors_grid"},
-                "roofline": {"bound": "fp32", "kernel": "score_kernel<HOMOGRAPHY>", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                             "traffic": None, "flops_per_eval": 42, "avg_launch_ms": score_ms / max(launches, 1)}}
-        if world == 1 and not args.no_cpu:
-            from oracle import oracle as O
-            t0 = time.perf_counter()
-            ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_GRID, cell_size=50,
-                           threshold=THR, confidence=CONF, max_iterations=128, seed=1)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ref["evals"] / dt, "unit": "evals/s", "cores": 1, "kind": "port",
-                                    "sample": "the first 128 hypotheses of the same fit (sequential oracle, one thread; includes its grid build)"}
-        print(json.dumps(line))
+    n_e2e = max(1, min(steps, 3))
+    ms_e2e, st_e2e = bracket(step_e2e, n_e2e)
+    t_all = D.reduce_max([ms / steps, ms_e2e / n_e2e])
+    sums = D.reduce_sum([sum(x[0] for x in st), sum(x[1] for x in st), sum(x[2] for x in st), sum(x[0] for x in st_e2e) / n_e2e])
+    # every rank must hold the same result (the gathered scores and select_kernel are identical everywhere)
+    mine = [float(st[-1][5]), float(st[-1][6]), float(st[-1][7]), float(st[-1][8])]
+    lo_, hi_ = D.reduce_max(mine), [-v for v in D.reduce_max([-v for v in mine])]
+    ranks_agree = lo_ == hi_ == mine
+    assert ranks_agree, f"C5: ranks disagree: rank {rank} has {mine}, max {lo_}, min {hi_}"
+    parity = None
+    if n == 1000000 and os.path.exists(C5_GOLDEN):
+        gold = json.load(open(C5_GOLDEN))
+        parity = all(int(st[-1][i]) == int(gold[k]) for i, k in ((5, "iterations"), (6, "inliers"), (7, "best_hyp"), (8, "model_crc")))
+        assert parity, f"C5: result differs from the single-GPU / oracle record {gold}: {st[-1][5:9]}"
+    executed, launches, score_ms = sum(x[1] for x in st), sum(x[3] for x in st), sum(x[4] for x in st)
+    info = ctx.device_info()
+    peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
+    out = {"workload": f"C5 homography N={n}, 10% inliers (clustered), NAPSAC grid cell 50, max_iter {MAX_IT}, conf {CONF}; one robust fit, "
+                       f"hypotheses of every round of {K} samples sharded over {world} GPU(s), one NCCL all-gather per round",
+           "scaling": "strong", "ms_per_fit": t_all[0], "evals_per_s": sums[0] / steps / (t_all[0] * 1e-3),
+           "evals_executed_per_s": sums[1] / steps / (t_all[0] * 1e-3),
+           "iterations": st[-1][5], "inliers": st[-1][6], "best_hyp": st[-1][7], "model_crc": st[-1][8], "rounds": st[-1][9],
+           "parity_vs_n1": parity, "parity_note": "iterations / inliers / winning sample / model CRC32 equal tests/golden/c5_n1_oracle.json "
+           "(the CPU oracle's full fit, = the 1-GPU result) on every rank", "ranks_agree": bool(ranks_agree),
+           "gpu_launches_per_fit": sums[2] / steps / world, "e2e_ms_per_fit": t_all[1], "e2e_evals_per_s": sums[3] / (t_all[1] * 1e-3),
+           "h2d_bytes_per_fit": n * 16,
+           "score_kernel_frac_of_fp32_peak": 42.0 * executed / (score_ms * 1e-3) / 1e12 / peak, "score_share_of_fit": score_ms / ms,
+           "clocks": clk}
     ctx.close()
+    return out
+
+
+def run_c5(args):
+    import torch
+
+    from ransac_b200 import dist as D
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    rank, world = D.init("nccl")
+    c5 = c5_leg(args, rank, world, local, args.steps, max(args.warmup, 3))
+    if rank == 0:
+        line = {"metric": METRIC, "value": c5["evals_per_s"], "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": c5["ms_per_fit"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": c5["workload"], "c5": c5,
+                                                "l2": "the 32 MB point set (AoS + pair layout) is L2 resident by design: it is re-read by every model block"},
+                "clocks": c5["clocks"], "gpu_launches": int(c5["gpu_launches_per_fit"] * args.steps * world),
+                "e2e": {"value": c5["e2e_evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": c5["h2d_bytes_per_fit"], "d2h_bytes_per_step": 168 + 4 * c5["rounds"],
+                        "ms_per_step": c5["e2e_ms_per_fit"], "note": "includes the device-side grid build of set_neighbors_grid"}}
+        print(json.dumps(line))
     D.finalize()
 
 
@@ -513,10 +549,11 @@ def main():
     ap.add_argument("--round-size", type=int, default=256, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
+    ap.add_argument("--no-c5", action="store_true", help="skip the second leg (config.c5: the hypothesis-sharded 1M-point fit)")
     ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
-    ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 workload (0 = max(2048, 1024 x ranks))")
+    ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 leg (0 = 2048)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = max(args.warmup, 1)

@@ -77,7 +77,9 @@ typedef struct {
     unsigned prosac_termination_length;   /* PROSAC: frozen for the call; 0 = n */
     unsigned prosac_hyp_count;            /* PROSAC: t of the first sample of this call (starts at 1) */
 } usac_sampler_cfg;
-/* samples_out: K x m int32 (m = 2/4/7/5), hypothesis ids first_hyp .. first_hyp+K-1 */
+/* samples_out: K x m int32 (m = 2/4/7/5), hypothesis ids first_hyp .. first_hyp+K-1. Samplers other than UNIFORM / NAPSAC /
+ * PROSAC (the reference's ProgressiveNapsac is an unfinished stub, progressive_sampler.hpp:149-172; Evsac / ProsacNapsac are
+ * not wired in init.cpp:23-50) and rng values other than USAC_RNG_* are rejected with USAC_ERR_ARG. */
 int usac_gpu_sample(usac_gpu_ctx* ctx, int problem, const usac_sampler_cfg* cfg, uint64_t first_hyp, int K, int* samples_out);
 
 /* ---- Estimator: replaces Estimator::EstimateModel x K (estimator.hpp:19; line2d/homography/fundamental/essential) */
@@ -101,6 +103,11 @@ typedef struct {
     /* model.hpp:13,25: LocOpt - 0 NullLO, 1 InItLORsc (inner + iterative LO), 2 InItFLORsc (limited samples); runs on every new
      * best model (ransac.cpp:108-110; local_optimization/inner_local_optimization.hpp:74-133, iterative_local_optimization.hpp) */
     int lo;
+    /* model.hpp:26-29 (Model::setLOParametres): 0 = the reference defaults 14 / 20 / 4 / 10 */
+    unsigned lo_sample_size, lo_inner_iterations, lo_iterative_iterations, lo_threshold_multiplier;
+    /* model.hpp:39: SPRT-rejected models of the first this-many hypotheses still get a full inlier count (sprt.hpp:243-257)
+     * and do not burn an iteration (ransac.cpp:77-85). 0 = the reference default 20. */
+    unsigned max_hypothesis_test_before_sprt;
 } usac_fit_cfg;
 
 typedef struct {
@@ -116,7 +123,14 @@ typedef struct {
     unsigned long long useful_evals; /* the part of `evals` the sequential loop of ransac.cpp:58-139 would also have
                                         executed: models of the samples up to the one that ended the loop */
     unsigned lo_inner_iters, lo_iterative_iters;   /* RansacOutput::getLOInnerIters / getLOIterativeIters */
+    float msac;                  /* MSAC truncated cost sum_i min(err_i, threshold) = score + (n - inliers) * threshold, from the two
+                                    quantities of Score (quality.hpp:85-100); NaN under SPRT, where `score` is an inlier count */
 } usac_fit_result;
+
+/* the same derivation for the Quality API: MSAC truncated cost of a model from usac_gpu_score's outputs */
+static inline float usac_msac_cost(int n_points, int inliers, float sum_err, float threshold) {
+    return sum_err + (float)(n_points - inliers) * threshold;
+}
 
 int usac_gpu_fit(usac_gpu_ctx* ctx, const usac_fit_cfg* cfg, usac_fit_result* results /* [num_problems] */);
 

@@ -139,13 +139,17 @@ class GpuContext:
 
     # ---- fused fit ----
     def fit_records(self, threshold, confidence=0.95, max_iterations=10000, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, seed=1,
-                    sprt=False, round_size=0, neighbors=NEIGH_NONE, sample_table=None, rank=0, nranks=1, lo=0):
+                    sprt=False, round_size=0, neighbors=NEIGH_NONE, sample_table=None, rank=0, nranks=1, lo=0, lo_params=None,
+                    max_hypothesis_test_before_sprt=0):
         """One robust fit per uploaded problem; returns a numpy record array laid out as usac_fit_result (no per-problem
         Python work: this is what a batched caller uses)."""
         cfg = capi.FitCfg()
         cfg.sampler = capi.SamplerCfg(sampler, rng, seed, neighbors, 0, 0)
         cfg.threshold, cfg.confidence, cfg.max_iterations = threshold, confidence, max_iterations
         cfg.sprt, cfg.round_size, cfg.rank, cfg.nranks, cfg.lo = int(sprt), round_size, rank, nranks, int(lo)
+        if lo_params is not None:     # (lo_sample_size, lo_inner_iterations, lo_iterative_iterations, lo_threshold_multiplier), model.hpp:26-29
+            cfg.lo_sample_size, cfg.lo_inner_iterations, cfg.lo_iterative_iterations, cfg.lo_threshold_multiplier = [int(v) for v in lo_params]
+        cfg.max_hypothesis_test_before_sprt = int(max_hypothesis_test_before_sprt)
         if sample_table is not None:
             t = np.ascontiguousarray(sample_table, dtype=np.int32)
             self._table = t
@@ -162,7 +166,7 @@ class GpuContext:
         return [{"model": np.array(r["model"][:w], np.float32), "inliers": int(r["inliers"]), "score": float(r["score"]),
                  "iterations": int(r["iterations"]), "samples_drawn": int(r["samples_drawn"]), "best_hyp": int(r["best_hyp"]),
                  "best_model_idx": int(r["best_model_idx"]), "rounds": int(r["rounds"]), "evals": int(r["evals"]),
-                 "useful_evals": int(r["useful_evals"]), "lo_inner": int(r["lo_inner_iters"]), "lo_iterative": int(r["lo_iterative_iters"])} for r in rec]
+                 "useful_evals": int(r["useful_evals"]), "lo_inner": int(r["lo_inner_iters"]), "lo_iterative": int(r["lo_iterative_iters"]), "msac": float(r["msac"])} for r in rec]
 
     def estimate_nonminimal(self, ids, problem=0):
         """Estimator::EstimateModelNonMinimalSample on a list of point ids -> model (9 or 3 floats) or None."""

@@ -28,13 +28,16 @@ class SamplerCfg(C.Structure):
 class FitCfg(C.Structure):
     _fields_ = [("sampler", SamplerCfg), ("threshold", C.c_float), ("confidence", C.c_float), ("max_iterations", C.c_uint),
                 ("sprt", C.c_int), ("round_size", C.c_int), ("sample_table", C.POINTER(C.c_int)),
-                ("sample_table_rows", C.c_uint), ("rank", C.c_int), ("nranks", C.c_int), ("lo", C.c_int)]
+                ("sample_table_rows", C.c_uint), ("rank", C.c_int), ("nranks", C.c_int), ("lo", C.c_int),
+                ("lo_sample_size", C.c_uint), ("lo_inner_iterations", C.c_uint), ("lo_iterative_iterations", C.c_uint),
+                ("lo_threshold_multiplier", C.c_uint), ("max_hypothesis_test_before_sprt", C.c_uint)]
 
 
 class FitResult(C.Structure):
     _fields_ = [("model", C.c_float * 9), ("inliers", C.c_int), ("score", C.c_float), ("iterations", C.c_uint),
                 ("samples_drawn", C.c_uint), ("best_hyp", C.c_longlong), ("best_model_idx", C.c_int), ("rounds", C.c_uint),
-                ("evals", C.c_ulonglong), ("useful_evals", C.c_ulonglong), ("lo_inner_iters", C.c_uint), ("lo_iterative_iters", C.c_uint)]
+                ("evals", C.c_ulonglong), ("useful_evals", C.c_ulonglong), ("lo_inner_iters", C.c_uint), ("lo_iterative_iters", C.c_uint),
+                ("msac", C.c_float)]
 
 
 class RefitResult(C.Structure):

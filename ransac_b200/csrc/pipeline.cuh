@@ -37,6 +37,7 @@ struct RoundArgs {
     const int* pool;             // shuffled point pools (ProblemDesc::pool_off)
     struct SprtModelResult* sprt_res;   // [slot][K*S]
     int* done_out;               // [slot] FitState::done after the round (the only thing the host reads per round)
+    unsigned before_sprt;        // model.hpp:39 max_hypothesis_test_before_sprt
     int limit_remaining;         // 1: samples the sequential loop can no longer reach (index >= max_iters - iters at the start of
                                  // the round; the bound never grows) are not solved or scored
 };
@@ -149,6 +150,9 @@ __global__ void napsac_seed_kernel(const RoundArgs a) {
         if (tries == pd.n) p = -1;           // no usable neighbourhood anywhere: uniform fallback for this sample
     }
     a.seeds[(size_t)slot * a.K + j] = p;
+    // how often the round uses each seed point (second half of the cursor segment, all zero between rounds): a seed used once -
+    // the common case - needs no search for earlier uses in sample_kernel
+    if (p >= 0) atomicAdd(&a.cursors[pd.cursor_off + pd.n + p], 1u);
 }
 
 __global__ void napsac_commit_kernel(const RoundArgs a) {
@@ -156,7 +160,11 @@ __global__ void napsac_commit_kernel(const RoundArgs a) {
     if (j >= a.K) return;
     const int pid = a.active[slot];
     const int p = a.seeds[(size_t)slot * a.K + j];
-    if (p >= 0) atomicAdd(&a.cursors[a.prob[pid].cursor_off + p], (unsigned)(a.m - 1));
+    if (p >= 0) {
+        const ProblemDesc pd = a.prob[pid];
+        atomicAdd(&a.cursors[pd.cursor_off + p], (unsigned)(a.m - 1));
+        a.cursors[pd.cursor_off + pd.n + p] = 0u;                     // use count back to zero for the next round
+    }
 }
 
 __global__ void sample_kernel(const RoundArgs a) {
@@ -201,7 +209,8 @@ __global__ void sample_kernel(const RoundArgs a) {
             philox_unique(a.seed, hyp, 0, n, m, s);
         } else {
             unsigned c = a.cursors[pd.cursor_off + p];
-            for (int i = 0; i < j; i++) c += (seeds[i] == p) ? (unsigned)(m - 1) : 0u;   // earlier uses within this round
+            if (a.cursors[pd.cursor_off + n + p] > 1u)                                     // rare: the round draws this seed more than once
+                for (int i = 0; i < j; i++) c += (seeds[i] == p) ? (unsigned)(m - 1) : 0u;   // earlier uses within this round
             s[0] = p;
             if (a.neighbors == USAC_NEIGH_KNN) {
                 const int* row = a.knn + pd.knn_off + (size_t)pd.knn * p;

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const 
         pa = na; pb = nb; idx = wrap(idx + 2);
     }
     res.good = good; res.tested_inl = tin; res.tested_pts = tp; res.full_inl = tin;
-    if (!good && (unsigned long long)st.samples_drawn + (unsigned long long)j < 20ull) {
+    if (!good && (unsigned long long)st.samples_drawn + (unsigned long long)j < (unsigned long long)a.before_sprt) {
         // sprt.hpp:243-257: keep counting from the point after the rejecting one
         int pos = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q + (unsigned long long)tp) % (unsigned long long)n);
         int rest = n - tp, c = 0;

@@ -267,27 +267,27 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     if (estimator < USAC_EST_LINE2D || estimator > USAC_EST_ESSENTIAL) return fail(c, USAC_ERR_ARG, "set_points: unknown estimator");
     cudaSetDevice(c->device);
     const int dim = usac_point_dim(estimator);
-    c->est_prev = c->est;
-    c->est = estimator; c->P = P;
-    const std::vector<ProblemDesc> old = std::move(c->h_prob);  // equally sized point sets keep their termination-table offsets
-    c->h_prob.assign(P, ProblemDesc());
-    c->h_prob_pushed.clear(); c->maxima_fetched = false;
+    // validate and lay out in locals first: the context changes only once nothing can fail any more, and a failure after that
+    // point leaves it empty (P = 0) rather than half updated
+    std::vector<ProblemDesc> desc(P);
     std::vector<long long> pair_offs(P);
     long long aos = 0, pairs = 0;
+    const bool same_shape = c->h_prob.size() == (size_t)P && estimator == c->est;
     for (int p = 0; p < P; p++) {
         const int n = n_per_problem[p];
         if (n < usac_sample_size(estimator)) return fail(c, USAC_ERR_ARG, "set_points: a problem has fewer points than the minimal sample");
-        ProblemDesc& d = c->h_prob[p];
+        ProblemDesc& d = desc[p];
         memset(&d, 0, sizeof(d));
         d.n = n; d.n_pairs = (n + 1) / 2; d.aos_off = aos; d.pair_off = pairs;
         d.growth_off = d.term_off = d.pool_off = d.knn_off = d.grid_off = d.cell_start_off = d.cursor_off = -1;
-        if (old.size() == (size_t)P && old[p].n == n && estimator == c->est_prev) d.term_off = old[p].term_off;
+        if (same_shape && c->h_prob[p].n == n) d.term_off = c->h_prob[p].term_off;   // equally sized point sets keep their termination-table offsets
         pair_offs[p] = pairs;
         aos += n; pairs += d.n_pairs;
     }
-    c->total_points = aos; c->total_pairs = pairs;
-    c->h_pool_set.assign(P, 0);
-    c->side = SideUsed();                 // neighbourhoods / pools belong to the previous point sets
+    struct Rollback {                          // any early return below leaves an empty, consistent context
+        usac_gpu_ctx* c; bool armed = true;
+        ~Rollback() { if (armed) { c->P = 0; c->est = 0; c->h_prob.clear(); c->h_prob_pushed.clear(); c->total_points = c->total_pairs = 0; c->term_signature.clear(); c->state_init_sig.clear(); } }
+    } rollback{c};
     const size_t pair_floats = (dim == 4) ? 8 : 4;
     CUDA_TRY(c, c->d_aos.ensure((size_t)aos * dim));
     CUDA_TRY(c, c->d_pairs.ensure((size_t)pairs * pair_floats));
@@ -303,16 +303,25 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     CUDA_TRY(c, c->d_done.ensure(P));
     if (c->h_state_cap < (size_t)P) {
         if (c->h_state) cudaFreeHost(c->h_state);
+        c->h_state = nullptr; c->h_state_cap = 0;
         CUDA_TRY(c, cudaMallocHost(&c->h_state, sizeof(FitState) * P));
         c->h_state_cap = P;
     }
     if (c->h_active_cap < (size_t)P) {
         if (c->h_active) cudaFreeHost(c->h_active);
-        CUDA_TRY(c, cudaMallocHost(&c->h_active, sizeof(int) * P));
         if (c->h_done) cudaFreeHost(c->h_done);
+        c->h_active = c->h_done = nullptr; c->h_active_cap = 0;
+        CUDA_TRY(c, cudaMallocHost(&c->h_active, sizeof(int) * P));
         CUDA_TRY(c, cudaMallocHost(&c->h_done, sizeof(int) * P));
         c->h_active_cap = P;
     }
+    c->est_prev = c->est;
+    c->est = estimator; c->P = P;
+    c->h_prob = std::move(desc);
+    c->h_prob_pushed.clear(); c->maxima_fetched = false;
+    c->total_points = aos; c->total_pairs = pairs;
+    c->h_pool_set.assign(P, 0);
+    c->side = SideUsed();                 // neighbourhoods / pools belong to the previous point sets
     {   // the point upload goes in 4 MB pieces: the copy engine serves streams in submission order, and the few-KB uploads of
         // another context's running fit (its per-round active list) must not wait behind one 100+ MB transfer
         const size_t bytes = (size_t)aos * dim * sizeof(float), piece = (size_t)4 << 20;
@@ -328,6 +337,7 @@ extern "C" int usac_gpu_set_points(usac_gpu_ctx* c, int estimator, const float* 
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // pair_offs / h_prob staging are stack/heap temporaries
     c->h_prob_pushed = c->h_prob;                    // d_prob = this + the coordinate maxima layout_kernel has just written
+    rollback.armed = false;
     return USAC_OK;
 }
 
@@ -378,13 +388,47 @@ static cudaError_t append_segment(DevBuf<T>& buf, size_t& used, const T* host, s
 }
 
 
+// reserve a segment of `count` elements at the end of a side array (contents undefined)
+template <class T>
+static cudaError_t reserve_segment(DevBuf<T>& buf, size_t used, size_t count, cudaStream_t s) {
+    if (used + count <= buf.cap) return cudaSuccess;
+    DevBuf<T> nb;
+    cudaError_t e = nb.ensure(std::max((used + count) * 2, (size_t)1024));
+    if (e != cudaSuccess) return e;
+    if (used) cudaMemcpyAsync(nb.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    cudaStreamSynchronize(s);
+    buf.release();
+    buf = nb;
+    return cudaSuccess;
+}
+
+// segment of the kNN side array for a problem: an earlier table of the same size is overwritten in place (no leak on repeated calls)
+static cudaError_t knn_segment(usac_gpu_ctx* c, ProblemDesc& d, int k, long long* off_out, bool* fresh) {
+    SideUsed& u = c->side;
+    if (d.knn_off >= 0 && d.knn == k) { *off_out = d.knn_off; *fresh = false; return cudaSuccess; }
+    cudaError_t e = reserve_segment(c->d_knn, u.knn, (size_t)d.n * k, c->stream);
+    if (e != cudaSuccess) return e;
+    *off_out = (long long)u.knn; *fresh = true;
+    return cudaSuccess;
+}
+
 extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const int* neighbors, int k) {
     if (!c || problem < 0 || problem >= c->P || !neighbors || k < 1) return fail(c, USAC_ERR_ARG, "set_neighbors_knn: bad arguments");
+    if (k < usac_sample_size(c->est) - 1)
+        return fail(c, USAC_ERR_ARG, "set_neighbors_knn: k must be at least sample size - 1 (napsac_sampler.hpp:49 asserts it: a smaller k repeats points within a sample)");
     cudaSetDevice(c->device);
     SideUsed& u = c->side;
     ProblemDesc& d = c->h_prob[problem];
-    CUDA_TRY(c, append_segment(c->d_knn, u.knn, neighbors, (size_t)d.n * k, &d.knn_off, c->stream));
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)d.n, &d.cursor_off, c->stream));
+    for (size_t i = 0; i < (size_t)d.n * k; i++)
+        if (neighbors[i] < 0 || neighbors[i] >= d.n) return fail(c, USAC_ERR_ARG, "set_neighbors_knn: neighbour index out of range");
+    long long off;
+    bool fresh;
+    CUDA_TRY(c, knn_segment(c, d, k, &off, &fresh));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_knn.p + off, neighbors, sizeof(int) * (size_t)d.n * k, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (fresh) u.knn += (size_t)d.n * k;
+    d.knn_off = off;
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)d.n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -425,20 +469,6 @@ __global__ void grid_scatter_kernel(const int* __restrict__ sidx, const int* __r
     rank[p] = q - cell_start[cid];
 }
 
-// reserve a segment of `count` elements at the end of a side array (contents undefined)
-template <class T>
-static cudaError_t reserve_segment(DevBuf<T>& buf, size_t used, size_t count, cudaStream_t s) {
-    if (used + count <= buf.cap) return cudaSuccess;
-    DevBuf<T> nb;
-    cudaError_t e = nb.ensure(std::max((used + count) * 2, (size_t)1024));
-    if (e != cudaSuccess) return e;
-    if (used) cudaMemcpyAsync(nb.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
-    cudaStreamSynchronize(s);
-    buf.release();
-    buf = nb;
-    return cudaSuccess;
-}
-
 // ---- device-side kNN build (nearest_neighbors.cpp:69-128), kernels in knn.cuh
 template <int DIM>
 static void launch_knn_query(int cap, int blocks, cudaStream_t st, const float4* spts, const int* sidx, const unsigned* skeys, const int* cell_start,
@@ -454,8 +484,11 @@ extern "C" int usac_gpu_build_neighbors_knn(usac_gpu_ctx* c, int problem, int k)
     ProblemDesc& d = c->h_prob[problem];
     const int n = d.n, dim = usac_point_dim(c->est);
     if (n < k + 1) return fail(c, USAC_ERR_ARG, "build_neighbors_knn: needs at least k + 1 points");
+    if (k < usac_sample_size(c->est) - 1) return fail(c, USAC_ERR_ARG, "build_neighbors_knn: k must be at least sample size - 1 (napsac_sampler.hpp:49)");
     SideUsed& u = c->side;
-    CUDA_TRY(c, reserve_segment(c->d_knn, u.knn, (size_t)n * k, c->stream));
+    long long knn_off;
+    bool knn_fresh;
+    CUDA_TRY(c, knn_segment(c, d, k, &knn_off, &knn_fresh));
     const int G = std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)n / 16.0))));
     const int ncells = G * G;
     CUDA_TRY(c, c->d_grid_keys.ensure((size_t)n + 8));                       // 2 x n unsigned keys + bbox + grid descriptor
@@ -482,14 +515,14 @@ extern "C" int usac_gpu_build_neighbors_knn(usac_gpu_ctx* c, int problem, int k)
     CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_grid_temp.p, tb, keys, skeys, idx, sidx, n, 0, bits, c->stream));
     knn::cell_start_kernel<<<(ncells + 1 + 255) / 256, 256, 0, c->stream>>>(skeys, n, ncells, c->d_knn_cells.p);
     knn::gather_kernel<<<g, 256, 0, c->stream>>>(pts, n, dim, sidx, c->d_knn_pts.p);
-    int* table = c->d_knn.p + u.knn;
+    int* table = c->d_knn.p + knn_off;
     if (dim == 4) launch_knn_query<4>(k + 1, (n + 127) / 128, c->stream, c->d_knn_pts.p, sidx, skeys, c->d_knn_cells.p, gd, G, n, k, table);
     else launch_knn_query<2>(k + 1, (n + 127) / 128, c->stream, c->d_knn_pts.p, sidx, skeys, c->d_knn_cells.p, gd, G, n, k, table);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    d.knn_off = (long long)u.knn;
-    u.knn += (size_t)n * k;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)n, &d.cursor_off, c->stream));
+    d.knn_off = knn_off;
+    if (knn_fresh) u.knn += (size_t)n * k;
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -547,7 +580,7 @@ extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cel
     d.cell_start_off = (long long)u.cell_start;
     u.grid += (size_t)n;
     u.cell_start += (size_t)n + 1;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, (size_t)n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_GRID;
     return push_desc(c);
 }
@@ -931,6 +964,17 @@ static void fill_round_args(usac_gpu_ctx* c, RoundArgs& a, const usac_sampler_cf
     a.rank = 0; a.nranks = 1; a.nchunks = 1;
 }
 
+// Only the samplers that exist: the reference's ProgressiveNapsac never fills its sample (progressive_sampler.hpp:149-172) and
+// Evsac / ProsacNapsac are not wired (init.cpp:23-50) - an unknown enum must not silently become uniform sampling.
+static const char* check_sampler_cfg(const usac_sampler_cfg& s) {
+    if (s.sampler != USAC_SAMPLER_UNIFORM && s.sampler != USAC_SAMPLER_NAPSAC && s.sampler != USAC_SAMPLER_PROSAC)
+        return "sampler must be USAC_SAMPLER_UNIFORM, USAC_SAMPLER_NAPSAC or USAC_SAMPLER_PROSAC (Progressive NAPSAC is a stub in the reference and is not built)";
+    if (s.rng != USAC_RNG_PHILOX && s.rng != USAC_RNG_TABLE) return "rng must be USAC_RNG_PHILOX or USAC_RNG_TABLE";
+    if (s.sampler == USAC_SAMPLER_NAPSAC && s.neighbors != USAC_NEIGH_KNN && s.neighbors != USAC_NEIGH_GRID)
+        return "NAPSAC needs neighbors = USAC_NEIGH_KNN or USAC_NEIGH_GRID";
+    return nullptr;
+}
+
 static void launch_sampler(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
     dim3 g((a.K + 127) / 128, slots);
     if (a.sampler == USAC_SAMPLER_NAPSAC) { napsac_seed_kernel<<<g, 128, 0, c->stream>>>(a); c->last_launches++; }
@@ -952,6 +996,7 @@ static void init_state(FitState& s, const ProblemDesc& d, int est, unsigned max_
 
 extern "C" int usac_gpu_sample(usac_gpu_ctx* c, int problem, const usac_sampler_cfg* cfg, uint64_t first_hyp, int K, int* samples_out) {
     if (!c || !cfg || problem < 0 || problem >= c->P || K <= 0 || !samples_out) return fail(c, USAC_ERR_ARG, "sample: bad arguments");
+    if (const char* why = check_sampler_cfg(*cfg)) return fail(c, USAC_ERR_ARG, why);
     if (cfg->rng == USAC_RNG_TABLE) return fail(c, USAC_ERR_ARG, "sample: table replay has nothing to generate");
     cudaSetDevice(c->device);
     int rc = ensure_round_buffers(c, 1, K, 1, 1);
@@ -1057,8 +1102,13 @@ struct LoRunner {
     int *A, *B, *d_sample, *d_pos, *d_stat, *d_ok;
     float* d_model;
 
-    int init(usac_gpu_ctx* ctx, int problem_, int kind_, float threshold, uint64_t seed_) {
-        c = ctx; problem = problem_; kind = kind_; seed = seed_;
+    int init(usac_gpu_ctx* ctx, int problem_, const usac_fit_cfg* cfg) {
+        const float threshold = cfg->threshold;
+        c = ctx; problem = problem_; kind = cfg->lo; seed = cfg->sampler.seed;
+        if (cfg->lo_sample_size) sample_limit = (int)cfg->lo_sample_size;            // Model::setLOParametres, model.hpp:26-29
+        if (cfg->lo_inner_iterations) inner_iters = (int)cfg->lo_inner_iterations;
+        if (cfg->lo_iterative_iterations) iter_iters = (int)cfg->lo_iterative_iterations;
+        if (cfg->lo_threshold_multiplier) mult = (int)cfg->lo_threshold_multiplier;
         const ProblemDesc& d = c->h_prob[problem];
         n = d.n; m = usac_sample_size(c->est); w = c->est == USAC_EST_LINE2D ? 3 : 9; dim = usac_point_dim(c->est);
         theta = threshold; lo_thr = threshold;
@@ -1237,6 +1287,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
     const bool is_prosac = cfg->sampler.sampler == USAC_SAMPLER_PROSAC, is_sprt = cfg->sprt != 0;
     const float log_1_p = (float)logf(1 - cfg->confidence);
     const int KS = K * S;
+    const unsigned before_sprt = cfg->max_hypothesis_test_before_sprt ? cfg->max_hypothesis_test_before_sprt : 20u;   // model.hpp:39
     std::vector<int> h_nmodels(K), ids;
     std::vector<SprtModelResult> h_res(KS);
     std::vector<int2> h_scores(KS);
@@ -1257,7 +1308,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         if (is_sprt) sprt.init(c->est, n, (unsigned)m, cfg->max_iterations);
         if (is_prosac) { prosac_growth(n, (unsigned)m, growth); pterm.init(growth, n, (unsigned)m, cfg->confidence, cfg->max_iterations); }
         LoRunner lo;
-        if (cfg->lo) { rc = lo.init(c, p, cfg->lo, cfg->threshold, cfg->sampler.seed); if (rc) return rc; }
+        if (cfg->lo) { rc = lo.init(c, p, cfg); if (rc) return rc; }
         bool done = false;
         while (!done && hs.iters < hs.max_iters) {
             if (is_prosac) hs.prosac_term_len = pterm.termination_length;
@@ -1276,6 +1327,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
             fill_round_args(c, a, cfg->sampler, K);
             a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
             a.table_rows = cfg->sample_table_rows; a.nchunks = nchunks; a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
+            a.before_sprt = before_sprt;
             launch_sampler(c, a, 1);
             switch (c->est) {
                 case USAC_EST_LINE2D: launch_solve<USAC_EST_LINE2D>(c, a, 1); break;
@@ -1321,7 +1373,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 for (int i = 0; i < h_nmodels[j]; i++) {
                     const int q = j * S + i;
                     unsigned long long cost;
-                    if (is_sprt) cost = (unsigned long long)h_res[q].tested_pts + ((!h_res[q].good && hyp0 + j < 20) ? (unsigned long long)(n - h_res[q].tested_pts) : 0ull);
+                    if (is_sprt) cost = (unsigned long long)h_res[q].tested_pts + ((!h_res[q].good && hyp0 + j < before_sprt) ? (unsigned long long)(n - h_res[q].tested_pts) : 0ull);
                     else cost = n;
                     evals += cost;
                     if (stopped) continue;
@@ -1332,7 +1384,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                         const SprtModelResult& r = h_res[q];
                         if (r.good) { if (r.tested_inl > hs.best_cnt) last_improving = r.tested_inl; }
                         else { rej_inl += (unsigned long long)r.tested_inl; rej_pts += (unsigned long long)r.tested_pts; }
-                        if (!r.good && hs.iters >= 20) { hs.iters++; continue; }       // ransac.cpp:77-85
+                        if (!r.good && hs.iters >= before_sprt) { hs.iters++; continue; }       // ransac.cpp:77-85
                         inl = r.full_inl; score = (float)inl;                           // sprt.hpp:240-241
                     } else {
                         inl = h_scores[q].x; memcpy(&score, &h_scores[q].y, 4);
@@ -1382,6 +1434,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         r.inliers = hs.best_cnt; r.score = hs.best_sum; r.iterations = hs.iters; r.samples_drawn = hs.samples_drawn;
         r.best_hyp = hs.best_hyp; r.best_model_idx = hs.best_midx; r.rounds = hs.rounds; r.evals = hs.evals; r.useful_evals = hs.useful_evals;
         if (cfg->lo) { r.lo_inner_iters = lo.inner_done; r.lo_iterative_iters = lo.iterative_done; }
+        r.msac = is_sprt ? nanf("") : usac_msac_cost(pd.n, r.inliers, r.score, cfg->threshold);
     }
     return USAC_OK;
 }
@@ -1424,9 +1477,12 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     const int nranks = std::max(cfg->nranks, 1), rank = cfg->rank;
     if (rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "fit: rank out of range");
     if (nranks > 1 && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_nccl_init or usac_gpu_set_allgather");
+    if (const char* why = check_sampler_cfg(cfg->sampler)) return fail(c, USAC_ERR_ARG, why);
     if (cfg->sampler.rng == USAC_RNG_TABLE && (!cfg->sample_table || cfg->sample_table_rows == 0)) return fail(c, USAC_ERR_ARG, "fit: empty sample table");
     if (cfg->lo != 0 && cfg->lo != 1 && cfg->lo != 2) return fail(c, USAC_ERR_ARG, "fit: lo must be 0 (none), 1 (InItLORsc) or 2 (InItFLORsc); GC / IRLS are not built");
     if (cfg->lo && c->est == USAC_EST_LINE2D) return fail(c, USAC_ERR_ARG, "fit: local optimisation of line models is not built");
+    if (cfg->lo && cfg->lo_sample_size && (cfg->lo_sample_size < (unsigned)usac_sample_size(c->est) + 1 || cfg->lo_sample_size > 16))
+        return fail(c, USAC_ERR_ARG, "fit: lo_sample_size must lie in [sample size + 1, 16]");
     const bool host_replay = cfg->sprt || cfg->lo || cfg->sampler.sampler == USAC_SAMPLER_PROSAC;
     if (host_replay && nranks > 1) return fail(c, USAC_ERR_ARG, "fit: SPRT / PROSAC termination with hypothesis sharding is not supported");
     cudaSetDevice(c->device);
@@ -1613,6 +1669,7 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         r.inliers = s.best_cnt; r.score = s.best_sum; r.iterations = s.iters; r.samples_drawn = s.samples_drawn;
         r.best_hyp = s.best_hyp; r.best_model_idx = s.best_midx; r.rounds = s.rounds; r.evals = s.evals;
         r.useful_evals = s.useful_evals;
+        r.msac = usac_msac_cost(c->h_prob[p].n, r.inliers, r.score, cfg->threshold);
     }
     if (trace)
         fprintf(stderr, "usac_gpu_fit trace: %d problems, %d rounds: setup %.0f us, enqueue %.0f us, wait %.0f us, total %.0f us (GPU events: %.0f us, scoring %.0f us)\n",

@@ -89,6 +89,46 @@ def test_emulated_ranks_match_single_gpu_and_oracle(cfg, world):
     assert sum(r["useful_evals"] for r in results) == ref["evals"]           # the shards partition the sequential work
 
 
+def test_config5_emulated_ranks_full_size():
+    """BASELINE config 5 at its stated size (1M correspondences, NAPSAC grid): the hypotheses of every round split over 4
+    emulated ranks give the single-GPU result on every rank (which test_gpu_parity checks against the oracle)."""
+    from ransac_b200 import GpuContext
+    from ransac_b200.api import NEIGH_GRID, SAMPLER_NAPSAC
+    pts = gen.make(5)[0]
+    world = 4
+    kw = dict(sampler=SAMPLER_NAPSAC, neighbors=NEIGH_GRID, seed=1, round_size=1024)
+    one = GpuContext(0)
+    one.set_points(O.EST_HOMOGRAPHY, pts)
+    one.set_neighbors_grid(0, 50)
+    single = one.fit(2.0, 0.95, 4096, **kw)[0]
+    one.close()
+    ex = HostExchange(world)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            ctx = GpuContext(0)
+            ctx.set_points(O.EST_HOMOGRAPHY, pts)
+            ctx.set_neighbors_grid(0, 50)
+            ctx._check(ctx.L.usac_gpu_set_allgather(ctx.h, ex.fns[rank], None), "set_allgather")
+            results[rank] = ctx.fit(2.0, 0.95, 4096, rank=rank, nranks=world, **kw)[0]
+            ctx.close()
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+            ex.barrier.abort()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    for r in results:
+        for k in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+            assert r[k] == single[k], (k, r[k], single[k])
+        assert np.array_equal(r["model"].view(np.uint32), single["model"].view(np.uint32))
+    assert sum(r["useful_evals"] for r in results) == single["useful_evals"]
+
+
 def test_nccl_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
