@@ -15,8 +15,9 @@ all run to their own adaptive termination through usac_gpu_fit (sample -> solve 
           over --pipe parts, each double-buffered (two contexts), so that uploads overlap the fits of other parts/steps.
   roofline : the scoring kernel, FP32 bound (BASELINE.json: "the roofline is FP32 FMA throughput plus HBM point
           streaming"); algorithmic 42 flop per homography evaluation.
-  cpu_baseline / --impl reference : the CPU oracle (a restatement - the reference needs OpenCV-contrib/Eigen/nanoflann
-          and cannot be compiled here) on the box's host cores, on a bounded sample of the same problems.
+  cpu_baseline / --impl reference : the reference's own Ransac::run compiled from its sources (oracle/_ref, built in the
+          development container by oracle/Makefile.ref and shipped prebuilt; kind "reference") on the box's host cores, on a
+          bounded sample of the same problems; the oracle restatement (kind "port") when that library is absent.
 
 Multi-GPU: one process per GPU (torchrun); independent image pairs shard across ranks with no data-path collective
 (weak scaling: every rank owns --problems pairs). `--workload c5` instead shards the HYPOTHESES of one 1M-point fit
@@ -96,16 +97,37 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_fits(problems, seeds, threads):
-    """-> (evals, seconds, iterations list) of oracle fits (reference-sequential semantics) over `problems`."""
+def ref_available():
+    """oracle/_ref/libusac_ref.so: the reference's own usac/ sources compiled in the development container (oracle/Makefile.ref);
+    it travels to the GPU box as a prebuilt file. Without it the CPU arm falls back to the oracle port."""
+    try:
+        from oracle import ref as R
+        R.lib()
+        return True
+    except Exception:   # noqa: BLE001
+        return False
+
+
+def cpu_fits(problems, seeds, threads, impl="port"):
+    """-> (evals, seconds, results) of CPU fits over `problems`, independent fits spread over `threads` host threads.
+    impl "reference": Ransac::Ransac + Ransac::run of the compiled reference (evals = main-loop iterations x N, the scoring work
+    of ransac.cpp:97; the refit loop's <= 8 x N evaluations are not counted); "port": the oracle restatement."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle as O
     O.lib()
+    if impl == "reference":
+        from oracle import ref as R
 
-    def one(args):
-        p, s = args
-        return O.ransac(p, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=s)
+        def one(args):
+            p, s = args
+            r = R.ransac_run(O.EST_HOMOGRAPHY, p, THR, conf=CONF, max_it=MAX_IT, seed=s)
+            r["evals"] = int(r["iterations"]) * len(p)
+            return r
+    else:
+        def one(args):
+            p, s = args
+            return O.ransac(p, O.EST_HOMOGRAPHY, rng=O.RNG_PHILOX, threshold=THR, confidence=CONF, max_iterations=MAX_IT, seed=s)
     t0 = time.perf_counter()
     if threads == 1:
         rs = [one(a) for a in zip(problems, seeds)]
@@ -116,20 +138,30 @@ def cpu_fits(problems, seeds, threads):
     return sum(r["evals"] for r in rs), dt, rs
 
 
+REF_SAMPLE_NOTE = ("oracle/_ref/libusac_ref.so = the reference's own usac/ sources (Ransac::run, HomographyEstimator::GetError, DLT4p ...) compiled "
+                   "-O2 -ffp-contract=off with stand-in OpenCV headers; its 4-point solver takes the wrong row of a thin SVD (dlt.cpp:43-48), so its "
+                   "termination criterion never fires and every fit runs max_iter iterations - the metric is evaluations per second either way")
+
+
 def cpu_baseline(budget_s=12.0):
     """Bounded sample: as many C2 problems as fit ~budget_s of wall time on all host cores (the reference itself is
     single-threaded; the per-core figure is reported next to it)."""
     cores = os.cpu_count() or 1
+    impl = "reference" if ref_available() else "port"
     probe = make_problems(2, 5000)
-    e1, t1, _ = cpu_fits(probe, [1, 1], 1)
+    e1, t1, _ = cpu_fits(probe, [1, 1], 1, impl)
     per_fit = t1 / 2
     count = int(max(cores, min(4096, budget_s / per_fit * cores * 0.8)))
     problems = make_problems(count, 1000)
-    evals, dt, rs = cpu_fits(problems, [1] * count, cores)
-    return {"value": evals / dt, "unit": "evals/s", "cores": cores, "kind": "port",
-            "sample": f"{count} of the C2 image pairs (first seeds of the GPU batch), oracle/libusac_oracle.so -O2 -ffp-contract=off, "
-                      f"{cores} threads over independent fits; single thread: {e1 / t1:.3e} evals/s",
-            "ms_per_fit": dt / count * 1e3, "single_thread_value": e1 / t1}
+    evals, dt, rs = cpu_fits(problems, [1] * count, cores, impl)
+    out = {"value": evals / dt, "unit": "evals/s", "cores": cores, "kind": impl,
+           "sample": f"{count} of the C2 image pairs (first seeds of the GPU batch), {cores} threads over independent fits; single thread: "
+                     f"{e1 / t1:.3e} evals/s. " + (REF_SAMPLE_NOTE if impl == "reference" else "oracle/libusac_oracle.so (restatement) -O2 -ffp-contract=off"),
+           "ms_per_fit": dt / count * 1e3, "single_thread_value": e1 / t1}
+    if impl == "reference":     # the oracle port beside it, for information (it terminates adaptively like the GPU path)
+        ep, tp, _ = cpu_fits(problems[:max(cores, 64)], [1] * max(cores, 64), cores, "port")
+        out["oracle_port_value"] = ep / tp
+    return out
 
 
 def run_reference_arm(args):
@@ -137,25 +169,26 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores, args.ref_problems)
+    impl = "reference" if ref_available() else "port"
+    per_step = max(cores, args.ref_problems if impl == "port" else min(args.ref_problems, 2 * cores))
     problems = make_problems(per_step, 1000)
     seeds = [1] * per_step
-    for _ in range(args.warmup):
-        cpu_fits(problems[:cores], seeds[:cores], cores)
+    for _ in range(args.warmup if impl == "port" else min(args.warmup, 1)):
+        cpu_fits(problems[:cores], seeds[:cores], cores, impl)
     evals = 0
     t = 0.0
     for _ in range(args.steps):
-        e, dt, _ = cpu_fits(problems, seeds, cores)
+        e, dt, _ = cpu_fits(problems, seeds, cores, impl)
         evals += e
         t += dt
     v = evals / t
+    sample = (f"{per_step} C2 image pairs per step, all host threads over independent fits; " +
+              (REF_SAMPLE_NOTE if impl == "reference" else "CPU oracle (restated reference), oracle/libusac_oracle.so"))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(per_step), "problems_per_step": per_step, "ms_per_fit": t / args.steps / per_step * 1e3},
-            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} C2 image pairs per step, CPU oracle (restated reference; the reference needs "
-                                       "OpenCV-contrib/Eigen/nanoflann and does not compile here), all host threads over independent fits"},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": impl, "sample": sample},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -96,6 +96,9 @@ def lib():
         L.orc_refit.restype = C.c_int
         L.orc_sprt_pool.argtypes = [C.c_uint64, C.c_int, ip]
         L.orc_sprt_pool.restype = None
+        up = C.POINTER(C.c_uint)
+        L.orc_sprt_sequence.argtypes = [C.c_int, fp, C.c_int, C.c_float, C.c_uint64, C.c_uint, fp, C.c_int, ip, ip, ip, up, up, dp, ip, ip]
+        L.orc_prosac_termination_sequence.argtypes = [C.c_int, fp, C.c_int, C.c_float, C.c_float, C.c_uint, fp, C.c_int, up, up, up, up]
         _lib = L
     return _lib
 

@@ -1,0 +1,3 @@
+// stand-in for <opencv2/core.hpp>: see cvshim.hpp (test infrastructure, oracle/_ref build only)
+#pragma once
+#include "../cvshim.hpp"

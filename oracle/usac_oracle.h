@@ -127,6 +127,12 @@ void orc_lo_counters(orc_lo*, unsigned* inner, unsigned* iterative, unsigned lon
 void orc_lo_get_model_score(orc_lo*, float* best_model, int* best_inl_io, float* best_sum_io);
 /* the SPRT pool permutation orc_ransac uses for this seed (sprt.hpp:93-107) */
 void orc_sprt_pool(uint64_t seed, int n, int* pool_out);
+/* sequences for the cross-check against the compiled reference (oracle/_ref; see usac_oracle_ransac.cpp) */
+int orc_sprt_sequence(int est, const float* points, int n, float thr, uint64_t seed, unsigned max_it, const float* models, int M,
+                      const int* hyp, int* good_out, int* inl_out, unsigned* pool_idx_after, unsigned* bound_after,
+                      double* hist_out, int* nhist, int* pool_out);
+int orc_prosac_termination_sequence(int est, const float* points, int n, float thr, float conf, unsigned max_it, const float* models, int M,
+                                    const unsigned* hyp_count, const unsigned* largest, unsigned* max_samples_out, unsigned* term_len_out);
 
 #ifdef __cplusplus
 }

@@ -445,3 +445,55 @@ extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc
     orc_sampler_free(sampler);
     return best_inl > 0 ? 0 : 1;   /* ransac.cpp:143-147: the reference exits(111) when nothing was found */
 }
+
+/* ------------------------------------------------------------------------------------------------------
+ * Sequences for the cross-check against the compiled reference (oracle/_ref, tests/test_ref_build.py): the same inputs go
+ * through the reference's SPRT / ProsacTerminationCriteria classes (ref_driver.cpp) and through the restatements above.
+ * ------------------------------------------------------------------------------------------------------ */
+extern "C" int orc_sprt_sequence(int est, const float* points, int n, float thr, uint64_t seed, unsigned max_it, const float* models, int M,
+                                 const int* hyp, int* good_out, int* inl_out, unsigned* pool_idx_after, unsigned* bound_after,
+                                 double* hist_out, int* nhist, int* pool_out) {
+    const int m = est == ORC_EST_LINE2D ? 2 : est == ORC_EST_HOMOGRAPHY ? 4 : est == ORC_EST_FUNDAMENTAL ? 7 : 5;
+    orc_sampler* sampler = orc_sampler_new(ORC_SAMPLER_UNIFORM, ORC_RNG_GLIBC, n, m, seed);
+    Sprt sprt;
+    sprt.init(est, thr, (unsigned)n, (unsigned)m, max_it, [&]() { return orc_sampler_glibc_next(sampler); });
+    for (int i = 0; i < n; i++) pool_out[i] = (int)sprt.pool[i];
+    ErrFn f;
+    int best = 0;
+    unsigned long long evals = 0;
+    for (int q = 0; q < M; q++) {
+        f.set(est, models + 9 * q);
+        int inl = -1;
+        float score = -1;
+        const bool good = sprt.verify(f, points, hyp[q], (unsigned)best, inl, score, evals);
+        good_out[q] = good;
+        inl_out[q] = (good || hyp[q] < sprt.max_hyp_before) ? inl : -1;
+        bound_after[q] = 0xffffffffu;
+        if (inl_out[q] > best) { best = inl_out[q]; bound_after[q] = sprt.getUpperBoundIterations(best); }
+        pool_idx_after[q] = sprt.pool_idx;
+    }
+    *nhist = (int)sprt.hist.size();
+    for (int i = 0; i < *nhist && i < 4096; i++) {
+        hist_out[4 * i] = sprt.hist[i].epsilon; hist_out[4 * i + 1] = sprt.hist[i].delta; hist_out[4 * i + 2] = sprt.hist[i].A; hist_out[4 * i + 3] = sprt.hist[i].k;
+    }
+    orc_sampler_free(sampler);
+    return 0;
+}
+
+extern "C" int orc_prosac_termination_sequence(int est, const float* points, int n, float thr, float conf, unsigned max_it, const float* models, int M,
+                                               const unsigned* hyp_count, const unsigned* largest, unsigned* max_samples_out, unsigned* term_len_out) {
+    const int m = est == ORC_EST_LINE2D ? 2 : est == ORC_EST_HOMOGRAPHY ? 4 : est == ORC_EST_FUNDAMENTAL ? 7 : 5;
+    orc_sampler* sampler = orc_sampler_new(ORC_SAMPLER_PROSAC, ORC_RNG_PHILOX, n, m, 1);
+    ProsacTermination pterm;
+    pterm.init(orc_sampler_growth_function(sampler), (unsigned)n, (unsigned)m, thr, conf, max_it);
+    ErrFn f;
+    std::vector<unsigned char> mask(n);
+    for (int q = 0; q < M; q++) {
+        f.set(est, models + 9 * q);
+        for (int i = 0; i < n; i++) mask[i] = f(points, (unsigned)i) < thr;
+        max_samples_out[q] = pterm.update(hyp_count[q], mask, largest[q]);
+        term_len_out[q] = pterm.termination_length;
+    }
+    orc_sampler_free(sampler);
+    return 0;
+}

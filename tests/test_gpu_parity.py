@@ -696,7 +696,11 @@ def test_config5_full_size_napsac_grid(ctx):
                    threshold=2.0, confidence=0.95, max_iterations=2560, seed=1)
     assert_fit_equal(r, ref, O.EST_HOMOGRAPHY)
     assert r["useful_evals"] == ref["evals"]
-    assert r["inliers"] > 0.5 * mask.sum()
+    # NAPSAC draws all four points from one 50-px cell, so a minimal-sample homography only explains the inliers near that
+    # cell (which is why the reference pairs it with LO): the support is a fraction of the 100 000 true inliers, but it is
+    # made of true inliers
+    ids = ctx.get_inliers(r["model"], 2.0)
+    assert len(ids) == r["inliers"] > 0.05 * mask.sum() and mask[ids].mean() > 0.9
     full = ctx.fit(2.0, 0.95, 10000, round_size=2048, **kw)[0]        # the whole 10 000-sample fit: at least as good, same prefix
     assert full["inliers"] >= r["inliers"] and full["iterations"] == 10000
     assert abs(full["msac"] - (full["score"] + (len(pts) - full["inliers"]) * 2.0)) <= 1e-6 * full["msac"]
