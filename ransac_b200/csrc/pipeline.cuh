@@ -25,6 +25,8 @@ struct RoundArgs {
     int* offsets;                // [K]  exclusive prefix sum of nmodels
     float* recs;                 // [K*S][USAC_REC_STRIDE]
     int* mvalid;                 // [1]
+    uint2* items;                // compact work-item list of the scoring kernel: (slot, chunk << 16 | model group), only groups that hold models
+    unsigned* item_count;        // [0] = number of items (zeroed by the host before the round), [1] = the scoring kernel's draw counter
     int* part_cnt; float* part_sum; int nchunks;   // [nchunks][K*S]
     uint2* sample_scores;        // [K] per-sample best (cnt | midx<<30, sum bits); with nranks>1: [nranks][ceil(K/nranks)]
     // fit parameters
@@ -361,6 +363,17 @@ __global__ void __launch_bounds__(256) prepare_kernel(const RoundArgs a) {
         off += k;
     }
     if (threadIdx.x == 0) a.mvalid[slot] = total;
+    // Work items of the scoring kernel for this slot: (point chunk, group of 32 models) for the groups that exist. Fundamental
+    // matrices pass the oriented-epipolar filter for a fraction of the samples only, the five-point solver returns 0 or 1 model:
+    // a grid over K x S model slots would be mostly empty groups.
+    if (a.items) {
+        __shared__ unsigned s_base;
+        const unsigned ngroups = (unsigned)(total + 31) / 32u, count = ngroups * (unsigned)a.nchunks;
+        if (threadIdx.x == 0) s_base = atomicAdd(a.item_count, count);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < count; i += blockDim.x)          // model group fastest: neighbouring warps share the point tiles in L2
+            a.items[s_base + i] = make_uint2((unsigned)slot, ((i / ngroups) << 16) | (i % ngroups));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
 template <int EST> struct FastModel;
 
 template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
+    static constexpr bool WEIGHTED = false;
     // rows 0,1 negated so that dx = x2 - nx/nz is a single FFMA2; scalars are broadcast by the FFMA2 operand form
     float a11, a12, a13, a21, a22, a23, h31, h32, h33;
     float b11, b12, b13, b21, b22, b23, g31, g32, g33;
@@ -126,39 +127,105 @@ template <> struct FastModel<USAC_EST_HOMOGRAPHY> {
         if (oy) { t.y = 1.f; s.y = 0.f; }
         w = t;
     }
+    // score_sq.cuh: true = PROVEN outlier (the forward distance alone exceeds 2 thr by more than its guard band)
+    // The point is a PROVEN outlier iff the returned value is > 0 (a NaN proves nothing): (d1 nz)^2 - (2 thr |nz| + k1)^2.
+    __device__ __forceinline__ float2 reject(const float4 A, const float4 B) const {
+        P1 st;
+        phase1(A, B, st);
+        const float2 az = make_float2(fabsf(st.nz.x), fabsf(st.nz.y));
+        const float2 c = __ffma2_rn(dup(T2p), az, dup(k1));
+        return __ffma2_rn(make_float2(-c.x, -c.y), c, st.sa);
+    }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return 0.5f * (sum_em + (float)cnt * (2.f * thr)); }
     static __device__ __forceinline__ float strict_to_em(float err, float thr) { return 2.f * err - 2.f * thr; }
 };
 
 template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
+    // Two phases, like the homography evaluator, but the split is different: the squared Sampson error n^2/den needs no division
+    // for the DECISION (n^2 - thr*den < 0), only for the error sum of the inliers. phase1 computes n^2 and den (18 packed
+    // FMA-pipe instructions per pair of points, no MUFU); `sure` proves the outlier with the guard band folded into the
+    // constants: n^2 - (thr + b1)*den > b0 (one more FFMA2, chained compare). Only the pairs on which some model of the warp
+    // has a point that is NOT a proven outlier - an inlier or a point inside the band - run phase2: the exact decision value,
+    // the band, 1/den for the sum, counting and accumulation.
+#ifdef USAC_F_SINGLE_PHASE   /* tuning experiment (tools/): the round-1 single-phase form */
     static constexpr bool TWO_PHASE = false;
-    float f11, f12, f13, f21, f22, f23, f31, f32, f33, negthr, b1, b0;
+#else
+    static constexpr bool TWO_PHASE = true;
+#endif
+    static constexpr bool WEIGHTED = true;                                 // em = min(t, 0) * w
+    float f11, f12, f13, f21, f22, f23, f31, f32, f33, negthr, b1, b0, negthrP, b0P;
     __device__ __forceinline__ void load(const float* r) {
         f11 = r[0]; f12 = r[1]; f13 = r[2]; f21 = r[3]; f22 = r[4]; f23 = r[5]; f31 = r[6]; f32 = r[7]; f33 = r[8];
         negthr = -r[REC_THR]; b1 = r[REC_BAND]; b0 = r[REC_BAND + 1];
+        // sure-outlier test n^2 - thrP*den > b0P: both constants rounded UP by 2^-18 relative, far more than the roundings of
+        // the folded form (2^-23 each), so every point it rejects also satisfies t > s of the two-sided band test
+        negthrP = -(r[REC_THR] + b1) * 1.0000039f;
+        b0P = b0 * 1.0000039f + 1e-37f;
     }
-    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+    struct P1 { float2 n2, den; };
+    __device__ __forceinline__ void phase1(const float4 A, const float4 B, P1& s) const {
         const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
         const float2 a = __ffma2_rn(dup(f11), X1, __ffma2_rn(dup(f12), Y1, dup(f13)));
         const float2 b = __ffma2_rn(dup(f21), X1, __ffma2_rn(dup(f22), Y1, dup(f23)));
         const float2 c = __ffma2_rn(dup(f11), X2, __ffma2_rn(dup(f21), Y2, dup(f31)));
         const float2 d = __ffma2_rn(dup(f12), X2, __ffma2_rn(dup(f22), Y2, dup(f32)));
         const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, __ffma2_rn(dup(f31), X1, __ffma2_rn(dup(f32), Y1, dup(f33)))));
-        const float2 n2 = __fmul2_rn(n, n);
+        s.n2 = __fmul2_rn(n, n);
+        s.den = __ffma2_rn(d, d, __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a))));
+    }
+    __device__ __forceinline__ void sure(const P1& s, bool& ox, bool& oy) const {       // false for NaN
+        const float2 u = __ffma2_rn(dup(negthrP), s.den, s.n2);
+        ox = u.x > b0P; oy = u.y > b0P;
+    }
+    __device__ __forceinline__ void phase2(const float4, const float4, const P1& s, float2& t, float2& band) const {
+        t = __ffma2_rn(dup(negthr), s.den, s.n2);     // n^2 - thr*den  (< 0 <=> n^2/den < thr, no division)
+        band = __ffma2_rn(dup(b1), s.den, dup(b0));
+    }
+    __device__ __forceinline__ float2 weight(const P1& s) const { return make_float2(fast_rcp(s.den.x), fast_rcp(s.den.y)); }
+    // score_sq.cuh: proven outlier iff the returned value is > 0: (n^2 - b0P) - thrP den, 18 packed instructions
+    __device__ __forceinline__ float2 reject(const float4 A, const float4 B) const {
+        const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
+        const float2 a = __ffma2_rn(dup(f11), X1, __ffma2_rn(dup(f12), Y1, dup(f13)));
+        const float2 b = __ffma2_rn(dup(f21), X1, __ffma2_rn(dup(f22), Y1, dup(f23)));
+        const float2 c = __ffma2_rn(dup(f11), X2, __ffma2_rn(dup(f21), Y2, dup(f31)));
+        const float2 d = __ffma2_rn(dup(f12), X2, __ffma2_rn(dup(f22), Y2, dup(f32)));
+        const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, __ffma2_rn(dup(f31), X1, __ffma2_rn(dup(f32), Y1, dup(f33)))));
         const float2 den = __ffma2_rn(d, d, __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a))));
-        t = __ffma2_rn(dup(negthr), den, n2);     // n^2 - thr*den  (< 0 <=> n^2/den < thr, no division)
-        s = __ffma2_rn(dup(b1), den, dup(b0));
-        w = make_float2(fast_rcp(den.x), fast_rcp(den.y));                 // only the error sum needs the quotient
+        return __ffma2_rn(dup(negthrP), den, __ffma2_rn(n, n, dup(-b0P)));
+    }
+    __device__ __forceinline__ void eval(const float4 A, const float4 B, float2& t, float2& s, float2& w) const {
+        P1 st;
+        phase1(A, B, st);
+        phase2(A, B, st, t, s);
+        w = weight(st);                                                    // only the error sum needs the quotient
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return sum_em + (float)cnt * thr; }
     static __device__ __forceinline__ float strict_to_em(float err, float thr) { return err - thr; }
 };
 
 template <> struct FastModel<USAC_EST_ESSENTIAL> {
-    float e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0;
+    static constexpr bool WEIGHTED = false;
+    float e11, e12, e13, e21, e22, e23, e31, e32, e33, negT, ka, kb, k0, negka, C2;
     __device__ __forceinline__ void load(const float* r) {
         e11 = r[0]; e12 = r[1]; e13 = r[2]; e21 = r[3]; e22 = r[4]; e23 = r[5]; e31 = r[6]; e32 = r[7]; e33 = r[8];
         negT = -2.f * r[REC_THR]; ka = r[REC_BAND]; kb = r[REC_BAND + 1]; k0 = r[REC_BAND + 2];
+        negka = -ka;
+        const float c = (2.f * r[REC_THR] + k0) * 1.0000039f;             // rounded up by 2^-18: covers the roundings of the squared form
+        C2 = c * c * 1.0000039f;
+    }
+    // score_sq.cuh: the one-sided test of phase1/sure without the rsqrt. da = |a1| / L with L = |l12|; da alone beyond
+    // 2 thr + (ka / L + k0) proves the outlier:  |a1| / L - 2 thr > ka / L + k0  <=>  v := |a1| - ka > (2 thr + k0) L
+    // <=>  v |v| > (2 thr + k0)^2 L^2  (the left side keeps the sign of v, the right side is >= 0). 13 packed instructions, no MUFU.
+    __device__ __forceinline__ float2 reject(const float4 A, const float4 B) const {
+        const float2 X1 = make_float2(A.x, A.y), Y1 = make_float2(A.z, A.w), X2 = make_float2(B.x, B.y), Y2 = make_float2(B.z, B.w);
+        const float2 l1 = __ffma2_rn(dup(e11), X2, __ffma2_rn(dup(e21), Y2, dup(e31)));
+        const float2 l2 = __ffma2_rn(dup(e12), X2, __ffma2_rn(dup(e22), Y2, dup(e32)));
+        const float2 l3 = __ffma2_rn(dup(e13), X2, __ffma2_rn(dup(e23), Y2, dup(e33)));
+        const float2 a1 = __ffma2_rn(l1, X1, __ffma2_rn(l2, Y1, l3));
+        const float2 a2 = __ffma2_rn(l2, l2, __fmul2_rn(l1, l1));
+        const float2 v = __fadd2_rn(make_float2(fabsf(a1.x), fabsf(a1.y)), dup(negka));
+        const float2 m = __fmul2_rn(dup(C2), a2);
+        return __ffma2_rn(v, make_float2(fabsf(v.x), fabsf(v.y)), make_float2(-m.x, -m.y));   // > 0: proven outlier
     }
     // Two phases, as for the homography: err = (da + db)/2 with da = |p1.l|/|l12| (l = E^T p2) and db >= 0, so da alone
     // beyond 2*thr + (its band + the band of the final sum) proves the outlier; phase2 adds the other epipolar distance.
@@ -211,6 +278,7 @@ template <> struct FastModel<USAC_EST_ESSENTIAL> {
 
 template <> struct FastModel<USAC_EST_LINE2D> {
     static constexpr bool TWO_PHASE = false;
+    static constexpr bool WEIGHTED = false;
     float a, b, c, negthr, band;
     __device__ __forceinline__ void load(const float* r) { a = r[0]; b = r[1]; c = r[2]; negthr = -r[REC_THR]; band = r[REC_BAND]; }
     // line pairs are [xa xb ya yb]: one float4 per pair (B unused)
@@ -220,6 +288,11 @@ template <> struct FastModel<USAC_EST_LINE2D> {
         t = make_float2(fabsf(v.x) + negthr, fabsf(v.y) + negthr);
         s = dup(band);
         w = t;
+    }
+    __device__ __forceinline__ float2 reject(const float4 A, const float4) const {   // score_sq.cuh: > 0 = proven outlier
+        const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w);
+        const float2 v = __ffma2_rn(dup(a), X, __ffma2_rn(dup(b), Y, dup(c)));
+        return make_float2(fabsf(v.x) + (negthr - band), fabsf(v.y) + (negthr - band));
     }
     static __device__ __forceinline__ float finish(float sum_em, int cnt, float thr) { return sum_em + (float)cnt * thr; }
     static __device__ __forceinline__ float strict_to_em(float err, float thr) { return err - thr; }
@@ -239,7 +312,23 @@ struct ScoreArgs {
     float* part_sum;
     unsigned* work;              // global work-item counter, never reset: this launch's items are work - work_base
     unsigned work_base;
+    const uint2* items;          // optional compact item list written by prepare_kernel (slot, chunk << 16 | model group); NULL: dense grid
+    const unsigned* item_count;  // number of entries of `items` (device side: the host does not know how many models a round produced)
 };
+
+// work item -> (slot, chunk, model group); false when the item is past the end
+__device__ __forceinline__ bool score_item(const ScoreArgs& a, unsigned item, unsigned total, int mgroups, int& slot, int& chunk, int& mgroup) {
+    if (item >= total) return false;
+    if (a.items) {
+        const uint2 it = a.items[item];
+        slot = (int)it.x; chunk = (int)(it.y >> 16); mgroup = (int)(it.y & 0xffffu);
+    } else {
+        mgroup = (int)(item % (unsigned)mgroups);
+        const unsigned rest = item / (unsigned)mgroups;
+        chunk = (int)(rest % (unsigned)a.nchunks); slot = (int)(rest / (unsigned)a.nchunks);
+    }
+    return true;
+}
 
 // Slow path of one lane: the reference's exact arithmetic for point `idx` of the problem. Returns the lane's `em`
 // contribution: negative (its sign bit is the inlier flag) for an inlier, +0 otherwise. Pure, so the hot loop keeps
@@ -285,17 +374,15 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
     __syncwarp();
 
     const int mgroups = a.mblocks * NWARPS;
-    const unsigned total = (unsigned)a.slots * (unsigned)a.nchunks * (unsigned)mgroups;
+    const unsigned total = a.items ? *a.item_count : (unsigned)a.slots * (unsigned)a.nchunks * (unsigned)mgroups;
     uint32_t g = 0;                                                  // tiles consumed so far by this warp (uniform)
 
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(a.work, 1u) - a.work_base;   // every warp overdraws exactly once (accounted by the host)
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total) break;
-        const int mgroup = (int)(item % (unsigned)mgroups);
-        const unsigned rest = item / (unsigned)mgroups;
-        const int chunk = (int)(rest % (unsigned)a.nchunks), slot = (int)(rest / (unsigned)a.nchunks);
+        int slot, chunk, mgroup;
+        if (!score_item(a, item, total, mgroups, slot, chunk, mgroup)) break;
         const int M = a.mvalid ? a.mvalid[slot] : a.M;
         if (mgroup * 32 >= M) continue;                              // uniform per warp
         const ProblemDesc pd = a.prob[a.active ? a.active[slot] : slot];
@@ -377,8 +464,9 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                                 load_pair(j + q, A, B);
                                 float2 t, sb;
                                 fm.phase2(A, B, st[q], t, sb);
-                                em[q] = make_float2(ox ? 0.f : fminf(t.x, 0.f), oy ? 0.f : fminf(t.y, 0.f));
                                 unsure = unsure || (!ox && !(fabsf(t.x) > sb.x)) || (!oy && !(fabsf(t.y) > sb.y));
+                                if constexpr (FastModel<EST>::WEIGHTED) t = __fmul2_rn(t, fm.weight(st[q]));   // weights are >= 0; inf/NaN * (t >= 0) is dropped by fminf
+                                em[q] = make_float2(ox ? 0.f : fminf(t.x, 0.f), oy ? 0.f : fminf(t.y, 0.f));
                             }
                         }
                     } else {
@@ -388,9 +476,9 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                             load_pair(j + q, A, B);
                             float2 t, sb, w;
                             fm.eval(A, B, t, sb, w);
-                            em[q] = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
-                            if (EST == USAC_EST_FUNDAMENTAL) em[q] = __fmul2_rn(em[q], w);
                             unsure = unsure || !(fabsf(t.x) > sb.x) || !(fabsf(t.y) > sb.y);   // also catches NaN
+                            if constexpr (FastModel<EST>::WEIGHTED) t = __fmul2_rn(t, w);
+                            em[q] = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
                         }
                     }
                     if (__any_sync(0xffffffffu, unsure)) break;
@@ -407,10 +495,11 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score
                     load_pair(j, A, B);
                     float2 t, sb, w;
                     fm.eval(A, B, t, sb, w);
+                    const bool ux = !(fabsf(t.x) > sb.x), uy = !(fabsf(t.y) > sb.y);
+                    if constexpr (FastModel<EST>::WEIGHTED) t = __fmul2_rn(t, w);
                     float2 e1 = make_float2(fminf(t.x, 0.f), fminf(t.y, 0.f));
-                    if (EST == USAC_EST_FUNDAMENTAL) e1 = __fmul2_rn(e1, w);
-                    if (!(fabsf(t.x) > sb.x)) e1.x = strict_em<EST>(rec, aos, idx0 + 2 * j, pd.n);
-                    if (!(fabsf(t.y) > sb.y)) e1.y = strict_em<EST>(rec, aos, idx0 + 2 * j + 1, pd.n);
+                    if (ux) e1.x = strict_em<EST>(rec, aos, idx0 + 2 * j, pd.n);
+                    if (uy) e1.y = strict_em<EST>(rec, aos, idx0 + 2 * j + 1, pd.n);
                     cnt += (__float_as_uint(e1.x) >> 31) + (__float_as_uint(e1.y) >> 31);
                     sum[0] = __fadd2_rn(sum[0], e1);
                 }

@@ -20,7 +20,7 @@
 #include "essential.cuh"
 #include "pipeline.cuh"
 #include "score.cuh"
-#include "score_queue.cuh"
+#include "score_sq.cuh"
 #include "sprt.cuh"
 #include "refit.cuh"
 #include "knn.cuh"
@@ -87,6 +87,8 @@ struct usac_gpu_ctx {
     DevBuf<int> d_grid_ints;                  // grid build scratch: 4n ints + 1
     DevBuf<unsigned char> d_grid_temp;        // CUB temporary storage
     DevBuf<unsigned> d_work;                  // work-item counter of the scoring kernel (monotone; see launch_score)
+    DevBuf<uint2> d_items;                    // compact work-item list of a round (prepare_kernel -> scoring kernel)
+    DevBuf<unsigned> d_item_count;            // [0] items in d_items, [1] draw counter of that launch; zeroed before every round
     unsigned work_next = 0;
     DevBuf<int> d_knn_cells;                  // kNN build scratch: cell_start of the search grid
     DevBuf<float4> d_knn_pts;                 // kNN build scratch: points in cell order
@@ -178,7 +180,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release(); c->d_items.release(); c->d_item_count.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -604,7 +606,7 @@ extern "C" int usac_gpu_set_sprt_pool(usac_gpu_ctx* c, int problem, const int* p
 // ------------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------------------------
-static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
+static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks, bool dense_survivors = false) {
     a.mblocks = mblocks; a.slots = slots;
     constexpr int warps_per_cta = USAC_SCORE_THREADS / 32;
     const long long items = (long long)slots * a.nchunks * mblocks * warps_per_cta;            // one item = 32 models x one point chunk
@@ -612,28 +614,37 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks) {
                                                         (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS);
     // the kernel's warps draw items from a counter that is never reset: this launch owns [work_base, work_base + items),
     // and every warp draws exactly one value beyond that before it exits
-    a.work = c->d_work.p; a.work_base = c->work_next;
-    c->work_next += (unsigned)items + grid * warps_per_cta;
+    unsigned grid_ctas = grid;
+    if (a.items) {      // the round's compact item list: its length is known on the device only; the list's own draw counter starts at 0
+        grid_ctas = (unsigned)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS;
+        a.work = c->d_item_count.p + 1; a.work_base = 0;
+    } else {
+        a.work = c->d_work.p; a.work_base = c->work_next;
+        c->work_next += (unsigned)items + grid * warps_per_cta;
+    }
     auto& ev = c->next_score_event();
     cudaEventRecord(ev.first, c->stream);
-    // USAC_GPU_SCORE_QUEUE=1: the experimental survivor-queue kernel (score_queue.cuh) for the two-phase evaluators
-    static const int use_queue = [] { const char* e = getenv("USAC_GPU_SCORE_QUEUE"); return e ? atoi(e) : 0; }();
-    if (use_queue > 0 && (c->est == USAC_EST_HOMOGRAPHY || c->est == USAC_EST_ESSENTIAL)) {
-        if (use_queue == 2) {                                        // out-of-line drain (not yet run on a GPU)
-            if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY, true><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
-            else score_queue_kernel<USAC_EST_ESSENTIAL, true><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
-        } else {
-            if (c->est == USAC_EST_HOMOGRAPHY) score_queue_kernel<USAC_EST_HOMOGRAPHY, false><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
-            else score_queue_kernel<USAC_EST_ESSENTIAL, false><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a);
+    // homography / fundamental / essential models of a RANSAC round (nearly every evaluation a provable outlier): the
+    // survivor-queue kernel (score_sq.cuh). The accumulate-in-the-loop kernel (score.cuh) keeps the cases where survivors are
+    // dense or the arithmetic is trivial: caller-supplied models of the Quality API (typically good models: a third of the
+    // points survive) and lines (3 flops per evaluation: the push would cost more than the arithmetic). Both are exact.
+    // USAC_GPU_SCORE_LEGACY=1 / =2 force the loop / queue kernel for every launch (A/B runs, tools/).
+    static const int legacy = [] { const char* e = getenv("USAC_GPU_SCORE_LEGACY"); return e ? atoi(e) : 0; }();
+    if (legacy == 1 || c->est == USAC_EST_LINE2D || (dense_survivors && legacy != 2)) {
+        switch (c->est) {
+            case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+            case USAC_EST_HOMOGRAPHY: score_kernel<USAC_EST_HOMOGRAPHY><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+            case USAC_EST_FUNDAMENTAL: score_kernel<USAC_EST_FUNDAMENTAL><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+            default: score_kernel<USAC_EST_ESSENTIAL><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
         }
-    } else
-    switch (c->est) {
-        case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
-        case USAC_EST_HOMOGRAPHY: score_kernel<USAC_EST_HOMOGRAPHY><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
-        case USAC_EST_FUNDAMENTAL: score_kernel<USAC_EST_FUNDAMENTAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
-        default: score_kernel<USAC_EST_ESSENTIAL><<<grid, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+    } else {
+        switch (c->est) {
+            case USAC_EST_HOMOGRAPHY: score_sq_kernel<USAC_EST_HOMOGRAPHY><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+            case USAC_EST_FUNDAMENTAL: score_sq_kernel<USAC_EST_FUNDAMENTAL><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+            default: score_sq_kernel<USAC_EST_ESSENTIAL><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
+        }
     }
-    if (cudaPeekAtLastError() != cudaSuccess) c->work_next = a.work_base;   // not launched: the counter did not move (callers report the error)
+    if (!a.items && cudaPeekAtLastError() != cudaSuccess) c->work_next = a.work_base;   // not launched: the counter did not move (callers report the error)
     cudaEventRecord(ev.second, c->stream);
     c->last_launches++;
     c->last_score_launches++;
@@ -647,7 +658,7 @@ static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_p
     static const int per_warp = [] { const char* e = getenv("USAC_GPU_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
     const long long warps = (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS * (USAC_SCORE_THREADS / 32);
     const long long base = (long long)slots * mblocks * (USAC_SCORE_THREADS / 32);
-    const int max_chunks = std::max(1, max_pairs / (2 * USAC_TILE_PAIRS));
+    const int max_chunks = std::min(65535, std::max(1, max_pairs / (2 * USAC_TILE_PAIRS)));
     int nc = (int)std::min<long long>((per_warp * warps + base - 1) / base, max_chunks);
     nc = std::max(nc, 1);
     int cp = (max_pairs + nc - 1) / nc;
@@ -716,10 +727,10 @@ extern "C" int usac_gpu_score(usac_gpu_ctx* c, int problem, const float* models,
     CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     prepare_models_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(c->est, c->d_q_models.p, M, w, threshold, c->d_prob.p, problem, c->d_q_recs.p);
     c->last_launches++;
-    ScoreArgs a;
+    ScoreArgs a{};
     a.pairs = c->d_pairs.p; a.aos = c->d_aos.p; a.prob = c->d_prob.p; a.active = c->d_active.p; a.recs = c->d_q_recs.p; a.mvalid = nullptr;
     a.M = M; a.mstride = M; a.chunk_pairs = chunk_pairs; a.nchunks = nchunks; a.part_cnt = c->d_part_cnt.p; a.part_sum = c->d_part_sum.p;
-    launch_score(c, a, 1, mblocks);
+    launch_score(c, a, 1, mblocks, /*dense_survivors=*/true);
     final_reduce_kernel<<<(M + 31) / 32, 256, 0, c->stream>>>(c->d_part_cnt.p, c->d_part_sum.p, M, M, nchunks, c->d_q_cnt.p, c->d_q_sum.p);
     c->last_launches++;
     if (inliers_out) CUDA_TRY(c, cudaMemcpyAsync(inliers_out, c->d_q_cnt.p, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream));
@@ -926,6 +937,8 @@ static int ensure_round_buffers(usac_gpu_ctx* c, int slots, int K, int nchunks, 
     CUDA_TRY(c, c->d_scores.ensure(std::max(sk, (size_t)slots * per_rank)));
     CUDA_TRY(c, c->d_scores_all.ensure((size_t)slots * per_rank * nranks));
     CUDA_TRY(c, c->d_sprt_res.ensure(sk * S));
+    CUDA_TRY(c, c->d_items.ensure((size_t)slots * nchunks * ((size_t)(K * S + 31) / 32)));
+    CUDA_TRY(c, c->d_item_count.ensure(2));
     return USAC_OK;
 }
 
@@ -1346,7 +1359,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 }
                 CUDA_TRY(c, cudaMemcpyAsync(h_res.data(), c->d_sprt_res.p, sizeof(SprtModelResult) * KS, cudaMemcpyDeviceToHost, c->stream));
             } else {
-                ScoreArgs sa;
+                ScoreArgs sa{};
                 sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
                 sa.mvalid = c->d_mvalid.p; sa.M = KS; sa.mstride = KS; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
                 sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
@@ -1597,7 +1610,11 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         for (int p : active) max_pairs = std::max(max_pairs, c->h_prob[p].n_pairs);
         const int mblocks = (K * S + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS;
         int chunk_pairs, nchunks;
-        plan_chunks(c, slots, std::max(1, mblocks / nranks), max_pairs, &chunk_pairs, &nchunks);
+        // chunks are planned for the model groups a round is EXPECTED to produce (the item list holds the real ones): one model
+        // per sample for lines and homographies; about every second sample for the five-point solver (0 or 1 model) and for
+        // the seven-point solver after the oriented-epipolar filter (0..3 models)
+        const int expect_models = (c->est == USAC_EST_FUNDAMENTAL || c->est == USAC_EST_ESSENTIAL) ? (K + 1) / 2 : K;
+        plan_chunks(c, slots, std::max(1, ((expect_models + USAC_SCORE_THREADS - 1) / USAC_SCORE_THREADS) / nranks), max_pairs, &chunk_pairs, &nchunks);
         rc = ensure_round_buffers(c, slots, K, nchunks, nranks);
         if (rc) return rc;
         RoundArgs a;
@@ -1607,6 +1624,8 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         a.table_rows = cfg->sample_table_rows; a.rank = rank; a.nranks = nranks; a.nchunks = nchunks;
         a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
         a.limit_remaining = 1;
+        a.items = c->d_items.p; a.item_count = c->d_item_count.p;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_item_count.p, 0, 2 * sizeof(unsigned), c->stream));
 
         launch_sampler(c, a, slots);
         switch (c->est) {
@@ -1618,10 +1637,11 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
         c->last_launches++;
         {
-            ScoreArgs sa;
+            ScoreArgs sa{};
             sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = act_cur; sa.recs = c->d_recs.p;
             sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
             sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
+            sa.items = c->d_items.p; sa.item_count = c->d_item_count.p;
             launch_score(c, sa, slots, mblocks);
             dim3 gr((K + 127) / 128, slots);
             if (nchunks > 8) reduce_chunks_kernel<<<dim3((K + 31) / 32, slots), 256, 0, c->stream>>>(a);
