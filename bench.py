@@ -385,8 +385,13 @@ def run_native(args):
     useful_all, useful_e2e_all, executed_all, launches_all = cnt.tolist()
 
     if rank == 0:
-        fp32_peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12       # TFLOP/s at the max SM clock
+        fp32_nominal = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12    # TFLOP/s at the max SM clock
         measured_ffma = ctx.measure_fp32_peak()
+        # MEASURED_PEAKS.json carries HBM and bf16 figures only: the FP32 denominator is MEASURED in this run (a register-resident
+        # FFMA loop on every SM, usac_gpu_measure_fp32_peak), the nominal 2 x 128 lanes x SMs x max clock is kept beside it
+        fp32_peak = measured_ffma if measured_ffma > 0 else fp32_nominal
+        peak_source = (f"measured in this run: register-resident FFMA loop, {measured_ffma:.1f} TFLOP/s (nominal 2*128 lanes*SMs*max SM clock = "
+                       f"{fp32_nominal:.1f}; MEASURED_PEAKS.json has no FP32 figure)")
         flops_launch = FLOPS_PER_EVAL["homography"] * executed / max(score_launches, 1)
         ach = flops_launch / (score_ms / max(score_launches, 1) * 1e-3) / 1e12
         peaks = {}
@@ -400,20 +405,22 @@ def run_native(args):
         pair_launches = sum(s[7] for s in stats)
         alg_bytes_launch = (16.0 * N_POINTS * pair_launches + 128.0 * executed / N_POINTS) / max(score_launches, 1)
         traffic, traffic_note = None, None
+        pipe = None
         try:   # DRAM bytes of one ncu --set full capture of this kernel (profiles/): a full-size launch, not this run's average
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            pipe = tj.get("fma_pipe_pct")
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_note = f"{tj['launch']}: {traffic / 1e6:.1f} MB DRAM vs {tj['algorithmic_bytes'] / 1e6:.1f} MB algorithmic ({tj['source']})"
         except Exception:   # noqa: BLE001
             pass
-        roofline = {"bound": "fp32", "kernel": "score_kernel<HOMOGRAPHY>", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+        roofline = {"bound": "fp32", "kernel": "score_sq_kernel<HOMOGRAPHY>", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": ach / fp32_peak, "traffic": traffic, "traffic_note": traffic_note,
-                    "peak_source": "2*128 lanes*SMs*max SM clock from the device (no FP32 figure in MEASURED_PEAKS.json); "
-                                   f"register-resident FFMA loop measured in this run: {measured_ffma:.1f} TFLOP/s",
+                    "fma_pipe_busy_pct_ncu": pipe,
+                    "peak_source": peak_source, "peak_nominal": fp32_nominal, "frac_of_nominal": ach / fp32_nominal,
                     "flops_per_eval": 42, "evals_per_launch": executed / max(score_launches, 1),
                     "note": "achieved = ALGORITHMIC flops (42 per evaluation, the reference's formulation) / launch time. The kernel is exact but does "
-                            "less arithmetic than that: the backward half of the symmetric transfer error (60 % of the flops) is evaluated only for "
-                            "point pairs on which some model of the warp is not already proven an outlier by its forward distance",
+                            "less arithmetic than that: a division-free forward test proves most evaluations outliers; the rest is re-evaluated with "
+                            "the reference's arithmetic from a per-warp survivor queue. fma_pipe_busy_pct_ncu is the hardware-side figure (ncu capture, profiles/)",
                     "avg_launch_ms": score_ms / max(score_launches, 1), "score_share_of_step": score_ms / ms_single,
                     "hbm": {"algorithmic_bytes_per_launch": alg_bytes_launch,
                             "achieved_gbs": alg_bytes_launch / (score_ms / max(score_launches, 1) * 1e-3) / 1e9,
@@ -432,6 +439,8 @@ def run_native(args):
                 "roofline": roofline}
         if c5 is not None:
             line["config"]["c5"] = c5
+        if not args.no_epipolar:
+            line.update(epipolar_rooflines(local, fp32_peak, peak_source))
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         if args.latency:
@@ -559,6 +568,36 @@ def run_c5(args):
     D.finalize()
 
 
+def epipolar_rooflines(local, fp32_peak, peak_source, steps=6):
+    """roofline_f / roofline_e: the scoring kernel on fundamental (squared Sampson, 33 flop) and essential (symmetric epipolar
+    distance, 44 flop) hypotheses: one round of K = 1024 samples (the seven-point solver keeps a model for ~15 % of the samples: a round has to be this long to fill its warps) for each of 1184 image pairs of 4000 correspondences with the
+    inlier ratios of BASELINE.json's configs 3 and 4 (25 % / 20 %), device resident; CUDA events around the one scoring launch
+    of every fit (usac_gpu_last_timing), best of `steps`."""
+    from ransac_b200 import GpuContext, capi
+    from ransac_b200 import generator as gen
+    out = {}
+    B, K = 1184, 1024
+    for name, est, make, thr, flops in (("roofline_f", capi.EST_FUNDAMENTAL, lambda s: gen.fundamental(n=N_POINTS, inlier_ratio=0.25, seed=s)[0], 2.0, 33),
+                                        ("roofline_e", capi.EST_ESSENTIAL, lambda s: gen.essential(n=N_POINTS, inlier_ratio=0.2, seed=s)[0], 2.5e-3, 44)):
+        pts = np.concatenate([make(7000 + i) for i in range(B)])
+        ctx = GpuContext(local)
+        ctx.set_points(est, pts, [N_POINTS] * B)
+        best, ev = None, 0.0
+        for rep in range(steps + 2):
+            res = ctx.fit_records(thr, CONF, K, seed=rep + 1, round_size=K)
+            t = ctx.last_timing()
+            if rep >= 2 and t["score_launches"] == 1 and (best is None or t["score_ms"] < best):
+                best, ev = t["score_ms"], float(res["evals"].sum())
+        ctx.close()
+        if best:
+            ach = flops * ev / (best * 1e-3) / 1e12
+            out[name] = {"bound": "fp32", "kernel": f"score_sq_kernel<{'FUNDAMENTAL' if est == capi.EST_FUNDAMENTAL else 'ESSENTIAL'}>", "achieved": ach,
+                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "flops_per_eval": flops, "evals_per_launch": ev,
+                         "launch_ms": best, "peak_source": peak_source,
+                         "workload": f"{B} image pairs x {K} samples x {N_POINTS} correspondences, one scoring launch per fit"}
+    return out
+
+
 def single_fit_latency(ctx, pts, timed):
     """ms per robust fit when ONE image pair is fitted alone (launch/sync latency bound), median of 20."""
     from ransac_b200 import capi
@@ -582,6 +621,7 @@ def main():
     ap.add_argument("--round-size", type=int, default=256, help="samples per round and problem")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
+    ap.add_argument("--no-epipolar", action="store_true", help="skip the roofline_f / roofline_e legs (Sampson / essential scoring kernels)")
     ap.add_argument("--no-c5", action="store_true", help="skip the second leg (config.c5: the hypothesis-sharded 1M-point fit)")
     ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")

@@ -148,6 +148,23 @@ typedef struct {
 } usac_refit_result;
 int usac_gpu_refit(usac_gpu_ctx* ctx, int problem, const float* model_in, int best_inliers, float threshold, usac_refit_result* out);
 
+/* ---- plugin-granularity entry points for SPRT, PROSAC and local optimisation --------------------------------------------------- */
+/* replaces the point walk of SPRT::verifyModelAndGetModelScore (sprt.hpp:191-257) for M models: model q walks the shuffled pool
+ * (usac_gpu_set_sprt_pool) from position start[q] under the test (epsilon, delta, A), lambda in double exactly as sprt.hpp:205-234;
+ * count_all[q] != 0 (the first max_hypothesis_test_before_sprt hypotheses): a rejected model still gets its full inlier count
+ * (sprt.hpp:243-257). The test history / re-design (sprt.hpp:259-311) is host arithmetic and stays with the caller (usac/sprt.hpp). */
+typedef struct { int good, tested_inliers, tested_points, inliers; } usac_sprt_result;
+int usac_gpu_sprt_verify(usac_gpu_ctx* ctx, int problem, const float* models, int M, float threshold, double epsilon, double delta, double A,
+                         const unsigned* start, const int* count_all, usac_sprt_result* out);
+/* replaces LocalOptimization::GetModelScore (local_optimization.hpp:19) for InItLORsc (1) / InItFLORsc (2): inner + iterative local
+ * optimisation of one so-far-the-best model (inner_local_optimization.hpp:74-133, iterative_local_optimization.hpp:61-135).
+ * model / inliers / score are updated in place when LO finds a bigger Score; *call_counter keys the random 14-point subsets
+ * (Philox, seed) and advances; *inner_iters / *iterative_iters accumulate. Parameters as in usac_fit_cfg (0 = defaults). */
+int usac_gpu_lo_model_score(usac_gpu_ctx* ctx, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* model, int* inliers, float* score,
+                            unsigned* inner_iters, unsigned* iterative_iters);
+/* ProsacSampler::initProsacSampler growth function T'_n (prosac_sampler.hpp:62-114); pure host arithmetic, out[n] */
+void usac_prosac_growth_function(unsigned n, unsigned sample_size, unsigned* out);
+
 /* Exchange hook for nranks > 1: called once per round with this rank's packed per-sample scores; must fill `all`
  * with the nranks contributions in rank order (an all-gather). `d_` pointers are device memory on ctx's stream.
  * libusac_gpu's own NCCL binding (usac_gpu_nccl_*) installs one; tests install a host emulation. */

@@ -40,6 +40,10 @@ class FitResult(C.Structure):
                 ("msac", C.c_float)]
 
 
+class SprtResult(C.Structure):
+    _fields_ = [("good", C.c_int), ("tested_inliers", C.c_int), ("tested_points", C.c_int), ("inliers", C.c_int)]
+
+
 class RefitResult(C.Structure):
     _fields_ = [("model", C.c_float * 9), ("inliers", C.c_int), ("accepted", C.c_int)]
 
@@ -51,7 +55,7 @@ def declared_symbols():
     """Every function the header declares (used by the symbol-export test)."""
     text = open(HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(usac_gpu_[a-z0-9_]+)\s*\(", text)) - {"usac_gpu_ctx"})
+    return sorted(set(re.findall(r"\b(usac_(?:gpu|prosac)_[a-z0-9_]+)\s*\(", text)) - {"usac_gpu_ctx"})
 
 
 _lib = None
@@ -87,6 +91,10 @@ def load():
     L.usac_gpu_fit.argtypes = [vp, C.POINTER(FitCfg), C.POINTER(FitResult)]
     L.usac_gpu_estimate_nonminimal.argtypes = [vp, C.c_int, ip, C.c_int, fp, ip]
     L.usac_gpu_refit.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.POINTER(RefitResult)]
+    L.usac_gpu_sprt_verify.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_uint), ip, C.POINTER(SprtResult)]
+    L.usac_gpu_lo_model_score.argtypes = [vp, C.c_int, C.POINTER(FitCfg), C.POINTER(C.c_uint64), fp, ip, fp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    L.usac_prosac_growth_function.argtypes = [C.c_uint, C.c_uint, C.POINTER(C.c_uint)]
+    L.usac_prosac_growth_function.restype = None
     L.usac_gpu_set_allgather.argtypes = [vp, ALLGATHER_FN, vp]
     L.usac_gpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.usac_gpu_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -94,7 +102,7 @@ def load():
     L.usac_gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in declared_symbols():
         fn = getattr(L, name)
-        if name not in ("usac_gpu_destroy", "usac_gpu_last_error"):
+        if name not in ("usac_gpu_destroy", "usac_gpu_last_error", "usac_prosac_growth_function"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -18,6 +18,11 @@
 #ifndef USAC_SCORE_GRID_CTAS
 #define USAC_SCORE_GRID_CTAS USAC_SCORE_MIN_CTAS   // scoring CTAs launched per SM (<= USAC_SCORE_MIN_CTAS; fewer leaves room for other streams' kernels)
 #endif
+#ifndef USAC_SQ_MIN_CTAS
+#define USAC_SQ_MIN_CTAS 5           // resident CTAs per SM of the survivor-queue scoring kernel (score_sq.cuh): 96 registers, a few bytes of
+                                     // spill in the drain; one-box A/B (profiles/README.md): 5 beats 4 by 4 % on the bench and 6 - 9 % on the
+                                     // epipolar kernels, 6 is slower (spills)
+#endif
 #ifndef USAC_PPI
 #define USAC_PPI 4                  // point pairs per trip of the scoring loop (independent instruction streams)
 #endif

@@ -189,7 +189,8 @@ template <> struct FastModel<USAC_EST_FUNDAMENTAL> {
         const float2 b = __ffma2_rn(dup(f21), X1, __ffma2_rn(dup(f22), Y1, dup(f23)));
         const float2 c = __ffma2_rn(dup(f11), X2, __ffma2_rn(dup(f21), Y2, dup(f31)));
         const float2 d = __ffma2_rn(dup(f12), X2, __ffma2_rn(dup(f22), Y2, dup(f32)));
-        const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, __ffma2_rn(dup(f31), X1, __ffma2_rn(dup(f32), Y1, dup(f33)))));
+        const float2 cp = __ffma2_rn(dup(f31), X1, __ffma2_rn(dup(f32), Y1, dup(f33)));
+        const float2 n = __ffma2_rn(X2, a, __ffma2_rn(Y2, b, cp));    // (two scalar FFMA per product instead of the three-pair FFMA2: no gain, A/B r2m)
         const float2 den = __ffma2_rn(d, d, __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a))));
         return __ffma2_rn(dup(negthrP), den, __ffma2_rn(n, n, dup(-b0P)));
     }

@@ -61,34 +61,47 @@ __device__ __noinline__ void sq_drain(const uint32_t* __restrict__ q, uint32_t c
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     pre[lane] = incl - cnt;                                            // exclusive prefix: first dense position of lane's entries
     __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t t = base + lane;
-        if (t >= total) continue;
-        int l = 0;                                                     // owner: the largest l with pre[l] <= t
+    // two batches of 32 entries per trip: their point / record loads (L2 / L1 latency) are in flight together
+    for (uint32_t base = 0; base < total; base += 64) {
+        int l[2], idx[2];
+        bool on[2];
+        float4 p[2];
 #pragma unroll
-        for (int step = 16; step; step >>= 1) if (pre[l + step] <= t) l += step;
-        const int idx = (int)q[(t - pre[l]) * 32 + l];
-        if (idx >= n) continue;                                        // NaN padding of an odd point count
-        const float* rec = recs_group + (size_t)l * USAC_REC_STRIDE;
-        float err;
-        if (EST == USAC_EST_LINE2D) {
-            const float2 p = reinterpret_cast<const float2*>(aos)[idx];
-            err = strict_error<EST>(rec, p.x, p.y, 0.f, 0.f);
-        } else {
-            const float4 p = reinterpret_cast<const float4*>(aos)[idx];
-            err = strict_error<EST>(rec, p.x, p.y, p.z, p.w);
+        for (int h = 0; h < 2; h++) {
+            const uint32_t t = base + 32u * h + lane;
+            on[h] = t < total;
+            l[h] = 0; idx[h] = 0;
+            if (on[h]) {
+                int ll = 0;                                            // owner: the largest l with pre[l] <= t
+#pragma unroll
+                for (int step = 16; step; step >>= 1) if (pre[ll + step] <= t) ll += step;
+                l[h] = ll;
+                idx[h] = (int)q[(t - pre[ll]) * 32 + ll];
+                on[h] = idx[h] < n;                                    // NaN padding of an odd point count
+            }
+            p[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on[h]) {
+                if (EST == USAC_EST_LINE2D) { const float2 v = reinterpret_cast<const float2*>(aos)[idx[h]]; p[h] = make_float4(v.x, v.y, 0.f, 0.f); }
+                else p[h] = reinterpret_cast<const float4*>(aos)[idx[h]];
+            }
         }
-        if (err < rec[REC_THR]) {                                      // quality.hpp:90-94, strict `<`, NaN is an outlier
-            const unsigned long long fix = __double2ull_rn((double)err * scale);
-            atomicAdd(&mcnt[l], 1u);
-            atomicAdd(&mlo[l], (uint32_t)(fix & ((1u << USAC_SQ_LO_BITS) - 1u)));
-            atomicAdd(&mhi[l], (uint32_t)(fix >> USAC_SQ_LO_BITS));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!on[h]) continue;
+            const float* rec = recs_group + (size_t)l[h] * USAC_REC_STRIDE;
+            const float err = strict_error<EST>(rec, p[h].x, p[h].y, p[h].z, p[h].w);
+            if (err < rec[REC_THR]) {                                  // quality.hpp:90-94, strict `<`, NaN is an outlier
+                const unsigned long long fix = __double2ull_rn((double)err * scale);
+                atomicAdd(&mcnt[l[h]], 1u);
+                atomicAdd(&mlo[l[h]], (uint32_t)(fix & ((1u << USAC_SQ_LO_BITS) - 1u)));
+                atomicAdd(&mhi[l[h]], (uint32_t)(fix >> USAC_SQ_LO_BITS));
+            }
         }
     }
 }
 
 template <int EST>
-__global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SCORE_MIN_CTAS) score_sq_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SQ_MIN_CTAS) score_sq_kernel(const ScoreArgs a) {
     constexpr int PAIR_FLOATS = (EST == USAC_EST_LINE2D) ? 4 : 8;
     constexpr int NWARPS = USAC_SCORE_THREADS / 32;
     static_assert(USAC_SQ_LANE_CAP >= 4 * USAC_PPI, "a lane's queue must hold two trips of pushes");

@@ -53,26 +53,17 @@ __device__ __forceinline__ void decide_pair(const FastModel<EST>& fm, const floa
     if (!(fabsf(t.y) > s.y)) in1 = __float_as_uint(strict_em<EST>(rec, P, i1, n)) >> 31;
 }
 
+// One model's walk: the likelihood-ratio test of sprt.hpp:205-234 from pool position `start`, then - when `count_all` and the model
+// was rejected - the rest of the pool (sprt.hpp:243-257).
 template <int EST>
-__global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const float* __restrict__ pool_pts) {
-    const int slot = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.K * a.S) return;
-    const int j = q / a.S, i = q % a.S;
-    const int pid = a.active[slot];
-    const ProblemDesc pd = a.prob[pid];
-    const FitState& st = a.state[pid];
-    SprtModelResult res = {0, 0, 0, 0};
-    SprtModelResult* out = a.sprt_res + (size_t)slot * a.mstride + q;
-    if (i >= a.nmodels[(size_t)slot * a.K + j]) { *out = res; return; }
-    const float* rec = a.recs + ((size_t)slot * a.mstride + a.offsets[(size_t)slot * a.K + j] + i) * USAC_REC_STRIDE;
+__device__ __forceinline__ SprtModelResult sprt_walk_one(const float* __restrict__ rec, const float* __restrict__ P, int n, unsigned start,
+                                                         double eps, double delta, double A, bool count_all) {
     FastModel<EST> fm;
     fm.load(rec);
-    const int n = pd.n;
-    const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
-    const double eps = st.sprt_eps, delta = st.sprt_delta, A = st.sprt_A;
+    SprtModelResult res = {0, 0, 0, 0};
     const double r_in = __ddiv_rn(delta, eps), r_out = __ddiv_rn(__dsub_rn(1.0, delta), __dsub_rn(1.0, eps));
     auto wrap = [n](int v) { while (v >= n) v -= n; return v; };      // n may be as small as the minimal sample
-    int idx = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q) % (unsigned long long)n);
+    int idx = (int)(start % (unsigned)n);
     double lambda = 1.0;
     int tp = 0, tin = 0;
     bool good = true;
@@ -96,9 +87,9 @@ __global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const 
         pa = na; pb = nb; idx = wrap(idx + 2);
     }
     res.good = good; res.tested_inl = tin; res.tested_pts = tp; res.full_inl = tin;
-    if (!good && (unsigned long long)st.samples_drawn + (unsigned long long)j < (unsigned long long)a.before_sprt) {
+    if (!good && count_all) {
         // sprt.hpp:243-257: keep counting from the point after the rejecting one
-        int pos = (int)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q + (unsigned long long)tp) % (unsigned long long)n);
+        int pos = (int)(((unsigned long long)start + (unsigned long long)tp) % (unsigned long long)n);
         int rest = n - tp, c = 0;
 #pragma unroll 1
         while (rest > 0) {
@@ -112,7 +103,33 @@ __global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const 
         }
         res.full_inl = tin + c;
     }
-    *out = res;
+    return res;
+}
+
+template <int EST>
+__global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const float* __restrict__ pool_pts) {
+    const int slot = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.K * a.S) return;
+    const int j = q / a.S, i = q % a.S;
+    const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
+    const FitState& st = a.state[pid];
+    SprtModelResult* out = a.sprt_res + (size_t)slot * a.mstride + q;
+    if (i >= a.nmodels[(size_t)slot * a.K + j]) { *out = SprtModelResult{0, 0, 0, 0}; return; }
+    const float* rec = a.recs + ((size_t)slot * a.mstride + a.offsets[(size_t)slot * a.K + j] + i) * USAC_REC_STRIDE;
+    const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+    const unsigned start = (unsigned)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q) % (unsigned long long)pd.n);
+    const bool count_all = (unsigned long long)st.samples_drawn + (unsigned long long)j < (unsigned long long)a.before_sprt;
+    *out = sprt_walk_one<EST>(rec, P, pd.n, start, st.sprt_eps, st.sprt_delta, st.sprt_A, count_all);
+}
+
+// SPRT::verifyModelAndGetModelScore for caller-supplied models (usac_gpu_sprt_verify): one thread per model
+template <int EST>
+__global__ void __launch_bounds__(64) sprt_verify_kernel(const float* __restrict__ recs, int M, const float* __restrict__ P, int n, const unsigned* __restrict__ start,
+                                                         const int* __restrict__ count_all, double eps, double delta, double A, SprtModelResult* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    out[q] = sprt_walk_one<EST>(recs + (size_t)q * USAC_REC_STRIDE, P, n, start[q], eps, delta, A, count_all ? count_all[q] != 0 : false);
 }
 
 // per-model (count, sum) of a fully scored round, in (sample, root) slot order q = j*S + i (count -1 = no such model):

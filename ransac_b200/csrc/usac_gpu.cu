@@ -614,23 +614,25 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks, b
                                                         (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS);
     // the kernel's warps draw items from a counter that is never reset: this launch owns [work_base, work_base + items),
     // and every warp draws exactly one value beyond that before it exits
-    unsigned grid_ctas = grid;
-    if (a.items) {      // the round's compact item list: its length is known on the device only; the list's own draw counter starts at 0
-        grid_ctas = (unsigned)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS;
-        a.work = c->d_item_count.p + 1; a.work_base = 0;
-    } else {
-        a.work = c->d_work.p; a.work_base = c->work_next;
-        c->work_next += (unsigned)items + grid * warps_per_cta;
-    }
-    auto& ev = c->next_score_event();
-    cudaEventRecord(ev.first, c->stream);
     // homography / fundamental / essential models of a RANSAC round (nearly every evaluation a provable outlier): the
     // survivor-queue kernel (score_sq.cuh). The accumulate-in-the-loop kernel (score.cuh) keeps the cases where survivors are
     // dense or the arithmetic is trivial: caller-supplied models of the Quality API (typically good models: a third of the
     // points survive) and lines (3 flops per evaluation: the push would cost more than the arithmetic). Both are exact.
     // USAC_GPU_SCORE_LEGACY=1 / =2 force the loop / queue kernel for every launch (A/B runs, tools/).
     static const int legacy = [] { const char* e = getenv("USAC_GPU_SCORE_LEGACY"); return e ? atoi(e) : 0; }();
-    if (legacy == 1 || c->est == USAC_EST_LINE2D || (dense_survivors && legacy != 2)) {
+    const bool loop_kernel = legacy == 1 || c->est == USAC_EST_LINE2D || (dense_survivors && legacy != 2);
+    unsigned grid_ctas = grid;
+    if (a.items) {      // the round's compact item list: its length is known on the device only; the list's own draw counter starts at 0
+        grid_ctas = (unsigned)c->prop.multiProcessorCount * (loop_kernel ? USAC_SCORE_GRID_CTAS : USAC_SQ_MIN_CTAS);
+        a.work = c->d_item_count.p + 1; a.work_base = 0;
+    } else {
+        if (!loop_kernel) grid_ctas = (unsigned)std::min<long long>((items + warps_per_cta - 1) / warps_per_cta, (long long)c->prop.multiProcessorCount * USAC_SQ_MIN_CTAS);
+        a.work = c->d_work.p; a.work_base = c->work_next;
+        c->work_next += (unsigned)items + grid_ctas * warps_per_cta;
+    }
+    auto& ev = c->next_score_event();
+    cudaEventRecord(ev.first, c->stream);
+    if (loop_kernel) {
         switch (c->est) {
             case USAC_EST_LINE2D: score_kernel<USAC_EST_LINE2D><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
             case USAC_EST_HOMOGRAPHY: score_kernel<USAC_EST_HOMOGRAPHY><<<grid_ctas, USAC_SCORE_THREADS, 0, c->stream>>>(a); break;
@@ -656,7 +658,7 @@ static void launch_score(usac_gpu_ctx* c, ScoreArgs a, int slots, int mblocks, b
 // tile-fetch latency and 128 B of model record per lane).
 static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_pairs, int* chunk_pairs, int* nchunks) {
     static const int per_warp = [] { const char* e = getenv("USAC_GPU_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
-    const long long warps = (long long)c->prop.multiProcessorCount * USAC_SCORE_GRID_CTAS * (USAC_SCORE_THREADS / 32);
+    const long long warps = (long long)c->prop.multiProcessorCount * std::max(USAC_SCORE_GRID_CTAS, USAC_SQ_MIN_CTAS) * (USAC_SCORE_THREADS / 32);
     const long long base = (long long)slots * mblocks * (USAC_SCORE_THREADS / 32);
     const int max_chunks = std::min(65535, std::max(1, max_pairs / (2 * USAC_TILE_PAIRS)));
     int nc = (int)std::min<long long>((per_warp * warps + base - 1) / base, max_chunks);
@@ -1292,6 +1294,73 @@ static void launch_walk(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
     dim3 g((a.K * a.S + 63) / 64, slots);
     sprt_walk_kernel<EST><<<g, 64, 0, c->stream>>>(a, c->d_pool_pts.p);
     c->last_launches++;
+}
+
+extern "C" void usac_prosac_growth_function(unsigned n, unsigned sample_size, unsigned* out) {
+    if (!out || n == 0) return;
+    std::vector<unsigned> g;
+    prosac_growth(n, sample_size, g);
+    memcpy(out, g.data(), sizeof(unsigned) * n);
+}
+
+extern "C" int usac_gpu_lo_model_score(usac_gpu_ctx* c, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* model, int* inliers, float* score,
+                                       unsigned* inner_iters, unsigned* iterative_iters) {
+    if (!c || !cfg || problem < 0 || problem >= c->P || !call_counter || !model || !inliers || !score) return fail(c, USAC_ERR_ARG, "lo_model_score: bad arguments");
+    if (cfg->lo != 1 && cfg->lo != 2) return fail(c, USAC_ERR_ARG, "lo_model_score: lo must be 1 (InItLORsc) or 2 (InItFLORsc)");
+    if (c->est == USAC_EST_LINE2D) return fail(c, USAC_ERR_ARG, "lo_model_score: local optimisation of line models is not built");
+    if (!(cfg->threshold > 0.f)) return fail(c, USAC_ERR_ARG, "lo_model_score: threshold must be positive");
+    cudaSetDevice(c->device);
+    int rc = push_desc(c);
+    if (rc) return rc;
+    LoRunner lo;
+    rc = lo.init(c, problem, cfg);
+    if (rc) return rc;
+    lo.calls = *call_counter;
+    rc = lo.get_model_score(model, *inliers, *score);
+    *call_counter = lo.calls;
+    if (inner_iters) *inner_iters += lo.inner_done;
+    if (iterative_iters) *iterative_iters += lo.iterative_done;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+template <int EST>
+static void launch_sprt_verify(usac_gpu_ctx* c, const float* recs, int M, const float* P, int n, const unsigned* start, const int* count_all,
+                               double eps, double delta, double A, SprtModelResult* out) {
+    sprt_verify_kernel<EST><<<(M + 63) / 64, 64, 0, c->stream>>>(recs, M, P, n, start, count_all, eps, delta, A, out);
+}
+
+extern "C" int usac_gpu_sprt_verify(usac_gpu_ctx* c, int problem, const float* models, int M, float threshold, double epsilon, double delta, double A,
+                                    const unsigned* start, const int* count_all, usac_sprt_result* out) {
+    if (!c || problem < 0 || problem >= c->P || !models || M <= 0 || !start || !out || !(threshold > 0.f)) return fail(c, USAC_ERR_ARG, "sprt_verify: bad arguments");
+    if (!c->h_pool_set[problem]) return fail(c, USAC_ERR_STATE, "sprt_verify: usac_gpu_set_sprt_pool was not called for this problem");
+    cudaSetDevice(c->device);
+    int rc = push_desc(c);
+    if (rc) return rc;
+    const ProblemDesc& d = c->h_prob[problem];
+    const int w = c->est == USAC_EST_LINE2D ? 3 : 9, dim = usac_point_dim(c->est);
+    CUDA_TRY(c, c->d_q_models.ensure((size_t)M * w));
+    CUDA_TRY(c, c->d_q_recs.ensure((size_t)M * USAC_REC_STRIDE));
+    CUDA_TRY(c, c->d_sprt_res.ensure((size_t)M));
+    CUDA_TRY(c, c->d_q_ids.ensure((size_t)std::max(2 * M, d.n + 1)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, models, sizeof(float) * w * M, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_q_ids.p, start, sizeof(unsigned) * M, cudaMemcpyHostToDevice, c->stream));
+    if (count_all) CUDA_TRY(c, cudaMemcpyAsync(c->d_q_ids.p + M, count_all, sizeof(int) * M, cudaMemcpyHostToDevice, c->stream));
+    prepare_models_kernel<<<(M + 127) / 128, 128, 0, c->stream>>>(c->est, c->d_q_models.p, M, w, threshold, c->d_prob.p, problem, c->d_q_recs.p);
+    const float* P = c->d_pool_pts.p + (size_t)d.aos_off * dim;
+    const unsigned* d_start = reinterpret_cast<const unsigned*>(c->d_q_ids.p);
+    const int* d_all = count_all ? c->d_q_ids.p + M : nullptr;
+    switch (c->est) {
+        case USAC_EST_LINE2D: launch_sprt_verify<USAC_EST_LINE2D>(c, c->d_q_recs.p, M, P, d.n, d_start, d_all, epsilon, delta, A, c->d_sprt_res.p); break;
+        case USAC_EST_HOMOGRAPHY: launch_sprt_verify<USAC_EST_HOMOGRAPHY>(c, c->d_q_recs.p, M, P, d.n, d_start, d_all, epsilon, delta, A, c->d_sprt_res.p); break;
+        case USAC_EST_FUNDAMENTAL: launch_sprt_verify<USAC_EST_FUNDAMENTAL>(c, c->d_q_recs.p, M, P, d.n, d_start, d_all, epsilon, delta, A, c->d_sprt_res.p); break;
+        default: launch_sprt_verify<USAC_EST_ESSENTIAL>(c, c->d_q_recs.p, M, P, d.n, d_start, d_all, epsilon, delta, A, c->d_sprt_res.p); break;
+    }
+    static_assert(sizeof(usac_sprt_result) == sizeof(SprtModelResult), "usac_sprt_result mirrors SprtModelResult");
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->d_sprt_res.p, sizeof(usac_sprt_result) * M, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return USAC_OK;
 }
 
 // Rounds with SPRT and/or PROSAC termination (host_replay.hpp): device = sample, solve, verify/score; host = replay.

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 
@@ -44,24 +46,41 @@ public:
         if (usac_gpu_create(&ctx, device) != USAC_OK) throw std::runtime_error(std::string("usac_gpu_create: ") + usac_gpu_last_error(nullptr));
         points_size = points.rows;
         check(usac_gpu_set_points(ctx, estimator, points.ptr(), &points_size, 1), "usac_gpu_set_points");
+        host_points = points.ptr();
+        registry()[host_points] = this;
     }
-    ~GpuDevice() { usac_gpu_destroy(ctx); }
+    ~GpuDevice() {
+        auto it = registry().find(host_points);
+        if (it != registry().end() && it->second == this) registry().erase(it);
+        usac_gpu_destroy(ctx);
+    }
+    // The reference's factories receive the points matrix, not a device (init.cpp:3-51): the device that uploaded a matrix is
+    // found again through the address of its data (the reference borrows that same pointer for the estimator's lifetime).
+    static GpuDevice* find(const cv::Mat& points) {
+        auto it = registry().find(points.ptr());
+        return it == registry().end() ? nullptr : it->second;
+    }
+    const float* host_points = nullptr;
     GpuDevice(const GpuDevice&) = delete;
     GpuDevice& operator=(const GpuDevice&) = delete;
     void check(int rc, const char* what) const {
         if (rc != USAC_OK) throw std::runtime_error(std::string(what) + ": " + usac_gpu_last_error(ctx));
     }
+private:
+    static std::map<const float*, GpuDevice*>& registry() { static std::map<const float*, GpuDevice*> r; return r; }
 };
 
 // Estimator (estimator.hpp:19-40): EstimateModel = the device minimal solver on one sample (usac_gpu_estimate, K = 1);
 // setModelParameters + GetError(pidx) = usac_gpu_errors (all N errors in the reference's exact arithmetic, cached).
 class GpuEstimator : public Estimator {
     GpuDevice* dev;
+    bool owns_device;
     std::vector<float> errors;
     bool errors_valid = false;
     float model_params[9];
 public:
-    explicit GpuEstimator(GpuDevice* d) : dev(d), errors((size_t)d->points_size) {}
+    explicit GpuEstimator(GpuDevice* d, bool owns_device_ = false) : dev(d), owns_device(owns_device_), errors((size_t)d->points_size) {}
+    ~GpuEstimator() override { if (owns_device) delete dev; }
     int SampleNumber() override { return dev->estimator == USAC_EST_LINE2D ? 2 : dev->estimator == USAC_EST_HOMOGRAPHY ? 4 : dev->estimator == USAC_EST_FUNDAMENTAL ? 7 : 5; }
     unsigned int EstimateModel(const int* const sample, std::vector<Model*>& models) override {
         float out[USAC_MAX_MODELS_PER_SAMPLE * 9];
@@ -138,17 +157,45 @@ class GpuSampler : public Sampler {
     std::vector<int> block;
     int block_size, cursor;
     unsigned long long next_hyp = 0;
+    // PROSAC (prosac_sampler.hpp:19-60): growth function, the stopping length shared with ProsacTerminationCriteria, and the
+    // largest subset size reached so far. While the stopping length can change between samples the sampler draws one sample per
+    // device call (block size 1), so that every sample sees the current value like the reference's.
+    std::vector<unsigned int> growth_function;
+    unsigned int* termination_length = nullptr;
+    unsigned int largest_sample_size = 0, subset_size = 0, hyp_count = 1;
 public:
     GpuSampler(GpuDevice* d, const Model* model, int block_size_ = 256) : dev(d), block_size(block_size_), cursor(block_size_) {
         sample_size = model->sample_size; points_size = (unsigned int)d->points_size;
         cfg.sampler = usac_sampler_code(model->sampler); cfg.rng = USAC_RNG_PHILOX; cfg.seed = model->seed;
         cfg.neighbors = model->neighborsType == Grid ? USAC_NEIGH_GRID : model->neighborsType == Nanoflann ? USAC_NEIGH_KNN : USAC_NEIGH_NONE;
         cfg.prosac_termination_length = 0; cfg.prosac_hyp_count = 0;
+        if (cfg.sampler == USAC_SAMPLER_PROSAC) {
+            growth_function.resize(points_size);
+            usac_prosac_growth_function(points_size, sample_size, growth_function.data());
+            largest_sample_size = subset_size = sample_size;
+            block_size = 1; cursor = 1;
+        }
         block.resize((size_t)block_size * sample_size);
     }
+    void setTerminationLength(unsigned int* p) { termination_length = p; }
+    unsigned int* getGrowthFunction() { return growth_function.data(); }
+    unsigned int* getLargestSampleSize() { return &largest_sample_size; }
     void generateSample(int* sample) override {
         if (cursor == block_size) {
-            if (cfg.sampler == USAC_SAMPLER_PROSAC) cfg.prosac_hyp_count = (unsigned)next_hyp + 1;
+            if (cfg.sampler == USAC_SAMPLER_PROSAC) {
+                const unsigned int L = termination_length ? *termination_length : points_size;
+                if (!(subset_size > L)) {                                   // prosac_sampler.hpp:141-156: counters move only outside termination mode
+                    if (hyp_count > growth_function[subset_size - 1]) {
+                        if (++subset_size > points_size) subset_size = points_size;
+                        if (largest_sample_size < subset_size) largest_sample_size = subset_size;
+                    }
+                    cfg.prosac_hyp_count = hyp_count;
+                    hyp_count++;
+                } else {
+                    cfg.prosac_hyp_count = hyp_count;
+                }
+                cfg.prosac_termination_length = L;
+            }
             dev->check(usac_gpu_sample(dev->ctx, 0, &cfg, next_hyp, block_size, block.data()), "usac_gpu_sample");
             cursor = 0;
         }

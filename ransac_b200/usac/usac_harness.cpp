@@ -2,7 +2,7 @@
 // run(), print RansacOutput) over the GPU plugin layer. Points come from a `*_pts.txt`-style file (first line N, then N
 // rows `x1 y1 x2 y2`, or `x y` for lines - the format of dataset/homography/sift_update/*_pts.txt).
 //   usac_harness <points.txt> <line2d|homography|fundamental|essential> <uniform|prosac|napsac> <threshold> <confidence> [seed]
-//                [--sequential|--both] [--lo 1|2] [--knn K] [--report] [--runs N --csv out.csv [--gt-inliers G]]
+//                [--sequential|--both] [--sprt] [--lo 1|2] [--round K] [--max-iter N] [--knn K] [--report] [--runs N --csv out.csv [--gt-inliers G]]
 // Prints one `key=value` line per result (model as IEEE bit patterns, inlier ids as a hash) for the parity tests; --report adds the
 // human-readable block of Tests::test (test/test.cpp:38-53); --runs/--csv writes one statistics row in the column layout of
 // Logging::saveHeadOfCSV / saveResultsCSV (helper/Logging.h:47-97) over N runs with seeds seed .. seed+N-1.
@@ -56,7 +56,7 @@ static Stat stat_of(std::vector<double> v) {
 
 int main(int argc, char** argv) {
     if (argc < 6 || !std::strcmp(argv[1], "--help")) {
-        std::fprintf(stderr, "usage: %s <points.txt> <line2d|homography|fundamental|essential> <uniform|prosac|napsac> <threshold> <confidence> [seed] [--sequential|--both] [--lo 1|2] [--knn K] [--report] [--runs N --csv out.csv [--gt-inliers G]]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <points.txt> <line2d|homography|fundamental|essential> <uniform|prosac|napsac> <threshold> <confidence> [seed] [--sequential|--both] [--sprt] [--lo 1|2] [--round K] [--max-iter N] [--knn K] [--report] [--runs N --csv out.csv [--gt-inliers G]]\n", argv[0]);
         return argc < 2 ? 2 : (!std::strcmp(argv[1], "--help") ? 0 : 2);
     }
     const std::string est = argv[2], smp = argv[3];
@@ -83,6 +83,9 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--csv") && i + 1 < argc) csv = argv[++i];
         else if (!std::strcmp(argv[i], "--gt-inliers") && i + 1 < argc) gt_inliers = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--knn") && i + 1 < argc) knn = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--sprt")) model.setSprt(true);
+        else if (!std::strcmp(argv[i], "--round") && i + 1 < argc) model.gpu_round_size = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--max-iter") && i + 1 < argc) model.max_iterations = (unsigned)std::atoi(argv[++i]);
         else model.seed = std::strtoull(argv[i], nullptr, 10);
     }
     model.setCellSize(50);

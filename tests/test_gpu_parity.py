@@ -518,12 +518,33 @@ def test_cabi_rejects_bad_arguments(ctx):
         ctx.fit(2.0, 0.95, 100, rank=0, nranks=2)                     # sharding without an exchange
     with pytest.raises(UsacGpuError):
         ctx.set_neighbors_grid(0, 0)
+    for bad_sampler in (0, capi.SAMPLER_PROGRESSIVE_NAPSAC, 5, 6, 99):      # NullS / ProgressiveNAPSAC / Evsac / ProsacNapsac / junk: never a silent uniform fallback
+        with pytest.raises(UsacGpuError):
+            ctx.fit(2.0, 0.95, 100, sampler=bad_sampler)
+        with pytest.raises(UsacGpuError):
+            ctx.sample(16, sampler=bad_sampler)
+    with pytest.raises(UsacGpuError):
+        ctx.fit(2.0, 0.95, 100, rng=7)                                # unknown random generator
+    with pytest.raises(UsacGpuError):
+        ctx.fit(2.0, 0.95, 100, sampler=capi.SAMPLER_NAPSAC)          # NAPSAC without a neighbourhood type
+    table = np.tile(np.arange(1, 6, dtype=np.int32), (100, 1))
+    with pytest.raises(UsacGpuError):
+        ctx.set_neighbors_knn(0, table[:, :2])                        # k < sample size - 1 (napsac_sampler.hpp:49)
+    bad = table.copy(); bad[7, 3] = 100
+    with pytest.raises(UsacGpuError):
+        ctx.set_neighbors_knn(0, bad)                                 # neighbour index out of range
+    ctx.set_neighbors_knn(0, table); ctx.set_neighbors_knn(0, table)  # installing a table twice reuses its segment
+    with pytest.raises(UsacGpuError):
+        ctx.build_neighbors_knn(0, 2)
     assert L.usac_gpu_score(h, 5, None, 1, C.c_float(2.0), None, None) == capi.ERR_ARG   # unknown problem / NULL models
     assert b"score" in L.usac_gpu_last_error(h)
     cnt, s = ctx.score(np.zeros((0, 9), np.float32), 2.0)             # zero models: nothing to do, not an error
     assert len(cnt) == 0
     r = ctx.fit(2.0, 0.95, 500, seed=1)[0]                            # the context is still usable after the failures
     assert r["inliers"] > 20
+    with pytest.raises(UsacGpuError):
+        ctx.set_points(O.EST_HOMOGRAPHY, np.concatenate([pts, pts[:2]]), [100, 2])   # rejected before anything changes: a second problem of 2 points
+    assert ctx.fit(2.0, 0.95, 500, seed=1)[0]["inliers"] == r["inliers"]              # the previous point set is intact (validation precedes every mutation)
 
 
 def test_minimal_point_sets_and_all_outliers(ctx):

@@ -92,6 +92,62 @@ def test_fused_equals_sequential_equals_oracle(harness, tmp_path, cfg, est_name,
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("est_name,sampler,flags", [("fundamental", "prosac", ["--sprt"]), ("essential", "uniform", ["--sprt", "--lo", "1"]),
+                                                     ("homography", "uniform", ["--sprt"]), ("homography", "uniform", ["--lo", "2"]),
+                                                     ("fundamental", "prosac", [])])
+def test_sprt_prosac_lo_through_the_plugin_classes(harness, tmp_path, est_name, sampler, flags):
+    """BASELINE configs 3 and 4 through the usac/ C++ surface: Ransac's constructor wires SPRT (pool upload), ProsacTerminationCriteria
+    (shared stopping length / largest sample size) and InnerLocalOptimization through the init* factories (ransac.hpp:41-93, init.cpp:3-83).
+    run() with rounds of one sample == run_sequential() over the virtual plugin calls == the oracle's sequential loop + refit."""
+    from oracle import oracle as O
+    from ransac_b200 import generator as gen
+    est = {"homography": O.EST_HOMOGRAPHY, "fundamental": O.EST_FUNDAMENTAL, "essential": O.EST_ESSENTIAL}[est_name]
+    if est_name == "essential":
+        pts, thr = gen.essential(n=1500, inlier_ratio=0.45, seed=21)[0], 2.5e-3
+    elif est_name == "fundamental":
+        pts, thr = gen.make(3, n=1500)[0], 2.0
+    else:
+        pts, thr = gen.make(2, n=1500)[0], 2.0
+    p = tmp_path / "p.txt"
+    write_points(p, pts)
+    max_it = 400
+    r = subprocess.run([harness, str(p), est_name, sampler, repr(thr), "0.95", "7", "--both", "--round", "1", "--max-iter", str(max_it)] + flags,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    got = parse(r.stdout)
+    f, s = got["fused"], got["sequential"]
+    assert f["iterations"] == s["iterations"] and f["inliers"] == s["inliers"] and f["hash"] == s["hash"]
+    # error sums: the round kernel adds the survivors' exact errors in fixed point, the Quality call adds fast values in float (1e-4, BASELINE.json);
+    # under SPRT the score is an inlier count, after LO a lane sum - both bit-identical
+    assert abs(f["score"] - s["score"]) <= 1e-4 * abs(s["score"])
+    assert np.array_equal(f["model"], s["model"])
+    sprt, lo = "--sprt" in flags, int(flags[flags.index("--lo") + 1]) if "--lo" in flags else 0
+    ref = O.ransac(pts, est, sampler=O.SAMPLER_PROSAC if sampler == "prosac" else O.SAMPLER_UNIFORM, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95,
+                   max_iterations=max_it, seed=7, sprt=sprt, lo=lo)
+    fin = O.refit(est, pts, ref["model"], ref["inliers"], thr)
+    assert f["iterations"] == ref["iterations"] and f["inliers"] == fin["inliers"]
+    assert np.array_equal(f["model"], np.asarray(fin["model"], np.float32).view(np.uint32))
+    assert f["hash"] == fnv(fin["ids"][:fin["inliers"]])
+
+
+def test_init_factories_and_classes_keep_the_reference_signatures():
+    for fname, sigs in (("init.hpp", ("inline void initEstimator(Estimator*& estimator, ESTIMATOR est, const cv::Mat& points",
+                                      "inline void initSampler(Sampler*& sampler, const Model* const model, const cv::Mat& points)",
+                                      "inline void initTerminationCriteria(TerminationCriteria*& termination_criteria, const Model* const model, unsigned int points_size)",
+                                      "inline void initProsacTerminationCriteria(TerminationCriteria*& termination_criteria, Sampler*& prosac_sampler, const Model* const model,",
+                                      "inline void initLocalOptimization(LocalOptimization*& local_optimization, Model* model, Estimator* estimator, Quality* quality, unsigned int points_size)")),
+                        ("sprt.hpp", ("SPRT(Model* model, Estimator* estimator_, unsigned int points_size_)",
+                                      "bool verifyModelAndGetModelScore(Model* model, int current_hypothese, unsigned int maximum_score, Score* score)",
+                                      "unsigned int getUpperBoundIterations(int inliers_size)")),
+                        ("prosac_termination_criteria.hpp", ("ProsacTerminationCriteria(unsigned int* growth_function_, const Model* const model, unsigned int points_size_, Estimator* estimator_)",
+                                                             "unsigned int getUpBoundIterations(unsigned int hypCount, const cv::Mat& model)")),
+                        ("local_optimization.hpp", ("InnerLocalOptimization(Model* model, Estimator* estimator_, Quality*", "void GetModelScore(Model* best_model, Score* best_score) override"))):
+        text = open(os.path.join(USAC, fname)).read()
+        for sig in sigs:
+            assert sig in text, (fname, sig)
+
+
+@pytest.mark.gpu
 def test_harness_report_and_statistics_csv(harness, tmp_path):
     """The reference's human-readable block (test/test.cpp:38-53) and one statistics row in its CSV layout (helper/Logging.h:47-97)."""
     from ransac_b200 import generator as gen

@@ -11,20 +11,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ransac_b200 import GpuContext, capi  # noqa: E402
 from ransac_b200 import generator as gen  # noqa: E402
 
+# environment: SCORE_BENCH_INLIERS (inlier ratio of the epipolar data, default 0.01 = structureless), SCORE_BENCH_K (comma list of round sizes)
+INL = float(os.environ.get("SCORE_BENCH_INLIERS", "0.01"))
+KS = tuple(int(v) for v in os.environ.get("SCORE_BENCH_K", "128,256,512").split(","))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
 kind = sys.argv[2] if len(sys.argv) > 2 else "homography"
 N = 4000
 FLOPS = {"homography": 42, "fundamental": 33, "essential": 44, "line2d": 4}[kind]
 EST = {"homography": capi.EST_HOMOGRAPHY, "fundamental": capi.EST_FUNDAMENTAL, "essential": capi.EST_ESSENTIAL, "line2d": capi.EST_LINE2D}[kind]
-make = {"homography": lambda s: gen.homography(n=N, inlier_ratio=0.0, seed=s)[0], "fundamental": lambda s: gen.fundamental(n=N, inlier_ratio=0.01, seed=s)[0],
-        "essential": lambda s: gen.essential(n=N, inlier_ratio=0.01, seed=s)[0], "line2d": lambda s: gen.line2d(n=N, inlier_ratio=0.0, seed=s)[0]}[kind]
+make = {"homography": lambda s: gen.homography(n=N, inlier_ratio=0.0, seed=s)[0], "fundamental": lambda s: gen.fundamental(n=N, inlier_ratio=INL, seed=s)[0],
+        "essential": lambda s: gen.essential(n=N, inlier_ratio=INL, seed=s)[0], "line2d": lambda s: gen.line2d(n=N, inlier_ratio=0.0, seed=s)[0]}[kind]
 thr = {"homography": 2.0, "fundamental": 2.0, "essential": 2.5e-3, "line2d": 8.0}[kind]
 pts = np.concatenate([make(1000 + i) for i in range(B)])
 ctx = GpuContext(0)
 ctx.set_points(EST, pts, [N] * B)
 info = ctx.device_info()
 peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
-for K in (128, 256, 512):
+for K in KS:
     best, ev = 1e9, 0.0
     for rep in range(5):
         res = ctx.fit_records(thr, 0.95, K, seed=rep + 1, round_size=K)
