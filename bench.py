@@ -365,8 +365,8 @@ def run_native(args):
     timed_e2e(2)
     ms_e2e, stats_e2e = timed_e2e(args.steps)
     useful_e2e = sum(s[0] for s in stats_e2e)
-    # results: one 168-byte FitState record per problem at the end + one `done` int per still-active problem per round
-    d2h_step = B * 168 + sum(s[6] for s in stats_e2e) / args.steps * B * 4   # (upper bound: every problem active in every round)
+    # results: one 176-byte FitState record per problem at the end + one `done` int per still-active problem per round
+    d2h_step = B * 176 + sum(s[6] for s in stats_e2e) / args.steps * B * 4   # (upper bound: every problem active in every round)
 
     # ---- second leg: the hypothesis-sharded 1M-point fit (config.c5) ----
     c5 = None
@@ -562,7 +562,7 @@ def run_c5(args):
                 "data": "synthetic", "config": {"workload": c5["workload"], "c5": c5,
                                                 "l2": "the 32 MB point set (AoS + pair layout) is L2 resident by design: it is re-read by every model block"},
                 "clocks": c5["clocks"], "gpu_launches": int(c5["gpu_launches_per_fit"] * args.steps * world),
-                "e2e": {"value": c5["e2e_evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": c5["h2d_bytes_per_fit"], "d2h_bytes_per_step": 168 + 4 * c5["rounds"],
+                "e2e": {"value": c5["e2e_evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": c5["h2d_bytes_per_fit"], "d2h_bytes_per_step": 176 + 4 * c5["rounds"],
                         "ms_per_step": c5["e2e_ms_per_fit"], "note": "includes the device-side grid build of set_neighbors_grid"}}
         print(json.dumps(line))
     D.finalize()
@@ -610,7 +610,18 @@ def single_fit_latency(ctx, pts, timed):
     return float(np.median(vals))
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries loaded on the way may print there too (NCCL writes its version banner to
+    stdout when a communicator is created with NCCL_DEBUG set): file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -60,6 +60,7 @@ struct FitState {
     int best_midx;
     unsigned iters, max_iters, samples_drawn, rounds;
     int done;
+    int round_pending;     // select_kernel processed a round that winner_kernel has not finished yet (rounds may be enqueued ahead of the host's knowledge)
     unsigned long long evals, useful_evals;
     // PROSAC sampler state (prosac_sampler.hpp:19-31)
     unsigned prosac_t, prosac_n, prosac_largest, prosac_term_len;

@@ -211,8 +211,19 @@ __global__ void sample_kernel(const RoundArgs a) {
             philox_unique(a.seed, hyp, 0, n, m, s);
         } else {
             unsigned c = a.cursors[pd.cursor_off + p];
-            if (a.cursors[pd.cursor_off + n + p] > 1u)                                     // rare: the round draws this seed more than once
-                for (int i = 0; i < j; i++) c += (seeds[i] == p) ? (unsigned)(m - 1) : 0u;   // earlier uses within this round
+            if (a.cursors[pd.cursor_off + n + p] > 1u) {                                   // rare: the round draws this seed more than once
+                unsigned earlier = 0;                                                      // earlier uses within this round (independent loads, 8 in flight)
+                int i = 0;
+                for (; i + 8 <= j; i += 8) {
+                    int v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = seeds[i + u];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) earlier += (v[u] == p);
+                }
+                for (; i < j; i++) earlier += (seeds[i] == p);
+                c += earlier * (unsigned)(m - 1);
+            }
             s[0] = p;
             if (a.neighbors == USAC_NEIGH_KNN) {
                 const int* row = a.knn + pd.knn_off + (size_t)pd.knn * p;
@@ -463,6 +474,7 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
     const int slot = blockIdx.x;
     const int pid = a.active[slot];
     FitState& st = a.state[pid];
+    if (st.done) return;                                            // a round enqueued ahead of the host's knowledge: the fit has already ended
     const ProblemDesc pd = a.prob[pid];
     const unsigned* table = a.term_tables + pd.term_off;
     const int K = a.K, R = a.nranks;
@@ -547,6 +559,7 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
         st.done = (T < K) || !(st.iters < st.max_iters);
         st.samples_drawn += (unsigned)K;
         st.rounds += 1;
+        st.round_pending = 1;                                       // winner_kernel finishes this round
         st.useful_evals += (unsigned long long)s_useful * (unsigned long long)pd.n;
     }
 }
@@ -559,6 +572,8 @@ __global__ void winner_kernel(const RoundArgs a, int slots) {
     if (slot >= slots) return;
     const int pid = a.active[slot];
     FitState& st = a.state[pid];
+    if (!st.round_pending) { if (a.done_out) a.done_out[slot] = st.done; return; }   // round enqueued after the fit had ended: select_kernel skipped it
+    st.round_pending = 0;
     const ProblemDesc pd = a.prob[pid];
     const long long first = (long long)st.samples_drawn - a.K;       // select_kernel already advanced samples_drawn
     if (st.best_hyp >= first) {

@@ -1694,43 +1694,51 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
         a.limit_remaining = 1;
         a.items = c->d_items.p; a.item_count = c->d_item_count.p;
-        CUDA_TRY(c, cudaMemsetAsync(c->d_item_count.p, 0, 2 * sizeof(unsigned), c->stream));
+        // One large problem (a 1M-point fit is ~1 ms of scoring per round): several rounds are enqueued back to back and the host
+        // synchronises once per batch instead of once per round - a round that starts after the fit has ended solves and scores
+        // nothing (limit_remaining) and select_kernel / winner_kernel skip it. With many small problems the host needs the
+        // `done` flags after every round to size the next one, and a wasted round would cost as much as a useful one.
+        int rounds_ahead = 1;
+        if (P == 1 && max_n >= 65536) rounds_ahead = (int)std::min<unsigned>(8u, (cfg->max_iterations + (unsigned)K - 1) / (unsigned)K);
+        for (int ahead = 0; ahead < rounds_ahead; ahead++) {
+            CUDA_TRY(c, cudaMemsetAsync(c->d_item_count.p, 0, 2 * sizeof(unsigned), c->stream));
 
-        launch_sampler(c, a, slots);
-        switch (c->est) {
-            case USAC_EST_LINE2D: launch_round_est<USAC_EST_LINE2D>(c, a, slots, cfg->sprt); break;
-            case USAC_EST_HOMOGRAPHY: launch_round_est<USAC_EST_HOMOGRAPHY>(c, a, slots, cfg->sprt); break;
-            case USAC_EST_FUNDAMENTAL: launch_round_est<USAC_EST_FUNDAMENTAL>(c, a, slots, cfg->sprt); break;
-            default: launch_round_est<USAC_EST_ESSENTIAL>(c, a, slots, cfg->sprt); break;
-        }
-        prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
-        c->last_launches++;
-        {
-            ScoreArgs sa{};
-            sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = act_cur; sa.recs = c->d_recs.p;
-            sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
-            sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
-            sa.items = c->d_items.p; sa.item_count = c->d_item_count.p;
-            launch_score(c, sa, slots, mblocks);
-            dim3 gr((K + 127) / 128, slots);
-            if (nchunks > 8) reduce_chunks_kernel<<<dim3((K + 31) / 32, slots), 256, 0, c->stream>>>(a);
-            else reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
-            c->last_launches++;
-            const uint2* scores = c->d_scores.p;
-            if (nranks > 1) {
-                const size_t bytes = (size_t)slots * (K / nranks) * sizeof(uint2);
-                int grc = c->allgather(c->allgather_user, c->d_scores.p, c->d_scores_all.p, bytes, (void*)c->stream);
-                if (grc) return fail(c, USAC_ERR_NCCL, "fit: all-gather failed");
-                scores = c->d_scores_all.p;
+            launch_sampler(c, a, slots);
+            switch (c->est) {
+                case USAC_EST_LINE2D: launch_round_est<USAC_EST_LINE2D>(c, a, slots, cfg->sprt); break;
+                case USAC_EST_HOMOGRAPHY: launch_round_est<USAC_EST_HOMOGRAPHY>(c, a, slots, cfg->sprt); break;
+                case USAC_EST_FUNDAMENTAL: launch_round_est<USAC_EST_FUNDAMENTAL>(c, a, slots, cfg->sprt); break;
+                default: launch_round_est<USAC_EST_ESSENTIAL>(c, a, slots, cfg->sprt); break;
             }
-            select_kernel<<<slots, 256, 0, c->stream>>>(a, scores);
+            prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
             c->last_launches++;
-        }
-        switch (c->est) {
-            case USAC_EST_LINE2D: launch_winner_est<USAC_EST_LINE2D>(c, a, slots); break;
-            case USAC_EST_HOMOGRAPHY: launch_winner_est<USAC_EST_HOMOGRAPHY>(c, a, slots); break;
-            case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
-            default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
+            {
+                ScoreArgs sa{};
+                sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = act_cur; sa.recs = c->d_recs.p;
+                sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
+                sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
+                sa.items = c->d_items.p; sa.item_count = c->d_item_count.p;
+                launch_score(c, sa, slots, mblocks);
+                dim3 gr((K + 127) / 128, slots);
+                if (nchunks > 8) reduce_chunks_kernel<<<dim3((K + 31) / 32, slots), 256, 0, c->stream>>>(a);
+                else reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
+                c->last_launches++;
+                const uint2* scores = c->d_scores.p;
+                if (nranks > 1) {
+                    const size_t bytes = (size_t)slots * (K / nranks) * sizeof(uint2);
+                    int grc = c->allgather(c->allgather_user, c->d_scores.p, c->d_scores_all.p, bytes, (void*)c->stream);
+                    if (grc) return fail(c, USAC_ERR_NCCL, "fit: all-gather failed");
+                    scores = c->d_scores_all.p;
+                }
+                select_kernel<<<slots, 256, 0, c->stream>>>(a, scores);
+                c->last_launches++;
+            }
+            switch (c->est) {
+                case USAC_EST_LINE2D: launch_winner_est<USAC_EST_LINE2D>(c, a, slots); break;
+                case USAC_EST_HOMOGRAPHY: launch_winner_est<USAC_EST_HOMOGRAPHY>(c, a, slots); break;
+                case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
+                default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
+            }
         }
         compact_active_kernel<<<1, 1024, 0, c->stream>>>(act_cur, c->d_done.p, slots, act_next);
         c->last_launches++;
