@@ -474,7 +474,9 @@ def c5_leg(args, rank, world, local, steps, warmup):
     from ransac_b200 import dist as D
     from ransac_b200 import generator as gen
     n = args.c5_points
-    K = args.c5_round if args.c5_round > 0 else 2048        # samples per round; NOT inflated with the rank count (results do not depend on K)
+    # samples per round: two rounds cover the 10 000 iterations (5000 + 5000), the same for every rank count - results do not depend on K,
+    # samples the sequential loop can no longer reach are neither solved nor scored, and every round costs one exchange
+    K = args.c5_round if args.c5_round > 0 else 5000
     pts = gen.make(5, n=n)[0]
     host = torch.from_numpy(pts).pin_memory()
     ctx = GpuContext(local)
@@ -637,7 +639,7 @@ def main():
     ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
-    ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 leg (0 = 2048)")
+    ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 leg (0 = 5000)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = max(args.warmup, 1)

@@ -154,7 +154,10 @@ __global__ void napsac_seed_kernel(const RoundArgs a) {
     a.seeds[(size_t)slot * a.K + j] = p;
     // how often the round uses each seed point (second half of the cursor segment, all zero between rounds): a seed used once -
     // the common case - needs no search for earlier uses in sample_kernel
-    if (p >= 0) atomicAdd(&a.cursors[pd.cursor_off + pd.n + p], 1u);
+    if (p >= 0) {
+        atomicAdd(&a.cursors[pd.cursor_off + pd.n + p], 1u);
+        atomicMax(&a.cursors[pd.cursor_off + 2 * (size_t)pd.n + p], (unsigned)(a.K - j));   // third part of the segment: K - (first sample of the round
+    }                                                                                         // that uses this seed); 0 = none
 }
 
 __global__ void napsac_commit_kernel(const RoundArgs a) {
@@ -165,7 +168,8 @@ __global__ void napsac_commit_kernel(const RoundArgs a) {
     if (p >= 0) {
         const ProblemDesc pd = a.prob[pid];
         atomicAdd(&a.cursors[pd.cursor_off + p], (unsigned)(a.m - 1));
-        a.cursors[pd.cursor_off + pd.n + p] = 0u;                     // use count back to zero for the next round
+        a.cursors[pd.cursor_off + pd.n + p] = 0u;                     // use count and first user back to zero for the next round
+        a.cursors[pd.cursor_off + 2 * (size_t)pd.n + p] = 0u;
     }
 }
 
@@ -211,8 +215,11 @@ __global__ void sample_kernel(const RoundArgs a) {
             philox_unique(a.seed, hyp, 0, n, m, s);
         } else {
             unsigned c = a.cursors[pd.cursor_off + p];
-            if (a.cursors[pd.cursor_off + n + p] > 1u) {                                   // rare: the round draws this seed more than once
-                unsigned earlier = 0;                                                      // earlier uses within this round (independent loads, 8 in flight)
+            const unsigned uses = a.cursors[pd.cursor_off + n + p];
+            if (uses == 2u) {                                                              // the round draws this seed twice: am I the second one?
+                c += ((unsigned)j > (unsigned)a.K - a.cursors[pd.cursor_off + 2 * (size_t)n + p]) ? (unsigned)(m - 1) : 0u;
+            } else if (uses > 2u) {                                                        // rarer still: count the earlier uses within this round
+                unsigned earlier = 0;
                 int i = 0;
                 for (; i + 8 <= j; i += 8) {
                     int v[8];
@@ -349,7 +356,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* sm /
     return before;
 }
 
-__global__ void __launch_bounds__(256) prepare_kernel(const RoundArgs a) {
+__global__ void __launch_bounds__(1024) prepare_kernel(const RoundArgs a) {
     __shared__ int sm[33];
     const int slot = blockIdx.x;
     const int pid = a.active[slot];
@@ -425,8 +432,9 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const RoundArgs a) {
     __shared__ int s_c[8][3][32];
     __shared__ float s_s[8][3][32];
     const int slot = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + lane;
-    const bool mine = j < a.K && !(a.nranks > 1 && (j % a.nranks) != a.rank);
+    const int own = blockIdx.x * 32 + lane;                            // this rank's samples, densely: j = own * nranks + rank
+    const int j = a.nranks > 1 ? own * a.nranks + a.rank : own;
+    const bool mine = j < a.K;
     const int k = mine ? a.nmodels[(size_t)slot * a.K + j] : 0;
     const int off = mine ? a.offsets[(size_t)slot * a.K + j] : 0;
     for (int i = 0; i < 3; i++) {
@@ -453,7 +461,7 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const RoundArgs a) {
     }
     if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }
     const int per_rank = (a.K + a.nranks - 1) / a.nranks;
-    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + j / a.nranks) : ((size_t)slot * a.K + j);
+    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + own) : ((size_t)slot * a.K + j);
     a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
 }
 

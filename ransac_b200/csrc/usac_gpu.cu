@@ -111,6 +111,16 @@ struct usac_gpu_ctx {
     float last_total_ms = 0, last_score_ms = 0;
     int last_launches = 0, last_score_launches = 0;
 
+    // USAC_GPU_TRACE=2: per-kernel device times of a fit (events between the launches of the main loop), printed by rank-local stderr
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    size_t marks_used = 0;
+    void mark(const char* name) {
+        if (marks_used == marks.size()) { cudaEvent_t e; cudaEventCreate(&e); marks.push_back({name, e}); }
+        marks[marks_used].first = name;
+        cudaEventRecord(marks[marks_used].second, stream);
+        marks_used++;
+    }
+
     std::pair<cudaEvent_t, cudaEvent_t>& next_score_event() {
         if (score_events_used == score_events.size()) {
             cudaEvent_t a, b;
@@ -430,7 +440,7 @@ extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const in
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (fresh) u.knn += (size_t)d.n * k;
     d.knn_off = off;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)d.n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)d.n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -524,7 +534,7 @@ extern "C" int usac_gpu_build_neighbors_knn(usac_gpu_ctx* c, int problem, int k)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     d.knn_off = knn_off;
     if (knn_fresh) u.knn += (size_t)n * k;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -582,7 +592,7 @@ extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cel
     d.cell_start_off = (long long)u.cell_start;
     u.grid += (size_t)n;
     u.cell_start += (size_t)n + 1;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 2 * (size_t)n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_GRID;
     return push_desc(c);
 }
@@ -660,7 +670,9 @@ static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_p
     static const int per_warp = [] { const char* e = getenv("USAC_GPU_ITEMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
     const long long warps = (long long)c->prop.multiProcessorCount * std::max(USAC_SCORE_GRID_CTAS, USAC_SQ_MIN_CTAS) * (USAC_SCORE_THREADS / 32);
     const long long base = (long long)slots * mblocks * (USAC_SCORE_THREADS / 32);
-    const int max_chunks = std::min(65535, std::max(1, max_pairs / (2 * USAC_TILE_PAIRS)));
+    // a work item costs ~2 us before its first trip (draw, record load, first tile): items of a large problem stay >= 8 tiles
+    const int min_tiles = max_pairs >= 65536 ? 8 : 2;
+    const int max_chunks = std::min(65535, std::max(1, max_pairs / (min_tiles * USAC_TILE_PAIRS)));
     int nc = (int)std::min<long long>((per_warp * warps + base - 1) / base, max_chunks);
     nc = std::max(nc, 1);
     int cp = (max_pairs + nc - 1) / nc;
@@ -1570,6 +1582,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     cudaSetDevice(c->device);
     // USAC_GPU_TRACE=1: host-side wall-clock split of one fit on stderr (setup / enqueue / waiting for the round's flags / read-back)
     static const bool trace = getenv("USAC_GPU_TRACE") != nullptr;
+    static const bool trace_kernels = trace && atoi(getenv("USAC_GPU_TRACE")) >= 2;
+    c->marks_used = 0;
+#define TK(name) do { if (trace_kernels) c->mark(name); } while (0)
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -1588,28 +1603,30 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
 
     // termination tables (cached by n) and sampler side data
     {
-        std::map<int, long long> by_n;
-        std::vector<unsigned> all;
-        if (c->term_cache.size() > 64) c->term_cache.clear();
-        for (int p = 0; p < P; p++) {
-            const int n = c->h_prob[p].n;
-            auto it = by_n.find(n);
-            if (it == by_n.end()) {
-                auto key = std::make_tuple(n, m, cfg->confidence, cfg->max_iterations);
-                auto ct = c->term_cache.find(key);
-                if (ct == c->term_cache.end()) {
-                    std::vector<unsigned> t;
-                    standard_termination_table((unsigned)n, m, cfg->confidence, cfg->max_iterations, t);
-                    ct = c->term_cache.emplace(key, std::move(t)).first;
-                }
-                it = by_n.insert({n, (long long)all.size()}).first;
-                all.insert(all.end(), ct->second.begin(), ct->second.end());
-            }
-            c->h_prob[p].term_off = it->second;
-        }
         std::vector<long long> sig = {(long long)m, (long long)__builtin_bit_cast(unsigned, cfg->confidence), (long long)cfg->max_iterations};
         for (int p = 0; p < P; p++) sig.push_back(c->h_prob[p].n);
-        if (sig != c->term_signature || c->d_term.cap < all.size()) {
+        bool offsets_set = true;
+        for (int p = 0; p < P; p++) offsets_set = offsets_set && c->h_prob[p].term_off >= 0;
+        if (sig != c->term_signature || !offsets_set) {              // same sizes and parameters as the last fit: d_term already holds the tables
+            std::map<int, long long> by_n;
+            std::vector<unsigned> all;
+            if (c->term_cache.size() > 64) c->term_cache.clear();
+            for (int p = 0; p < P; p++) {
+                const int n = c->h_prob[p].n;
+                auto it = by_n.find(n);
+                if (it == by_n.end()) {
+                    auto key = std::make_tuple(n, m, cfg->confidence, cfg->max_iterations);
+                    auto ct = c->term_cache.find(key);
+                    if (ct == c->term_cache.end()) {
+                        std::vector<unsigned> t;
+                        standard_termination_table((unsigned)n, m, cfg->confidence, cfg->max_iterations, t);
+                        ct = c->term_cache.emplace(key, std::move(t)).first;
+                    }
+                    it = by_n.insert({n, (long long)all.size()}).first;
+                    all.insert(all.end(), ct->second.begin(), ct->second.end());
+                }
+                c->h_prob[p].term_off = it->second;
+            }
             CUDA_TRY(c, c->d_term.ensure(all.size()));
             CUDA_TRY(c, cudaMemcpyAsync(c->d_term.p, all.data(), sizeof(unsigned) * all.size(), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1701,16 +1718,19 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         int rounds_ahead = 1;
         if (P == 1 && max_n >= 65536) rounds_ahead = (int)std::min<unsigned>(8u, (cfg->max_iterations + (unsigned)K - 1) / (unsigned)K);
         for (int ahead = 0; ahead < rounds_ahead; ahead++) {
+            TK("round");
             CUDA_TRY(c, cudaMemsetAsync(c->d_item_count.p, 0, 2 * sizeof(unsigned), c->stream));
 
             launch_sampler(c, a, slots);
+            TK("sampler");
             switch (c->est) {
                 case USAC_EST_LINE2D: launch_round_est<USAC_EST_LINE2D>(c, a, slots, cfg->sprt); break;
                 case USAC_EST_HOMOGRAPHY: launch_round_est<USAC_EST_HOMOGRAPHY>(c, a, slots, cfg->sprt); break;
                 case USAC_EST_FUNDAMENTAL: launch_round_est<USAC_EST_FUNDAMENTAL>(c, a, slots, cfg->sprt); break;
                 default: launch_round_est<USAC_EST_ESSENTIAL>(c, a, slots, cfg->sprt); break;
             }
-            prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
+            TK("solve");
+            prepare_kernel<<<slots, (slots == 1 && K >= 1024) ? 1024 : 256, 0, c->stream>>>(a);   // one large problem: one CTA compacts the whole round
             c->last_launches++;
             {
                 ScoreArgs sa{};
@@ -1718,18 +1738,22 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
                 sa.mvalid = c->d_mvalid.p; sa.M = K * S; sa.mstride = K * S; sa.chunk_pairs = chunk_pairs; sa.nchunks = nchunks;
                 sa.part_cnt = c->d_part_cnt.p; sa.part_sum = c->d_part_sum.p;
                 sa.items = c->d_items.p; sa.item_count = c->d_item_count.p;
+                TK("prepare");
                 launch_score(c, sa, slots, mblocks);
+                TK("score");
                 dim3 gr((K + 127) / 128, slots);
-                if (nchunks > 8) reduce_chunks_kernel<<<dim3((K + 31) / 32, slots), 256, 0, c->stream>>>(a);
+                if (nchunks > 8) reduce_chunks_kernel<<<dim3(((K + nranks - 1) / nranks + 31) / 32, slots), 256, 0, c->stream>>>(a);
                 else reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
                 c->last_launches++;
                 const uint2* scores = c->d_scores.p;
+                TK("reduce");
                 if (nranks > 1) {
                     const size_t bytes = (size_t)slots * (K / nranks) * sizeof(uint2);
                     int grc = c->allgather(c->allgather_user, c->d_scores.p, c->d_scores_all.p, bytes, (void*)c->stream);
                     if (grc) return fail(c, USAC_ERR_NCCL, "fit: all-gather failed");
                     scores = c->d_scores_all.p;
                 }
+                TK("allgather");
                 select_kernel<<<slots, 256, 0, c->stream>>>(a, scores);
                 c->last_launches++;
             }
@@ -1739,12 +1763,17 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
                 case USAC_EST_FUNDAMENTAL: launch_winner_est<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
                 default: launch_winner_est<USAC_EST_ESSENTIAL>(c, a, slots); break;
             }
+            TK("select+winner");
         }
         compact_active_kernel<<<1, 1024, 0, c->stream>>>(act_cur, c->d_done.p, slots, act_next);
         c->last_launches++;
         std::swap(act_cur, act_next);
         // the one host sync of the round: one `done` flag per active problem
         CUDA_TRY(c, cudaMemcpyAsync(c->h_done, c->d_done.p, sizeof(int) * slots, cudaMemcpyDeviceToHost, c->stream));
+        if (P == 1) {                                                // single problem: its final state rides on the same synchronisation
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState), cudaMemcpyDeviceToHost, c->stream));
+            cudaEventRecord(c->ev1, c->stream);
+        }
         const auto t_r1 = now();
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaGetLastError());
@@ -1753,9 +1782,11 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         for (int q = 0; q < slots; q++) if (!c->h_done[q]) next.push_back(active[q]);
         active.swap(next);
     }
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState) * P, cudaMemcpyDeviceToHost, c->stream));
-    cudaEventRecord(c->ev1, c->stream);
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (P != 1) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState) * P, cudaMemcpyDeviceToHost, c->stream));
+        cudaEventRecord(c->ev1, c->stream);
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     collect_timing(c);
     const int w = c->est == USAC_EST_LINE2D ? 3 : 9;
     for (int p = 0; p < P; p++) {
@@ -1767,6 +1798,17 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         r.best_hyp = s.best_hyp; r.best_model_idx = s.best_midx; r.rounds = s.rounds; r.evals = s.evals;
         r.useful_evals = s.useful_evals;
         r.msac = usac_msac_cost(c->h_prob[p].n, r.inliers, r.score, cfg->threshold);
+    }
+    if (trace_kernels && c->marks_used > 1) {
+        std::map<std::string, double> tot;
+        for (size_t i = 1; i < c->marks_used; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->marks[i - 1].second, c->marks[i].second);
+            tot[c->marks[i].first] += ms * 1e3;
+        }
+        std::string line = "usac_gpu_fit kernels (us, device time between launches):";
+        for (auto& kv : tot) { char buf[96]; snprintf(buf, sizeof(buf), " %s=%.0f", kv.first.c_str(), kv.second); line += buf; }
+        fprintf(stderr, "%s\n", line.c_str());
     }
     if (trace)
         fprintf(stderr, "usac_gpu_fit trace: %d problems, %d rounds: setup %.0f us, enqueue %.0f us, wait %.0f us, total %.0f us (GPU events: %.0f us, scoring %.0f us)\n",
