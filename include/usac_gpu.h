@@ -158,10 +158,12 @@ int usac_gpu_sprt_verify(usac_gpu_ctx* ctx, int problem, const float* models, in
                          const unsigned* start, const int* count_all, usac_sprt_result* out);
 /* replaces LocalOptimization::GetModelScore (local_optimization.hpp:19) for InItLORsc (1) / InItFLORsc (2): inner + iterative local
  * optimisation of one so-far-the-best model (inner_local_optimization.hpp:74-133, iterative_local_optimization.hpp:61-135).
- * model / inliers / score are updated in place when LO finds a bigger Score; *call_counter keys the random 14-point subsets
- * (Philox, seed) and advances; *inner_iters / *iterative_iters accumulate. Parameters as in usac_fit_cfg (0 = defaults). */
-int usac_gpu_lo_model_score(usac_gpu_ctx* ctx, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* model, int* inliers, float* score,
-                            unsigned* inner_iters, unsigned* iterative_iters);
+ * One kernel launch per call (the whole inner / iterative loop runs on the device). model / inliers / score are updated in place when
+ * LO finds a bigger Score; *call_counter keys the random 14-point subsets (Philox, seed) and advances; *lo_threshold carries
+ * IterativeLocalOptimization's running threshold between calls (a member in the reference; NULL or <= 0 = start from the model
+ * threshold); *inner_iters / *iterative_iters accumulate. Parameters as in usac_fit_cfg (0 = defaults). */
+int usac_gpu_lo_model_score(usac_gpu_ctx* ctx, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* lo_threshold, float* model, int* inliers,
+                            float* score, unsigned* inner_iters, unsigned* iterative_iters);
 /* ProsacSampler::initProsacSampler growth function T'_n (prosac_sampler.hpp:62-114); pure host arithmetic, out[n] */
 void usac_prosac_growth_function(unsigned n, unsigned sample_size, unsigned* out);
 

@@ -14,7 +14,7 @@
  *  - every sum over points is a "lane sum": lane t of 256 adds elements t, t+256, ... in order, then the 256 partial sums are
  *    combined by a fixed binary tree (stride 128, 64, ..., 1) - the order a 256-thread block reduces in;
  *  - the null vector of A is the eigenvector of the smallest eigenvalue of A'A (A in float like the reference, A'A in double),
- *    found by 12 cyclic Jacobi sweeps;  - H = T2^-1 Hn T1 and F = T2' Fn T1 are evaluated in double, then rounded to float.
+ *    found by cyclic Jacobi sweeps (at most 12; rotations below 1e-17 relative are skipped, a sweep without a rotation ends the loop);  - H = T2^-1 Hn T1 and F = T2' Fn T1 are evaluated in double, then rounded to float.
  */
 #include "oracle_internal.h"
 
@@ -40,20 +40,23 @@ T lane_sum(int n, F value) {
     return part[0];
 }
 
-/* eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (row-major, destroyed): cyclic Jacobi, 12 sweeps */
+/* eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (row-major, destroyed): cyclic Jacobi, at most 12 sweeps */
 void smallest_eigenvector(double* S, int n, double* vec) {
     double V[81];
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 12; sweep++)
+    for (int sweep = 0; sweep < 12; sweep++) {
+        int rotations = 0;                                        /* a sweep without a rotation: converged */
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const double apq = S[p * n + q];
                 if (apq == 0.0) continue;
+                if (apq * apq <= 1e-34 * std::fabs(S[p * n + p] * S[q * n + q])) continue;   /* |apq| <= 1e-17 sqrt(|app aqq|): nothing left to rotate */
                 const double theta = (S[q * n + q] - S[p * n + p]) / (2.0 * apq);
                 const double tt = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
                 const double t = theta < 0.0 ? -tt : tt;
                 const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
                 if (!std::isfinite(c) || !std::isfinite(s)) continue;
+                rotations++;
                 for (int k = 0; k < n; k++) {                     /* columns p, q of S */
                     const double skp = S[k * n + p], skq = S[k * n + q];
                     S[k * n + p] = c * skp - s * skq;
@@ -70,6 +73,8 @@ void smallest_eigenvector(double* S, int n, double* vec) {
                     V[k * n + q] = s * vkp + c * vkq;
                 }
             }
+        if (!rotations) break;
+    }
     int best = 0;
     for (int i = 1; i < n; i++) if (S[i * n + i] < S[best * n + best]) best = i;
     for (int k = 0; k < n; k++) vec[k] = V[k * n + best];

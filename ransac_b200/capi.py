@@ -92,7 +92,7 @@ def load():
     L.usac_gpu_estimate_nonminimal.argtypes = [vp, C.c_int, ip, C.c_int, fp, ip]
     L.usac_gpu_refit.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.POINTER(RefitResult)]
     L.usac_gpu_sprt_verify.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_uint), ip, C.POINTER(SprtResult)]
-    L.usac_gpu_lo_model_score.argtypes = [vp, C.c_int, C.POINTER(FitCfg), C.POINTER(C.c_uint64), fp, ip, fp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    L.usac_gpu_lo_model_score.argtypes = [vp, C.c_int, C.POINTER(FitCfg), C.POINTER(C.c_uint64), fp, fp, ip, fp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
     L.usac_prosac_growth_function.argtypes = [C.c_uint, C.c_uint, C.POINTER(C.c_uint)]
     L.usac_prosac_growth_function.restype = None
     L.usac_gpu_set_allgather.argtypes = [vp, ALLGATHER_FN, vp]

@@ -9,6 +9,9 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 // standard_termination_criteria.hpp:52-62 (float arithmetic, truncation)
@@ -89,14 +92,20 @@ struct ProsacTermHost {
     float log_1_p = 0;
     static constexpr unsigned kMinTerminationLength = 20;
 
-    void init(const std::vector<unsigned>& growth_, unsigned n_, unsigned m_, float confidence, unsigned max_it) {   // :44-119
-        growth = growth_; n = n_; m = m_; max_iterations = max_it; termination_length = n;
-        log_1_p = (float)logf(1 - confidence);
+    // The initial non-randomness table (prosac_termination_criteria.hpp:58-113) depends on (n, m) only and costs ~0.5 M pow/mul per
+    // call: it is computed once per (n, m) and copied for every fit (the table itself is updated while a fit runs).
+    static const std::vector<unsigned>& initial_non_random_inliers(unsigned n, unsigned m) {
+        static std::mutex mu;
+        static std::map<std::pair<unsigned, unsigned>, std::vector<unsigned>> cache;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find({n, m});
+        if (it != cache.end()) return it->second;
+        if (cache.size() > 32) cache.clear();
         const float beta = 0.05f, non_randomness = 0.95f;               // float constants: the mixed float/double expressions below follow :58-103
-        non_random_inliers.assign(n, 0);
+        std::vector<unsigned> table(n, 0);
         std::vector<double> pn(n);
         for (size_t nn = (size_t)m + 1; nn <= n; ++nn) {
-            if (nn - 1 > 1000) { non_random_inliers[nn - 1] = non_random_inliers[nn - 2]; continue; }
+            if (nn - 1 > 1000) { table[nn - 1] = table[nn - 2]; continue; }
             std::fill(pn.begin(), pn.begin() + nn, 0.0);              // entries [m, nn) are the only ones read below
             pn[m] = (beta) * std::pow((double)1 - beta, (double)nn - m - 1) * (nn - m);
             double cur = pn[m];
@@ -111,8 +120,14 @@ struct ProsacTermHost {
                 acc += pn[i - 1];
                 if (acc < 1 - non_randomness) i_min = (unsigned)i; else break;
             }
-            non_random_inliers[nn - 1] = i_min;
+            table[nn - 1] = i_min;
         }
+        return cache.emplace(std::make_pair(n, m), std::move(table)).first->second;
+    }
+    void init(const std::vector<unsigned>& growth_, unsigned n_, unsigned m_, float confidence, unsigned max_it) {   // :44-119
+        growth = growth_; n = n_; m = m_; max_iterations = max_it; termination_length = n;
+        log_1_p = (float)logf(1 - confidence);
+        non_random_inliers = initial_non_random_inliers(n, m);
         maximality_samples.assign(n, 10000u);
     }
     // getUpBoundIterations(hypCount, model), :148-201; mask[i] = (GetError(i) < threshold) over the quality-sorted points

@@ -9,8 +9,7 @@
 // One CTA of 256 threads per call. Every sum over the points is a "lane sum": thread t adds elements t, t+256, ... in order,
 // then the 256 partials are combined by a fixed binary tree (stride 128 ... 1) - the host restatement used by the parity
 // tests adds in exactly this order, so the models are bit-identical. A is formed in float like the reference, A'A (45 unique
-// entries) is accumulated in double, and the null vector is the eigenvector of its smallest eigenvalue (12 cyclic Jacobi
-// sweeps, thread 0) instead of cv::SVD on A. All arithmetic strict (no FMA contraction).
+// entries) is accumulated in double, and the null vector is the eigenvector of its smallest eigenvalue (cyclic Jacobi sweeps, at most 12, ended by the first sweep without a rotation) instead of cv::SVD on A. All arithmetic strict (no FMA contraction).
 #pragma once
 #include "strict_math.cuh"
 
@@ -48,17 +47,20 @@ __device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, d
     const int k = threadIdx.x & 31;
     for (int i = k; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
     __syncwarp();
-    for (int sweep = 0; sweep < 12; sweep++)
+    for (int sweep = 0; sweep < 12; sweep++) {
+        int rotations = 0;                                               // a sweep without a rotation: converged (uniform over the warp)
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const sd apq(S[p * n + q]);
                 if (apq.v == 0.0) continue;                              // uniform: every lane reads the same element
+                if ((apq * apq).v <= (sd(1e-34) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v) continue;   // |apq| <= 1e-17 sqrt(|app aqq|)
                 const sd theta = (sd(S[q * n + q]) - sd(S[p * n + p])) / (sd(2.0) * apq);
                 const sd tt = sd(1.0) / (sd(fabs(theta.v)) + dsqrt(theta * theta + sd(1.0)));
                 const sd t = theta.v < 0.0 ? -tt : tt;
                 const sd c = sd(1.0) / dsqrt(t * t + sd(1.0)), s = t * c;
                 __syncwarp();                                            // everyone has read S[p][q], S[p][p], S[q][q]
                 if (!dfinite(c.v) || !dfinite(s.v)) continue;
+                rotations++;
                 if (k < n) {
                     const sd a(S[k * n + p]), b(S[k * n + q]);
                     S[k * n + p] = (c * a - s * b).v;
@@ -75,6 +77,8 @@ __device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, d
                 }
                 __syncwarp();
             }
+        if (!rotations) break;
+    }
     int best = 0;
     for (int i = 1; i < n; i++) if (S[i * n + i] < S[best * n + best]) best = i;
     if (k < n) vec[k] = V[k * n + best];

@@ -23,6 +23,7 @@
 #include "score_sq.cuh"
 #include "sprt.cuh"
 #include "refit.cuh"
+#include "lo.cuh"
 #include "knn.cuh"
 #include "host_replay.hpp"
 
@@ -96,6 +97,7 @@ struct usac_gpu_ctx {
     DevBuf<float> d_q_models, d_q_recs, d_q_sum, d_q_err;
     DevBuf<int> d_q_cnt, d_q_ids, d_q_ids2, d_q_ok, d_lo_ids_a, d_lo_ids_b, d_lo_small;
     DevBuf<float> d_q_model2;
+    DevBuf<LoIO> d_lo_io;
     // exchange
     usac_allgather_fn allgather = nullptr;
     void* allgather_user = nullptr;
@@ -191,7 +193,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
     c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release(); c->d_items.release(); c->d_item_count.release();
-    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release();
+    c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release(); c->d_lo_io.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -1125,9 +1127,6 @@ struct LoRunner {
     float theta, lo_thr, step;
     uint64_t seed, calls = 0;
     unsigned inner_done = 0, iterative_done = 0;
-    const float* aos;
-    int *A, *B, *d_sample, *d_pos, *d_stat, *d_ok;
-    float* d_model;
 
     int init(usac_gpu_ctx* ctx, int problem_, const usac_fit_cfg* cfg) {
         const float threshold = cfg->threshold;
@@ -1142,126 +1141,41 @@ struct LoRunner {
         step = (threshold * (unsigned)mult - threshold) / (unsigned)iter_iters;        // iterative_local_optimization.hpp:43
         CUDA_TRY(c, c->d_lo_ids_a.ensure((size_t)n));
         CUDA_TRY(c, c->d_lo_ids_b.ensure((size_t)n));
-        CUDA_TRY(c, c->d_lo_small.ensure(64));
-        CUDA_TRY(c, c->d_q_model2.ensure(9));
-        CUDA_TRY(c, c->d_q_models.ensure(9));
-        CUDA_TRY(c, c->d_q_recs.ensure(USAC_REC_STRIDE));
-        aos = c->d_aos.p + (size_t)d.aos_off * dim;
-        A = c->d_lo_ids_a.p; B = c->d_lo_ids_b.p;
-        d_sample = c->d_lo_small.p; d_pos = c->d_lo_small.p + 16; d_stat = c->d_lo_small.p + 32; d_ok = c->d_lo_small.p + 40;
-        d_model = c->d_q_model2.p;
-        return USAC_OK;
-    }
-    // Quality::getNumberInliers(.., thr, get_inliers = true, ids): device model -> ids, count, lane-summed errors
-    int score(const float* d_mod, float thr, int* ids, int& cnt, float& sum) {
-        prepare_models_kernel<<<1, 32, 0, c->stream>>>(c->est, d_mod, 1, w, thr, c->d_prob.p, problem, c->d_q_recs.p);
-        switch (c->est) {
-            case USAC_EST_HOMOGRAPHY: inliers_sum_kernel<USAC_EST_HOMOGRAPHY><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
-            case USAC_EST_FUNDAMENTAL: inliers_sum_kernel<USAC_EST_FUNDAMENTAL><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
-            case USAC_EST_ESSENTIAL: inliers_sum_kernel<USAC_EST_ESSENTIAL><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
-            default: inliers_sum_kernel<USAC_EST_LINE2D><<<1, 1024, 0, c->stream>>>(aos, n, c->d_q_recs.p, thr, ids, d_stat); break;
+        CUDA_TRY(c, c->d_lo_io.ensure(1));
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(c, cudaFuncSetAttribute(lo_kernel<USAC_EST_HOMOGRAPHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoShared)));
+            CUDA_TRY(c, cudaFuncSetAttribute(lo_kernel<USAC_EST_FUNDAMENTAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoShared)));
+            CUDA_TRY(c, cudaFuncSetAttribute(lo_kernel<USAC_EST_ESSENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoShared)));
+            attr_set = true;
         }
-        c->last_launches += 2;
-        int st[2];
-        CUDA_TRY(c, cudaMemcpyAsync(st, d_stat, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        cnt = st[0]; memcpy(&sum, &st[1], 4);
-        return USAC_OK;
-    }
-    // Estimator::LeastSquaresFitting on device ids -> d_model; ok
-    int fit_ids(const int* ids, int count, bool& ok) {
-        launch_nonminimal(c, aos, ids, count, d_model, d_ok);
-        int h = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&h, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        ok = h != 0;
-        return USAC_OK;
-    }
-    // 14 distinct positions in [0, count): two Philox draws (8 + 6), the second mapped past the first
-    int fit_random_subset(const int* from, int count, bool& ok) {
-        int pos[16], a[8], b[8];
-        const int k = sample_limit;
-        philox_unique(seed, calls, 7, count, std::min(k, 8), a);
-        for (int i = 0; i < std::min(k, 8); i++) pos[i] = a[i];
-        if (k > 8) {
-            philox_unique(seed, calls, 8, count - 8, k - 8, b);
-            int sorted[8];
-            for (int i = 0; i < 8; i++) sorted[i] = a[i];
-            std::sort(sorted, sorted + 8);
-            for (int i = 0; i < k - 8; i++) {
-                int v = b[i];
-                for (int q = 0; q < 8; q++) if (v >= sorted[q]) v++;
-                pos[8 + i] = v;
-            }
-        }
-        calls++;
-        CUDA_TRY(c, cudaMemcpyAsync(d_pos, pos, sizeof(int) * k, cudaMemcpyHostToDevice, c->stream));
-        gather_ids_kernel<<<1, 32, 0, c->stream>>>(from, d_pos, k, d_sample);
-        c->last_launches++;
-        return fit_ids(d_sample, k, ok);
-    }
-    static bool bigger(int ia, float sa, int ib, float sb) { return ia > ib || (ia == ib && sa > sb); }
-
-    int iterative(int& lo_inl, float& lo_sum, int best_inl, float best_sum, bool& fail) {
-        for (int it = 0; it < iter_iters; it++) {
-            lo_thr -= step;
-            if (lo_inl <= m) break;
-            bool ok = false;
-            int rc;
-            if (kind == 2) {                                              // GetScoreLimited
-                if (lo_inl > sample_limit) {
-                    if ((rc = fit_random_subset(B, lo_inl, ok))) return rc;
-                    if (!ok) continue;
-                } else {
-                    if ((rc = fit_ids(B, lo_inl, ok))) return rc;
-                    if (!ok) break;
-                }
-                if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
-            } else {                                                      // GetScoreUnlimited
-                if ((rc = fit_ids(B, lo_inl, ok))) return rc;
-                if (!ok) break;
-                if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
-                if (bigger(best_inl, best_sum, lo_inl, lo_sum)) break;
-            }
-            iterative_done++;
-        }
-        fail = false;
-        if (fabsf(lo_thr - theta) > 0.00001) { fail = true; lo_thr = theta; }
         return USAC_OK;
     }
 
-    // InnerLocalOptimization::GetModelScore: model / score updated in place
+    // InnerLocalOptimization::GetModelScore: model / score updated in place. One launch (lo.cuh), one synchronisation.
     int get_model_score(float* best_model, int& best_inl, float& best_sum) {
-        if (best_inl < 12) return USAC_OK;
-        int rc, cnt;
-        float sum;
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, best_model, sizeof(float) * w, cudaMemcpyHostToDevice, c->stream));
-        if ((rc = score(c->d_q_models.p, theta, A, cnt, sum))) return rc;      // quality->getInliers(best_model)
-        int avail = std::min(best_inl, cnt);                                      // ids present in A (never index past the list)
-        for (int it = 0; it < inner_iters; it++) {
-            bool ok = false;
-            if (avail > sample_limit) {
-                if ((rc = fit_random_subset(A, avail, ok))) return rc;
-                if (!ok) continue;
-            } else {
-                if ((rc = fit_ids(A, avail, ok))) return rc;
-                if (!ok) break;
-            }
-            lo_thr = (unsigned)mult * lo_thr;                                     // inner_local_optimization.hpp:101
-            int lo_inl;
-            float lo_sum;
-            if ((rc = score(d_model, lo_thr, B, lo_inl, lo_sum))) return rc;
-            if (lo_inl <= m) continue;
-            bool fail = false;
-            if ((rc = iterative(lo_inl, lo_sum, best_inl, best_sum, fail))) return rc;
-            if (!fail && bigger(lo_inl, lo_sum, best_inl, best_sum)) {
-                CUDA_TRY(c, cudaMemcpyAsync(best_model, d_model, sizeof(float) * w, cudaMemcpyDeviceToHost, c->stream));
-                CUDA_TRY(c, cudaMemcpyAsync(A, B, sizeof(int) * lo_inl, cudaMemcpyDeviceToDevice, c->stream));
-                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-                best_inl = lo_inl; best_sum = lo_sum; avail = lo_inl;
-            }
-            inner_done++;
+        if (best_inl < 12) return USAC_OK;                                              // inner_local_optimization.hpp:76
+        LoIO io;
+        memset(&io, 0, sizeof(io));
+        for (int i = 0; i < w; i++) io.model[i] = best_model[i];
+        io.inliers = best_inl; io.score = best_sum; io.lo_thr = lo_thr; io.calls = calls;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_lo_io.p, &io, sizeof(io), cudaMemcpyHostToDevice, c->stream));
+        LoArgs a;
+        a.aos = c->d_aos.p + (size_t)c->h_prob[problem].aos_off * dim; a.prob = c->d_prob.p; a.problem = problem; a.n = n; a.m = m; a.kind = kind;
+        a.sample_limit = sample_limit; a.inner_iters = inner_iters; a.iter_iters = iter_iters; a.mult = mult; a.theta = theta; a.step = step;
+        a.seed = seed; a.io = c->d_lo_io.p; a.A = c->d_lo_ids_a.p; a.B = c->d_lo_ids_b.p;
+        switch (c->est) {
+            case USAC_EST_HOMOGRAPHY: lo_kernel<USAC_EST_HOMOGRAPHY><<<1, LO_THREADS, sizeof(LoShared), c->stream>>>(a); break;
+            case USAC_EST_FUNDAMENTAL: lo_kernel<USAC_EST_FUNDAMENTAL><<<1, LO_THREADS, sizeof(LoShared), c->stream>>>(a); break;
+            default: lo_kernel<USAC_EST_ESSENTIAL><<<1, LO_THREADS, sizeof(LoShared), c->stream>>>(a); break;
         }
+        c->last_launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(&io, c->d_lo_io.p, sizeof(io), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaGetLastError());
+        for (int i = 0; i < w; i++) best_model[i] = io.model[i];
+        best_inl = io.inliers; best_sum = io.score; lo_thr = io.lo_thr; calls = io.calls;
+        inner_done += io.inner_done; iterative_done += io.iterative_done;
         return USAC_OK;
     }
 };
@@ -1315,8 +1229,8 @@ extern "C" void usac_prosac_growth_function(unsigned n, unsigned sample_size, un
     memcpy(out, g.data(), sizeof(unsigned) * n);
 }
 
-extern "C" int usac_gpu_lo_model_score(usac_gpu_ctx* c, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* model, int* inliers, float* score,
-                                       unsigned* inner_iters, unsigned* iterative_iters) {
+extern "C" int usac_gpu_lo_model_score(usac_gpu_ctx* c, int problem, const usac_fit_cfg* cfg, uint64_t* call_counter, float* lo_threshold, float* model, int* inliers,
+                                       float* score, unsigned* inner_iters, unsigned* iterative_iters) {
     if (!c || !cfg || problem < 0 || problem >= c->P || !call_counter || !model || !inliers || !score) return fail(c, USAC_ERR_ARG, "lo_model_score: bad arguments");
     if (cfg->lo != 1 && cfg->lo != 2) return fail(c, USAC_ERR_ARG, "lo_model_score: lo must be 1 (InItLORsc) or 2 (InItFLORsc)");
     if (c->est == USAC_EST_LINE2D) return fail(c, USAC_ERR_ARG, "lo_model_score: local optimisation of line models is not built");
@@ -1328,8 +1242,10 @@ extern "C" int usac_gpu_lo_model_score(usac_gpu_ctx* c, int problem, const usac_
     rc = lo.init(c, problem, cfg);
     if (rc) return rc;
     lo.calls = *call_counter;
+    if (lo_threshold && *lo_threshold > 0.f) lo.lo_thr = *lo_threshold;
     rc = lo.get_model_score(model, *inliers, *score);
     *call_counter = lo.calls;
+    if (lo_threshold) *lo_threshold = lo.lo_thr;
     if (inner_iters) *inner_iters += lo.inner_done;
     if (iterative_iters) *iterative_iters += lo.iterative_done;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));

@@ -9,6 +9,7 @@ class InnerLocalOptimization : public LocalOptimization {
     GpuDevice* dev;
     usac_fit_cfg cfg{};
     uint64_t calls = 0;                  // keys the random inlier subsets (Philox; the reference seeds mt19937 from random_device)
+    float lo_threshold = 0;              // IterativeLocalOptimization's running threshold survives calls (iterative_local_optimization.hpp:20-58)
 public:
     unsigned int lo_inner_iters = 0, lo_iterative_iters = 0;
 
@@ -28,7 +29,7 @@ public:
         const cv::Mat d = best_model->returnDescriptor();
         float params[9] = {0};
         for (int k = 0; k < d.rows * d.cols; k++) params[k] = d.ptr()[k];
-        dev->check(usac_gpu_lo_model_score(dev->ctx, 0, &cfg, &calls, params, &best_score->inlier_number, &best_score->score, &lo_inner_iters, &lo_iterative_iters),
+        dev->check(usac_gpu_lo_model_score(dev->ctx, 0, &cfg, &calls, &lo_threshold, params, &best_score->inlier_number, &best_score->score, &lo_inner_iters, &lo_iterative_iters),
                    "usac_gpu_lo_model_score");
         cv::Mat out(d.rows, d.cols);
         for (int k = 0; k < d.rows * d.cols; k++) out.ptr()[k] = params[k];
