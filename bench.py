@@ -572,15 +572,17 @@ def run_c5(args):
 
 def epipolar_rooflines(local, fp32_peak, peak_source, steps=6):
     """roofline_f / roofline_e: the scoring kernel on fundamental (squared Sampson, 33 flop) and essential (symmetric epipolar
-    distance, 44 flop) hypotheses: one round of K = 1024 samples (the seven-point solver keeps a model for ~15 % of the samples: a round has to be this long to fill its warps) for each of 1184 image pairs of 4000 correspondences with the
+    distance, 44 flop) hypotheses: one round of K samples for each of 1184 image pairs of 4000 correspondences with the
     inlier ratios of BASELINE.json's configs 3 and 4 (25 % / 20 %), device resident; CUDA events around the one scoring launch
     of every fit (usac_gpu_last_timing), best of `steps`."""
     from ransac_b200 import GpuContext, capi
     from ransac_b200 import generator as gen
     out = {}
-    B, K = 1184, 1024
-    for name, est, make, thr, flops in (("roofline_f", capi.EST_FUNDAMENTAL, lambda s: gen.fundamental(n=N_POINTS, inlier_ratio=0.25, seed=s)[0], 2.0, 33),
-                                        ("roofline_e", capi.EST_ESSENTIAL, lambda s: gen.essential(n=N_POINTS, inlier_ratio=0.2, seed=s)[0], 2.5e-3, 44)):
+    B = 1184
+    # K: the seven-point solver keeps a model for ~15 % of the samples (oriented-epipolar filter), the five-point solver for ~1/3: rounds of
+    # 2048 / 1024 samples give ~300 models per image pair - the model count of a 256-sample homography round (the bench's first rounds)
+    for name, est, make, thr, flops, K in (("roofline_f", capi.EST_FUNDAMENTAL, lambda s: gen.fundamental(n=N_POINTS, inlier_ratio=0.25, seed=s)[0], 2.0, 33, 2048),
+                                           ("roofline_e", capi.EST_ESSENTIAL, lambda s: gen.essential(n=N_POINTS, inlier_ratio=0.2, seed=s)[0], 2.5e-3, 44, 1024)):
         pts = np.concatenate([make(7000 + i) for i in range(B)])
         ctx = GpuContext(local)
         ctx.set_points(est, pts, [N_POINTS] * B)
