@@ -511,6 +511,26 @@ def c5_leg(args, rank, world, local, steps, warmup):
         ctx.set_neighbors_grid(0, 50)                       # times its neighbourhood build separately: test/test.cpp:17-29)
         return step()
 
+    # N > 1: first with one NCCL all-gather per round (the hook), then with the exchange over peer memory (IPC windows: the reduce
+    # kernel stores into every rank's window over NVLink, select_kernel waits for the flags) - the product's default when attached
+    ms_nccl, exchange = None, "none (one GPU)"
+    if world > 1:
+        bracket(step, warmup)
+        ms_nccl_total, st_nccl = bracket(step, steps)
+        ms_nccl = D.reduce_max([ms_nccl_total / steps])[0]
+        exchange = "NCCL all-gather per round"
+        if os.environ.get("USAC_BENCH_EXCHANGE", "peer") != "nccl":
+            try:
+                ctx.peer_attach(D.allgather_bytes(ctx.peer_export()), rank, world)
+                ok = 1.0
+            except Exception as e:   # noqa: BLE001
+                print(f"bench.py: peer windows unavailable on rank {rank}: {e}", file=sys.stderr)
+                ok = 0.0
+            all_ok, any_ok = -D.reduce_max([-ok])[0] >= 1.0, D.reduce_max([ok])[0] >= 1.0
+            if any_ok and not all_ok:
+                raise SystemExit("bench.py: peer windows attached on some ranks only")
+            if all_ok:
+                exchange = "peer windows over NVLink (stores from the reduce kernel + flags, no collective call)"
     bracket(step, warmup)
     clocks = ClockSampler(local)
     clocks.start()
@@ -534,8 +554,8 @@ def c5_leg(args, rank, world, local, steps, warmup):
     info = ctx.device_info()
     peak = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
     out = {"workload": f"C5 homography N={n}, 10% inliers (clustered), NAPSAC grid cell 50, max_iter {MAX_IT}, conf {CONF}; one robust fit, "
-                       f"hypotheses of every round of {K} samples sharded over {world} GPU(s), one NCCL all-gather per round",
-           "scaling": "strong", "ms_per_fit": t_all[0], "evals_per_s": sums[0] / steps / (t_all[0] * 1e-3),
+                       f"hypotheses of every round of {K} samples sharded over {world} GPU(s), one exchange of the per-sample scores per round",
+           "scaling": "strong", "exchange": exchange, "ms_per_fit_nccl": ms_nccl, "ms_per_fit": t_all[0], "evals_per_s": sums[0] / steps / (t_all[0] * 1e-3),
            "evals_executed_per_s": sums[1] / steps / (t_all[0] * 1e-3),
            "iterations": st[-1][5], "inliers": st[-1][6], "best_hyp": st[-1][7], "model_crc": st[-1][8], "rounds": st[-1][9],
            "parity_vs_n1": parity, "parity_note": "iterations / inliers / winning sample / model CRC32 equal tests/golden/c5_n1_oracle.json "

@@ -176,6 +176,20 @@ int usac_gpu_set_allgather(usac_gpu_ctx* ctx, usac_allgather_fn fn, void* user);
 int usac_gpu_nccl_unique_id(char id_out[128]);
 int usac_gpu_nccl_init(usac_gpu_ctx* ctx, const char id[128], int rank, int nranks);
 
+/* Exchange over peer memory (NVLink), the default of the hypothesis-sharded fit when attached: every rank owns an exchange
+ * window in its HBM; the kernel that reduces a round's scores stores this rank's part straight into every rank's window and
+ * raises a flag there, and the kernel that applies the round (best update + termination, ransac.cpp:103-137) waits for all
+ * flags - no collective call and no extra launch. One process per GPU: usac_gpu_peer_export on every rank, all-gather the
+ * USAC_PEER_HANDLE_BYTES handles with the launcher (rank order), usac_gpu_peer_attach on every rank. Ranks inside one process
+ * (one thread per GPU, or tests): usac_gpu_peer_window + usac_gpu_peer_attach_ptrs. Rounds larger than a window (131072
+ * samples x problems) fall back to the all-gather hook above. A rank that does not arrive within 2 s makes the others
+ * return USAC_ERR_NCCL instead of waiting for ever. */
+#define USAC_PEER_HANDLE_BYTES 64
+int usac_gpu_peer_export(usac_gpu_ctx* ctx, char handle_out[USAC_PEER_HANDLE_BYTES]);
+int usac_gpu_peer_attach(usac_gpu_ctx* ctx, const char* handles /* nranks x USAC_PEER_HANDLE_BYTES */, int rank, int nranks);
+int usac_gpu_peer_window(usac_gpu_ctx* ctx, void** window_out);
+int usac_gpu_peer_attach_ptrs(usac_gpu_ctx* ctx, void* const* windows /* [nranks], windows[rank] = own */, int rank, int nranks);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 /* device time (ms, CUDA events on ctx's stream) and launch count of the kernels of the last usac_gpu_fit/score call */
 int usac_gpu_last_timing(const usac_gpu_ctx* ctx, float* total_ms, float* score_kernel_ms, int* launches, int* score_launches);

@@ -200,6 +200,29 @@ class GpuContext:
     def nccl_init(self, unique_id, rank, nranks):
         self._check(self.L.usac_gpu_nccl_init(self.h, unique_id, rank, nranks), "nccl_init")
 
+    PEER_HANDLE_BYTES = 64
+
+    def peer_export(self):
+        """-> the CUDA IPC handle (bytes) of this rank's exchange window; all-gather the handles and call peer_attach."""
+        buf = C.create_string_buffer(self.PEER_HANDLE_BYTES)
+        self._check(self.L.usac_gpu_peer_export(self.h, buf), "peer_export")
+        return buf.raw
+
+    def peer_attach(self, handles, rank, nranks):
+        """handles: the nranks IPC handles in rank order (bytes objects or one concatenated bytes)."""
+        blob = handles if isinstance(handles, (bytes, bytearray)) else b"".join(handles)
+        assert len(blob) == nranks * self.PEER_HANDLE_BYTES
+        self._check(self.L.usac_gpu_peer_attach(self.h, bytes(blob), rank, nranks), "peer_attach")
+
+    def peer_window(self):
+        p = C.c_void_p()
+        self._check(self.L.usac_gpu_peer_window(self.h, C.byref(p)), "peer_window")
+        return p.value
+
+    def peer_attach_ptrs(self, windows, rank, nranks):
+        arr = (C.c_void_p * nranks)(*windows)
+        self._check(self.L.usac_gpu_peer_attach_ptrs(self.h, arr, rank, nranks), "peer_attach_ptrs")
+
 
 def nccl_unique_id():
     buf = C.create_string_buffer(128)

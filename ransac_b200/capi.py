@@ -98,6 +98,10 @@ def load():
     L.usac_gpu_set_allgather.argtypes = [vp, ALLGATHER_FN, vp]
     L.usac_gpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.usac_gpu_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.usac_gpu_peer_export.argtypes = [vp, C.c_char_p]
+    L.usac_gpu_peer_attach.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.usac_gpu_peer_window.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.usac_gpu_peer_attach_ptrs.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int]
     L.usac_gpu_last_timing.argtypes = [vp, fp, fp, ip, ip]
     L.usac_gpu_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     for name in declared_symbols():

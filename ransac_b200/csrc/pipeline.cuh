@@ -42,7 +42,64 @@ struct RoundArgs {
     unsigned before_sprt;        // model.hpp:39 max_hypothesis_test_before_sprt
     int limit_remaining;         // 1: samples the sequential loop can no longer reach (index >= max_iters - iters at the start of
                                  // the round; the bound never grows) are not solved or scored
+    // hypothesis sharding over peer memory (NVLink): the reduce kernels store this rank's per-sample scores straight into every
+    // rank's exchange window and raise a flag there; select_kernel waits for the flags of all ranks. No collective call.
+    void* const* peer_win;       // [nranks] exchange windows (PeerWindow layout below), own included; nullptr = exchange by the host's hook
+    void* peer_self;             // this rank's window
+    unsigned peer_seq;           // sequence number of this round (same on every rank, grows by one per round for the life of the windows)
+    unsigned peer_cap;           // uint2 entries per parity buffer
+    unsigned* peer_counter;      // CTAs of the reduce kernel that have stored their part
+    int* peer_error;             // set when a wait timed out
 };
+
+// Exchange window of one rank: flags[2][64] (sequence number last published by rank r, per parity), then two buffers of
+// peer_cap packed scores laid out [rank][slot][ceil(K / nranks)]. Two parities: a rank can be at most one round ahead of the
+// slowest one, because it needs everybody's part of round s before it can publish round s + 1.
+#define USAC_PEER_HEADER_BYTES 1024
+#define USAC_PEER_MAX_RANKS 64
+__device__ __forceinline__ uint2* peer_data(void* win, unsigned seq, unsigned cap) {
+    return reinterpret_cast<uint2*>(reinterpret_cast<char*>(win) + USAC_PEER_HEADER_BYTES) + (size_t)(seq & 1u) * cap;
+}
+__device__ __forceinline__ unsigned* peer_flags(void* win, unsigned seq) {
+    return reinterpret_cast<unsigned*>(win) + (seq & 1u) * USAC_PEER_MAX_RANKS;
+}
+// one packed score -> the same place in every rank's window
+__device__ __forceinline__ void peer_store(const RoundArgs& a, size_t idx, uint2 v) {
+    for (int r = 0; r < a.nranks; r++) peer_data(a.peer_win[r], a.peer_seq, a.peer_cap)[idx] = v;
+}
+// end of a reduce kernel (every thread of every CTA calls it): the last CTA to arrive raises this rank's flag everywhere
+__device__ __forceinline__ void peer_publish(const RoundArgs& a) {
+    __threadfence_system();                                          // this thread's remote stores are visible system-wide ...
+    __syncthreads();                                                 // ... before thread 0 counts the CTA in
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(a.peer_counter, 1u) == total - 1u) {
+            *a.peer_counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < a.nranks; r++) {
+                unsigned* f = peer_flags(a.peer_win[r], a.peer_seq) + a.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f), "r"(a.peer_seq) : "memory");
+            }
+        }
+    }
+}
+// start of select_kernel: until every rank has published this round (2 s limit: a rank that never arrives must not hang the GPU)
+__device__ __forceinline__ void peer_wait(const RoundArgs& a) {
+    if ((int)threadIdx.x < a.nranks) {
+        const unsigned* f = peer_flags(a.peer_self, a.peer_seq) + threadIdx.x;
+        unsigned long long t0 = 0, t1 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - a.peer_seq) >= 0) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { *a.peer_error = 1; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Guard-band constants of the fast scoring path (see score.cuh). u = 2^-24. All bounds are deliberately loose
@@ -403,26 +460,29 @@ __device__ __forceinline__ bool score_bigger(int ca, float sa, int cb, float sb)
 
 __global__ void reduce_kernel(const RoundArgs a) {
     const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.K) return;
-    if (a.nranks > 1 && (j % a.nranks) != a.rank) return;
-    const int k = a.nmodels[(size_t)slot * a.K + j];
-    const int off = a.offsets[(size_t)slot * a.K + j];
-    int bc = -1, bi = 0;
-    float bs = 0.f;
-    for (int i = 0; i < k; i++) {
-        int c = 0;
-        float s = 0.f;
-        for (int ch = 0; ch < a.nchunks; ch++) {
-            const size_t o = ((size_t)slot * a.nchunks + ch) * a.mstride + off + i;
-            c += a.part_cnt[o];
-            s += a.part_sum[o];
+    if (j < a.K && !(a.nranks > 1 && (j % a.nranks) != a.rank)) {
+        const int k = a.nmodels[(size_t)slot * a.K + j];
+        const int off = a.offsets[(size_t)slot * a.K + j];
+        int bc = -1, bi = 0;
+        float bs = 0.f;
+        for (int i = 0; i < k; i++) {
+            int c = 0;
+            float s = 0.f;
+            for (int ch = 0; ch < a.nchunks; ch++) {
+                const size_t o = ((size_t)slot * a.nchunks + ch) * a.mstride + off + i;
+                c += a.part_cnt[o];
+                s += a.part_sum[o];
+            }
+            if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
         }
-        if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
+        if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }                       // no model: midx 3 marks "nothing to compare"
+        const int per_rank = (a.K + a.nranks - 1) / a.nranks;
+        const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + j / a.nranks) : ((size_t)slot * a.K + j);
+        const uint2 v = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+        if (a.peer_win) peer_store(a, (size_t)a.rank * gridDim.y * per_rank + dst, v);
+        else a.sample_scores[dst] = v;
     }
-    if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }                       // no model: midx 3 marks "nothing to compare"
-    const int per_rank = (a.K + a.nranks - 1) / a.nranks;
-    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + j / a.nranks) : ((size_t)slot * a.K + j);
-    a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+    if (a.peer_win) peer_publish(a);
 }
 
 // The same for many point chunks (one large problem: hundreds of partials per model): a CTA of 8 warps owns 32 samples
@@ -450,19 +510,23 @@ __global__ void __launch_bounds__(256) reduce_chunks_kernel(const RoundArgs a) {
         s_s[warp][i][lane] = s;
     }
     __syncthreads();
-    if (warp != 0 || !mine) return;
-    int bc = -1, bi = 0;
-    float bs = 0.f;
-    for (int i = 0; i < k; i++) {
-        int c = 0;
-        float s = 0.f;
-        for (int w = 0; w < 8; w++) { c += s_c[w][i][lane]; s += s_s[w][i][lane]; }
-        if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
+    if (warp == 0 && mine) {
+        int bc = -1, bi = 0;
+        float bs = 0.f;
+        for (int i = 0; i < k; i++) {
+            int c = 0;
+            float s = 0.f;
+            for (int w = 0; w < 8; w++) { c += s_c[w][i][lane]; s += s_s[w][i][lane]; }
+            if (bc < 0 || score_bigger(c, s, bc, bs)) { bc = c; bs = s; bi = i; }
+        }
+        if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }
+        const int per_rank = (a.K + a.nranks - 1) / a.nranks;
+        const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + own) : ((size_t)slot * a.K + j);
+        const uint2 v = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+        if (a.peer_win) peer_store(a, (size_t)a.rank * gridDim.y * per_rank + dst, v);
+        else a.sample_scores[dst] = v;
     }
-    if (bc < 0) { bc = 0; bs = 0.f; bi = 3; }
-    const int per_rank = (a.K + a.nranks - 1) / a.nranks;
-    const size_t dst = (a.nranks > 1) ? ((size_t)slot * per_rank + own) : ((size_t)slot * a.K + j);
-    a.sample_scores[dst] = make_uint2((unsigned)bc | ((unsigned)bi << 30), __float_as_uint(bs));
+    if (a.peer_win) peer_publish(a);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -482,13 +546,17 @@ __global__ void __launch_bounds__(256) select_kernel(const RoundArgs a, const ui
     const int slot = blockIdx.x;
     const int pid = a.active[slot];
     FitState& st = a.state[pid];
+    if (a.peer_win) peer_wait(a);                                   // every rank's scores of this round have landed in this rank's window
     if (st.done) return;                                            // a round enqueued ahead of the host's knowledge: the fit has already ended
     const ProblemDesc pd = a.prob[pid];
     const unsigned* table = a.term_tables + pd.term_off;
     const int K = a.K, R = a.nranks;
     const int per_rank = (K + R - 1) / R;
     const uint2* sc = scores_all;
+    const bool peer = a.peer_win != nullptr;
+    if (peer) sc = peer_data(a.peer_self, a.peer_seq, a.peer_cap);
     auto load = [&](int j) -> uint2 {
+        if (peer) return __ldcv(sc + ((size_t)(j % R) * gridDim.x + slot) * per_rank + j / R);   // written by other GPUs: never from L1
         return (R > 1) ? sc[((size_t)(j % R) * gridDim.x + slot) * per_rank + j / R] : sc[(size_t)slot * K + j];
     };
     const unsigned long long carry_key = score_key(st.best_cnt, st.best_sum);

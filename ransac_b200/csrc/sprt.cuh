@@ -1,9 +1,13 @@
 // sprt.cuh - Wald SPRT verification (usac/sprt.hpp) on the device.
 //
-// sprt_walk_kernel: one thread per model of the round walks the shuffled point pool (sprt.hpp:93-107; the points are stored
-// once in pool order, so the walk is a contiguous stream) from its start offset (cursor + 32*q) mod N, updating the
-// likelihood ratio lambda in double exactly as sprt.hpp:205-234 does (lambda *= delta/eps for an inlier, (1-delta)/(1-eps)
-// otherwise; reject when lambda > A), under the test (eps, delta, A) frozen for the round. Errors come from the packed fast
+// Two kernels per round. sprt_walk_kernel: one thread per model of the round walks the first SPRT_HEAD points of its stretch of the
+// shuffled point pool (sprt.hpp:93-107; the points are stored once in pool order, so the walk is a contiguous stream) from its start
+// offset (cursor + 32*q) mod N, updating the likelihood ratio lambda in double exactly as sprt.hpp:205-234 does (lambda *= delta/eps
+// for an inlier, (1-delta)/(1-eps) otherwise; reject when lambda > A), under the test (eps, delta, A) frozen for the round. Almost all
+// models of a round are rejected there. The few that are not (and the rejected models of the first hypotheses, which count every
+// point) are handed to sprt_tail_kernel: one WARP per model, 64 points per step (lane = point, exact decisions, two ballots), then
+// the same multiplications in the same order, replicated in every lane - a model that passes the test walks all N points in
+// N/64 warp steps instead of N thread steps (C3: 2.5 ms -> 0.1 ms for the round). Errors come from the packed fast
 // evaluator with the same guard band + strict re-evaluation as the scoring kernel, so every inlier decision - hence
 // tested_pts / tested_inl - is bit-exact. Models rejected during the first 20 hypotheses finish counting their inliers
 // (sprt.hpp:243-257).
@@ -12,6 +16,11 @@
 #include "score.cuh"
 
 struct SprtModelResult { int good, tested_inl, tested_pts, full_inl; };
+// a walk handed from the thread-per-model head to the warp-per-model tail
+struct SprtCarry { int q, tp, tin, rejected; double lambda; unsigned start; int count_all; };
+#ifndef USAC_SPRT_HEAD
+#define USAC_SPRT_HEAD 64            // points a model walks in the thread-per-model kernel (even)
+#endif
 
 __host__ inline void sprt_init_state(FitState& s, int est) {
     // sprt.hpp:114-153 initial (epsilon, delta); A is designed on the host in usac_gpu_fit
@@ -55,12 +64,13 @@ __device__ __forceinline__ void decide_pair(const FastModel<EST>& fm, const floa
 
 // One model's walk: the likelihood-ratio test of sprt.hpp:205-234 from pool position `start`, then - when `count_all` and the model
 // was rejected - the rest of the pool (sprt.hpp:243-257).
+// Returns true when the walk is complete (`res` final); false when it has to be continued by a warp (`carry` filled, carry.q not set).
 template <int EST>
-__device__ __forceinline__ SprtModelResult sprt_walk_one(const float* __restrict__ rec, const float* __restrict__ P, int n, unsigned start,
-                                                         double eps, double delta, double A, bool count_all) {
+__device__ __forceinline__ bool sprt_walk_one(const float* __restrict__ rec, const float* __restrict__ P, int n, unsigned start,
+                                              double eps, double delta, double A, bool count_all, int head, SprtModelResult& res, SprtCarry& carry) {
     FastModel<EST> fm;
     fm.load(rec);
-    SprtModelResult res = {0, 0, 0, 0};
+    res = SprtModelResult{0, 0, 0, 0};
     const double r_in = __ddiv_rn(delta, eps), r_out = __ddiv_rn(__dsub_rn(1.0, delta), __dsub_rn(1.0, eps));
     auto wrap = [n](int v) { while (v >= n) v -= n; return v; };      // n may be as small as the minimal sample
     int idx = (int)(start % (unsigned)n);
@@ -70,7 +80,7 @@ __device__ __forceinline__ SprtModelResult sprt_walk_one(const float* __restrict
     PoolPoint<EST> pa, pb, na, nb;
     pa.load(P, idx); pb.load(P, wrap(idx + 1));
 #pragma unroll 1
-    while (tp < n) {
+    while (tp < n && tp < head) {
         const int i0 = idx, i1 = wrap(idx + 1);
         na.load(P, wrap(idx + 2)); nb.load(P, wrap(idx + 3));          // next pair in flight while this one is evaluated
         bool in0, in1;
@@ -87,6 +97,10 @@ __device__ __forceinline__ SprtModelResult sprt_walk_one(const float* __restrict
         pa = na; pb = nb; idx = wrap(idx + 2);
     }
     res.good = good; res.tested_inl = tin; res.tested_pts = tp; res.full_inl = tin;
+    if ((good && tp < n) || (!good && count_all && head < n)) {       // unfinished test, or a long count: a warp takes over
+        carry.tp = tp; carry.tin = tin; carry.rejected = good ? 0 : 1; carry.lambda = lambda; carry.start = start; carry.count_all = count_all ? 1 : 0;
+        return false;
+    }
     if (!good && count_all) {
         // sprt.hpp:243-257: keep counting from the point after the rejecting one
         int pos = (int)(((unsigned long long)start + (unsigned long long)tp) % (unsigned long long)n);
@@ -103,11 +117,70 @@ __device__ __forceinline__ SprtModelResult sprt_walk_one(const float* __restrict
         }
         res.full_inl = tin + c;
     }
+    return true;
+}
+
+// The rest of a walk by one warp: 64 pool points per step (lane l decides points base + l and base + 32 + l), then the 64
+// multiplications of sprt.hpp:205-234 in pool order, identically in every lane.
+template <int EST>
+__device__ __forceinline__ SprtModelResult sprt_walk_warp(const float* __restrict__ rec, const float* __restrict__ P, int n, const SprtCarry& cy,
+                                                          double eps, double delta, double A) {
+    const int lane = threadIdx.x & 31;
+    FastModel<EST> fm;
+    fm.load(rec);
+    const double r_in = __ddiv_rn(delta, eps), r_out = __ddiv_rn(__dsub_rn(1.0, delta), __dsub_rn(1.0, eps));
+    const unsigned un = (unsigned)n;
+    int tp = cy.tp, tin = cy.tin;
+    double lambda = cy.lambda;
+    bool good = !cy.rejected;
+    auto decide64 = [&](int done) -> unsigned long long {
+        const unsigned base = (unsigned)(((unsigned long long)cy.start + (unsigned long long)done) % un);
+        const int i0 = (int)((base + (unsigned)lane) % un), i1 = (int)((base + 32u + (unsigned)lane) % un);
+        PoolPoint<EST> a, b;
+        a.load(P, i0); b.load(P, i1);
+        bool in0, in1;
+        decide_pair<EST>(fm, rec, P, n, a, b, i0, i1, in0, in1);
+        return (unsigned long long)__ballot_sync(0xffffffffu, in0) | ((unsigned long long)__ballot_sync(0xffffffffu, in1) << 32);
+    };
+    if (good) {
+#pragma unroll 1
+        while (tp < n) {
+            const int cnt = min(64, n - tp);
+            const unsigned long long m = decide64(tp);
+            int rej_k = -1;
+#pragma unroll
+            for (int k = 0; k < 64; k++) {
+                const double ln = __dmul_rn(lambda, ((m >> k) & 1ull) ? r_in : r_out);
+                const bool live = k < cnt && rej_k < 0;
+                if (live && ln > A) rej_k = k;
+                else if (live) lambda = ln;
+            }
+            if (rej_k >= 0) {
+                tin += __popcll(m & ((2ull << rej_k) - 1ull)); tp += rej_k + 1; good = false;
+                break;
+            }
+            tin += __popcll(cnt == 64 ? m : (m & ((1ull << cnt) - 1ull))); tp += cnt;
+        }
+    }
+    SprtModelResult res;
+    res.good = good; res.tested_inl = tin; res.tested_pts = tp; res.full_inl = tin;
+    if (!good && cy.count_all) {                                      // sprt.hpp:243-257
+        int done = tp, c = 0;
+#pragma unroll 1
+        while (done < n) {
+            const int cnt = min(64, n - done);
+            const unsigned long long m = decide64(done);
+            c += __popcll(cnt == 64 ? m : (m & ((1ull << cnt) - 1ull)));
+            done += cnt;
+        }
+        res.full_inl = tin + c;
+    }
     return res;
 }
 
 template <int EST>
-__global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const float* __restrict__ pool_pts) {
+__global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const float* __restrict__ pool_pts, SprtCarry* __restrict__ carry,
+                                                       unsigned* __restrict__ carry_count) {
     const int slot = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.K * a.S) return;
     const int j = q / a.S, i = q % a.S;
@@ -120,16 +193,60 @@ __global__ void __launch_bounds__(64) sprt_walk_kernel(const RoundArgs a, const 
     const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
     const unsigned start = (unsigned)(((unsigned long long)st.sprt_cursor + 32ull * (unsigned long long)q) % (unsigned long long)pd.n);
     const bool count_all = (unsigned long long)st.samples_drawn + (unsigned long long)j < (unsigned long long)a.before_sprt;
-    *out = sprt_walk_one<EST>(rec, P, pd.n, start, st.sprt_eps, st.sprt_delta, st.sprt_A, count_all);
+    SprtModelResult res;
+    SprtCarry cy;
+    if (sprt_walk_one<EST>(rec, P, pd.n, start, st.sprt_eps, st.sprt_delta, st.sprt_A, count_all, USAC_SPRT_HEAD, res, cy)) { *out = res; return; }
+    cy.q = slot * a.mstride + q;
+    carry[atomicAdd(carry_count, 1u)] = cy;
 }
 
-// SPRT::verifyModelAndGetModelScore for caller-supplied models (usac_gpu_sprt_verify): one thread per model
+// the handed-over walks of a round: one warp each (grid-stride over the list)
+template <int EST>
+__global__ void __launch_bounds__(128) sprt_tail_kernel(const RoundArgs a, const float* __restrict__ pool_pts, const SprtCarry* __restrict__ carry,
+                                                        const unsigned* __restrict__ carry_count) {
+    const int warps = gridDim.x * (blockDim.x >> 5), lane = threadIdx.x & 31;
+    const unsigned count = *carry_count;
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
+        const SprtCarry cy = carry[e];
+        const int slot = cy.q / a.mstride, q = cy.q % a.mstride;
+        const int j = q / a.S, i = q % a.S;
+        const int pid = a.active[slot];
+        const ProblemDesc pd = a.prob[pid];
+        const FitState& st = a.state[pid];
+        const float* rec = a.recs + ((size_t)slot * a.mstride + a.offsets[(size_t)slot * a.K + j] + i) * USAC_REC_STRIDE;
+        const float* P = pool_pts + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
+        const SprtModelResult res = sprt_walk_warp<EST>(rec, P, pd.n, cy, st.sprt_eps, st.sprt_delta, st.sprt_A);
+        if (lane == 0) a.sprt_res[cy.q] = res;
+    }
+}
+
+// SPRT::verifyModelAndGetModelScore for caller-supplied models (usac_gpu_sprt_verify): the same two stages
 template <int EST>
 __global__ void __launch_bounds__(64) sprt_verify_kernel(const float* __restrict__ recs, int M, const float* __restrict__ P, int n, const unsigned* __restrict__ start,
-                                                         const int* __restrict__ count_all, double eps, double delta, double A, SprtModelResult* __restrict__ out) {
+                                                         const int* __restrict__ count_all, double eps, double delta, double A, SprtModelResult* __restrict__ out,
+                                                         SprtCarry* __restrict__ carry, unsigned* __restrict__ carry_count) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= M) return;
-    out[q] = sprt_walk_one<EST>(recs + (size_t)q * USAC_REC_STRIDE, P, n, start[q], eps, delta, A, count_all ? count_all[q] != 0 : false);
+    SprtModelResult res;
+    SprtCarry cy;
+    if (sprt_walk_one<EST>(recs + (size_t)q * USAC_REC_STRIDE, P, n, start[q], eps, delta, A, count_all ? count_all[q] != 0 : false, USAC_SPRT_HEAD, res, cy)) {
+        out[q] = res;
+        return;
+    }
+    cy.q = q;
+    carry[atomicAdd(carry_count, 1u)] = cy;
+}
+template <int EST>
+__global__ void __launch_bounds__(128) sprt_verify_tail_kernel(const float* __restrict__ recs, const float* __restrict__ P, int n, double eps, double delta, double A,
+                                                               SprtModelResult* __restrict__ out, const SprtCarry* __restrict__ carry,
+                                                               const unsigned* __restrict__ carry_count) {
+    const int warps = gridDim.x * (blockDim.x >> 5), lane = threadIdx.x & 31;
+    const unsigned count = *carry_count;
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += warps) {
+        const SprtCarry cy = carry[e];
+        const SprtModelResult res = sprt_walk_warp<EST>(recs + (size_t)cy.q * USAC_REC_STRIDE, P, n, cy, eps, delta, A);
+        if (lane == 0) out[cy.q] = res;
+    }
 }
 
 // per-model (count, sum) of a fully scored round, in (sample, root) slot order q = j*S + i (count -1 = no such model):

@@ -45,6 +45,22 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// pinned host staging (device -> host copies into pageable memory block the calling thread until the copy has run)
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct SideUsed { size_t knn = 0, grid = 0, cell_start = 0, cursors = 0, pool = 0; };   // elements used in the appended side arrays
 
 struct usac_gpu_ctx {
@@ -82,6 +98,13 @@ struct usac_gpu_ctx {
     DevBuf<float> d_models_raw, d_recs, d_part_sum;
     DevBuf<uint2> d_scores, d_scores_all;
     DevBuf<SprtModelResult> d_sprt_res;
+    DevBuf<SprtCarry> d_sprt_carry;          // walks handed from sprt_walk_kernel to sprt_tail_kernel
+    DevBuf<unsigned> d_sprt_count;
+    PinnedBuf<int> h_rp_nmodels;              // replay path: the round's results on the host
+    PinnedBuf<SprtModelResult> h_rp_res;
+    PinnedBuf<int2> h_rp_scores;
+    PinnedBuf<float> h_rp_models;
+    PinnedBuf<FitState> h_rp_state;
     DevBuf<int2> d_model_scores;
     DevBuf<float> d_pool_pts;          // the points in SPRT pool order (same offsets as d_aos)
     DevBuf<unsigned long long> d_grid_keys;   // grid build scratch: 2n keys
@@ -103,6 +126,17 @@ struct usac_gpu_ctx {
     void* allgather_user = nullptr;
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
+    // exchange over peer memory (usac_gpu_peer_*): this rank's window, the windows of all ranks, round sequence number
+    void* peer_self = nullptr;
+    unsigned peer_cap = 0;                    // uint2 entries per parity buffer
+    std::vector<void*> peer_opened;           // windows mapped with cudaIpcOpenMemHandle (closed in destroy)
+    DevBuf<void*> d_peer_win;
+    DevBuf<unsigned> d_peer_counter;
+    DevBuf<int> d_peer_error;
+    int* h_peer_error = nullptr;              // pinned
+    int peer_rank = -1, peer_nranks = 0;
+    unsigned peer_seq = 0;
+    unsigned long long peer_rounds = 0;       // rounds exchanged through the windows (diagnostics)
     // termination tables of the last fit (rebuilt only when (n, m, confidence, max_iterations) change)
     std::map<std::tuple<int, int, float, unsigned>, std::vector<unsigned>> term_cache;
     std::vector<long long> term_signature;   // what d_term currently holds: (m, confidence bits, max_iterations, n of every problem)
@@ -182,6 +216,10 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (void* w : c->peer_opened) cudaIpcCloseMemHandle(w);
+    if (c->peer_self) cudaFree(c->peer_self);
+    if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
+    c->d_peer_win.release(); c->d_peer_counter.release(); c->d_peer_error.release();
     if (c->nccl_comm && c->nccl_lib) {
         typedef int (*destroy_fn)(void*);
         destroy_fn f = (destroy_fn)dlsym(c->nccl_lib, "ncclCommDestroy");
@@ -192,7 +230,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     c->d_pool.release(); c->d_cursors.release(); c->d_growth.release(); c->d_term.release();
     c->d_samples.release(); c->d_nmodels.release(); c->d_offsets.release(); c->d_mvalid.release(); c->d_part_cnt.release();
     c->d_seeds.release(); c->d_table.release(); c->d_models_raw.release(); c->d_recs.release(); c->d_part_sum.release();
-    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release(); c->d_items.release(); c->d_item_count.release();
+    c->d_scores.release(); c->d_scores_all.release(); c->d_sprt_res.release(); c->d_sprt_carry.release(); c->d_sprt_count.release(); c->h_rp_nmodels.release(); c->h_rp_res.release(); c->h_rp_scores.release(); c->h_rp_models.release(); c->h_rp_state.release(); c->d_model_scores.release(); c->d_pool_pts.release(); c->d_grid_keys.release(); c->d_grid_ints.release(); c->d_grid_temp.release(); c->d_knn_cells.release(); c->d_knn_pts.release(); c->d_work.release(); c->d_items.release(); c->d_item_count.release();
     c->d_q_models.release(); c->d_q_recs.release(); c->d_q_sum.release(); c->d_q_err.release(); c->d_q_cnt.release(); c->d_q_ids.release(); c->d_q_ids2.release(); c->d_q_ok.release(); c->d_q_model2.release(); c->d_lo_ids_a.release(); c->d_lo_ids_b.release(); c->d_lo_small.release(); c->d_lo_io.release();
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -1215,11 +1253,21 @@ static void launch_solve(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
     }
     c->last_launches++;
 }
+// warps of the tail kernels: one per handed-over walk, at most 8 per SM (a walk is a latency chain, not a throughput problem)
+static int sprt_tail_blocks(const usac_gpu_ctx* c, size_t walks) {
+    return (int)std::max<size_t>(1, std::min<size_t>((walks + 3) / 4, (size_t)c->prop.multiProcessorCount * 2));
+}
 template <int EST>
-static void launch_walk(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+static int launch_walk(usac_gpu_ctx* c, const RoundArgs& a, int slots) {
+    const size_t walks = (size_t)slots * a.mstride;
+    CUDA_TRY(c, c->d_sprt_carry.ensure(walks));
+    CUDA_TRY(c, c->d_sprt_count.ensure(1));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_sprt_count.p, 0, sizeof(unsigned), c->stream));
     dim3 g((a.K * a.S + 63) / 64, slots);
-    sprt_walk_kernel<EST><<<g, 64, 0, c->stream>>>(a, c->d_pool_pts.p);
-    c->last_launches++;
+    sprt_walk_kernel<EST><<<g, 64, 0, c->stream>>>(a, c->d_pool_pts.p, c->d_sprt_carry.p, c->d_sprt_count.p);
+    sprt_tail_kernel<EST><<<sprt_tail_blocks(c, walks), 128, 0, c->stream>>>(a, c->d_pool_pts.p, c->d_sprt_carry.p, c->d_sprt_count.p);
+    c->last_launches += 2;
+    return USAC_OK;
 }
 
 extern "C" void usac_prosac_growth_function(unsigned n, unsigned sample_size, unsigned* out) {
@@ -1255,7 +1303,8 @@ extern "C" int usac_gpu_lo_model_score(usac_gpu_ctx* c, int problem, const usac_
 template <int EST>
 static void launch_sprt_verify(usac_gpu_ctx* c, const float* recs, int M, const float* P, int n, const unsigned* start, const int* count_all,
                                double eps, double delta, double A, SprtModelResult* out) {
-    sprt_verify_kernel<EST><<<(M + 63) / 64, 64, 0, c->stream>>>(recs, M, P, n, start, count_all, eps, delta, A, out);
+    sprt_verify_kernel<EST><<<(M + 63) / 64, 64, 0, c->stream>>>(recs, M, P, n, start, count_all, eps, delta, A, out, c->d_sprt_carry.p, c->d_sprt_count.p);
+    sprt_verify_tail_kernel<EST><<<sprt_tail_blocks(c, (size_t)M), 128, 0, c->stream>>>(recs, P, n, eps, delta, A, out, c->d_sprt_carry.p, c->d_sprt_count.p);
 }
 
 extern "C" int usac_gpu_sprt_verify(usac_gpu_ctx* c, int problem, const float* models, int M, float threshold, double epsilon, double delta, double A,
@@ -1270,6 +1319,9 @@ extern "C" int usac_gpu_sprt_verify(usac_gpu_ctx* c, int problem, const float* m
     CUDA_TRY(c, c->d_q_models.ensure((size_t)M * w));
     CUDA_TRY(c, c->d_q_recs.ensure((size_t)M * USAC_REC_STRIDE));
     CUDA_TRY(c, c->d_sprt_res.ensure((size_t)M));
+    CUDA_TRY(c, c->d_sprt_carry.ensure((size_t)M));
+    CUDA_TRY(c, c->d_sprt_count.ensure(1));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_sprt_count.p, 0, sizeof(unsigned), c->stream));
     CUDA_TRY(c, c->d_q_ids.ensure((size_t)std::max(2 * M, d.n + 1)));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_q_models.p, models, sizeof(float) * w * M, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_q_ids.p, start, sizeof(unsigned) * M, cudaMemcpyHostToDevice, c->stream));
@@ -1292,23 +1344,62 @@ extern "C" int usac_gpu_sprt_verify(usac_gpu_ctx* c, int problem, const float* m
 }
 
 // Rounds with SPRT and/or PROSAC termination (host_replay.hpp): device = sample, solve, verify/score; host = replay.
+static void print_marks(usac_gpu_ctx* c) {
+    if (c->marks_used < 2) return;
+    std::map<std::string, double> tot;
+    for (size_t i = 1; i < c->marks_used; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->marks[i - 1].second, c->marks[i].second);
+        tot[c->marks[i].first] += ms * 1e3;
+    }
+    std::string line = "usac_gpu_fit kernels (us, device time between launches):";
+    for (auto& kv : tot) { char buf[96]; snprintf(buf, sizeof(buf), " %s=%.0f", kv.first.c_str(), kv.second); line += buf; }
+    fprintf(stderr, "%s\n", line.c_str());
+}
+
 static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results, int K) {
     const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
     const bool is_prosac = cfg->sampler.sampler == USAC_SAMPLER_PROSAC, is_sprt = cfg->sprt != 0;
     const float log_1_p = (float)logf(1 - cfg->confidence);
     const int KS = K * S;
     const unsigned before_sprt = cfg->max_hypothesis_test_before_sprt ? cfg->max_hypothesis_test_before_sprt : 20u;   // model.hpp:39
-    std::vector<int> h_nmodels(K), ids;
-    std::vector<SprtModelResult> h_res(KS);
-    std::vector<int2> h_scores(KS);
-    std::vector<float> h_models((size_t)KS * 9);
+    std::vector<int> ids;
     std::vector<unsigned char> mask;
     std::vector<unsigned> growth;
-    int rc = ensure_round_buffers(c, 1, K, 1, 1);
+    // Solve-ahead: with the uniform sampler a sample depends on its hypothesis id only, so the minimal solver runs for G rounds of K
+    // samples at once (the five-point solver is a latency chain of ~0.7 ms per warp: 512 warps leave the GPU empty) and each round
+    // verifies its own K of them under its own frozen test - the semantics of rounds of K are untouched.
+    int G = 1;
+    if (is_sprt && !is_prosac && cfg->sampler.sampler == USAC_SAMPLER_UNIFORM) {
+        const char* e = getenv("USAC_GPU_SOLVE_AHEAD");
+        G = e ? std::max(1, atoi(e)) : (c->est == USAC_EST_ESSENTIAL ? 4 : 2);
+        while (G > 1 && (size_t)K * G > 8192) G--;
+    }
+    const int KB = K * G;                                         // samples per solved block
+    int rc = ensure_round_buffers(c, 1, KB, 1, 1);
     if (rc) return rc;
     CUDA_TRY(c, c->d_model_scores.ensure(KS));
+    CUDA_TRY(c, c->h_rp_nmodels.ensure(K));
+    CUDA_TRY(c, c->h_rp_res.ensure(KS));
+    CUDA_TRY(c, c->h_rp_scores.ensure(KS));
+    CUDA_TRY(c, c->h_rp_models.ensure((size_t)KS * 9));
+    CUDA_TRY(c, c->h_rp_state.ensure(1));
+    int* const h_nmodels = c->h_rp_nmodels.p;
+    SprtModelResult* const h_res = c->h_rp_res.p;
+    int2* const h_scores = c->h_rp_scores.p;
+    float* const h_models = c->h_rp_models.p;
+    // USAC_GPU_TRACE: host wall-clock split of the replay path on stderr (tables / enqueue / waiting for the round / replay / LO / mask)
+    static const bool trace = getenv("USAC_GPU_TRACE") != nullptr;
+    static const bool trace_kernels = trace && atoi(getenv("USAC_GPU_TRACE")) >= 2;
+#define RK(name) do { if (trace_kernels && c->marks_used < 4096) c->mark(name); } while (0)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count(); };
+    double t_tables = 0, t_enqueue = 0, t_wait = 0, t_replay = 0, t_lo = 0, t_mask = 0;
+    int n_rounds = 0, n_lo = 0, n_mask = 0;
 
     for (int p = 0; p < P; p++) {
+        const auto t_p0 = now();
         const ProblemDesc& pd = c->h_prob[p];
         const unsigned n = (unsigned)pd.n;
         FitState& hs = c->h_state[p];
@@ -1320,7 +1411,11 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         LoRunner lo;
         if (cfg->lo) { rc = lo.init(c, p, cfg); if (rc) return rc; }
         bool done = false;
+        int block_round = 0;                                       // rounds since the first solved block of this problem
+        t_tables += us(t_p0, now());
         while (!done && hs.iters < hs.max_iters) {
+            const auto t_r0 = now();
+            n_rounds++;
             if (is_prosac) hs.prosac_term_len = pterm.termination_length;
             if (is_sprt) { const SprtTestH& t = sprt.current(); hs.sprt_eps = t.epsilon; hs.sprt_delta = t.delta; hs.sprt_A = t.A; hs.sprt_cursor = sprt.cursor; }
             CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p + p, &hs, sizeof(FitState), cudaMemcpyHostToDevice, c->stream));
@@ -1333,28 +1428,46 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 rc = ensure_round_buffers(c, 1, K, nchunks, 1);
                 if (rc) return rc;
             }
+            RK("start");
+            // ---- sample + solve + records: once per block of G rounds ----
+            const int g = block_round % G;                       // this round's position in the solved block
+            if (g == 0) {
+                RoundArgs b;
+                fill_round_args(c, b, cfg->sampler, KB);
+                b.thr = cfg->threshold; b.confidence = cfg->confidence; b.max_iterations = cfg->max_iterations;
+                b.table_rows = cfg->sample_table_rows; b.nchunks = nchunks; b.sprt = cfg->sprt; b.pool = c->d_pool.p; b.sprt_res = c->d_sprt_res.p;
+                b.before_sprt = before_sprt;
+                launch_sampler(c, b, 1);
+                RK("sample");
+                switch (c->est) {
+                    case USAC_EST_LINE2D: launch_solve<USAC_EST_LINE2D>(c, b, 1); break;
+                    case USAC_EST_HOMOGRAPHY: launch_solve<USAC_EST_HOMOGRAPHY>(c, b, 1); break;
+                    case USAC_EST_FUNDAMENTAL: launch_solve<USAC_EST_FUNDAMENTAL>(c, b, 1); break;
+                    default: launch_solve<USAC_EST_ESSENTIAL>(c, b, 1); break;
+                }
+                RK("solve");
+                prepare_kernel<<<1, KB >= 1024 ? 1024 : 256, 0, c->stream>>>(b);
+                c->last_launches++;
+                RK("prepare");
+            }
+            block_round++;
+            // this round's view of the block: samples [g K, (g + 1) K); record offsets stay relative to the block
             RoundArgs a;
             fill_round_args(c, a, cfg->sampler, K);
             a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
             a.table_rows = cfg->sample_table_rows; a.nchunks = nchunks; a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
             a.before_sprt = before_sprt;
-            launch_sampler(c, a, 1);
-            switch (c->est) {
-                case USAC_EST_LINE2D: launch_solve<USAC_EST_LINE2D>(c, a, 1); break;
-                case USAC_EST_HOMOGRAPHY: launch_solve<USAC_EST_HOMOGRAPHY>(c, a, 1); break;
-                case USAC_EST_FUNDAMENTAL: launch_solve<USAC_EST_FUNDAMENTAL>(c, a, 1); break;
-                default: launch_solve<USAC_EST_ESSENTIAL>(c, a, 1); break;
-            }
-            prepare_kernel<<<1, 256, 0, c->stream>>>(a);
-            c->last_launches++;
+            a.nmodels = c->d_nmodels.p + (size_t)g * K; a.offsets = c->d_offsets.p + (size_t)g * K;
+            a.models_raw = c->d_models_raw.p + (size_t)g * KS * 9;
             if (is_sprt) {
                 switch (c->est) {
-                    case USAC_EST_LINE2D: launch_walk<USAC_EST_LINE2D>(c, a, 1); break;
-                    case USAC_EST_HOMOGRAPHY: launch_walk<USAC_EST_HOMOGRAPHY>(c, a, 1); break;
-                    case USAC_EST_FUNDAMENTAL: launch_walk<USAC_EST_FUNDAMENTAL>(c, a, 1); break;
-                    default: launch_walk<USAC_EST_ESSENTIAL>(c, a, 1); break;
+                    case USAC_EST_LINE2D: rc = launch_walk<USAC_EST_LINE2D>(c, a, 1); break;
+                    case USAC_EST_HOMOGRAPHY: rc = launch_walk<USAC_EST_HOMOGRAPHY>(c, a, 1); break;
+                    case USAC_EST_FUNDAMENTAL: rc = launch_walk<USAC_EST_FUNDAMENTAL>(c, a, 1); break;
+                    default: rc = launch_walk<USAC_EST_ESSENTIAL>(c, a, 1); break;
                 }
-                CUDA_TRY(c, cudaMemcpyAsync(h_res.data(), c->d_sprt_res.p, sizeof(SprtModelResult) * KS, cudaMemcpyDeviceToHost, c->stream));
+                if (rc) return rc;
+                CUDA_TRY(c, cudaMemcpyAsync(h_res, c->d_sprt_res.p, sizeof(SprtModelResult) * KS, cudaMemcpyDeviceToHost, c->stream));
             } else {
                 ScoreArgs sa{};
                 sa.pairs = c->d_pairs.p; sa.aos = c->d_aos.p; sa.prob = c->d_prob.p; sa.active = c->d_active.p; sa.recs = c->d_recs.p;
@@ -1363,14 +1476,20 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 launch_score(c, sa, 1, mblocks);
                 model_scores_kernel<<<dim3((KS + 127) / 128, 1), 128, 0, c->stream>>>(a, c->d_model_scores.p);
                 c->last_launches++;
-                CUDA_TRY(c, cudaMemcpyAsync(h_scores.data(), c->d_model_scores.p, sizeof(int2) * KS, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(h_scores, c->d_model_scores.p, sizeof(int2) * KS, cudaMemcpyDeviceToHost, c->stream));
             }
-            FitState dev_state;
-            CUDA_TRY(c, cudaMemcpyAsync(h_nmodels.data(), c->d_nmodels.p, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(c, cudaMemcpyAsync(h_models.data(), c->d_models_raw.p, sizeof(float) * KS * 9, cudaMemcpyDeviceToHost, c->stream));
+            RK("walk_or_score");
+            FitState& dev_state = *c->h_rp_state.p;
+            CUDA_TRY(c, cudaMemcpyAsync(h_nmodels, a.nmodels, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(h_models, a.models_raw, sizeof(float) * KS * 9, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(c, cudaMemcpyAsync(&dev_state, c->d_state.p + p, sizeof(FitState), cudaMemcpyDeviceToHost, c->stream));
+            RK("d2h");
+            const auto t_r1 = now();
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // the host sync of the round
             CUDA_TRY(c, cudaGetLastError());
+            const auto t_r2 = now();
+            t_enqueue += us(t_r0, t_r1); t_wait += us(t_r1, t_r2);
+            double t_lo_round = 0, t_mask_round = 0;
 
             // ---- replay the round in hypothesis order (ransac.cpp:58-139) ----
             const unsigned long long hyp0 = hs.samples_drawn;
@@ -1402,13 +1521,20 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                     if (inl > hs.best_cnt || (inl == hs.best_cnt && score > hs.best_sum)) {   // Score::bigger
                         float cand[9] = {0};
                         for (int k = 0; k < w; k++) cand[k] = h_models[(size_t)q * 9 + k];
-                        if (cfg->lo) { rc = lo.get_model_score(cand, inl, score); if (rc) return rc; }   // ransac.cpp:108-110
+                        if (cfg->lo) {                                                   // ransac.cpp:108-110
+                            const auto t0 = now();
+                            rc = lo.get_model_score(cand, inl, score);
+                            if (rc) return rc;
+                            t_lo_round += us(t0, now()); n_lo++;
+                        }
                         hs.best_cnt = inl; hs.best_sum = score; hs.best_hyp = (long long)(hyp0 + j); hs.best_midx = i;
                         for (int k = 0; k < w; k++) hs.best_model[k] = cand[k];
                         if (is_prosac) {                                                 // ransac.cpp:123-125
+                            const auto t0 = now();
                             rc = fetch_mask(c, p, hs.best_model, cfg->threshold, mask, ids);
                             if (rc) return rc;
                             hs.max_iters = pterm.update(hs.iters, mask, dev_state.prosac_largest_next);
+                            t_mask_round += us(t0, now()); n_mask++;
                         } else {
                             hs.max_iters = standard_termination_value((unsigned)inl, n, m, log_1_p, cfg->max_iterations);
                         }
@@ -1436,6 +1562,8 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
             hs.rounds++;
             hs.evals += evals;
             hs.useful_evals += useful;
+            t_lo += t_lo_round; t_mask += t_mask_round;
+            t_replay += us(t_r2, now()) - t_lo_round - t_mask_round;
         }
         hs.done = 1;
         usac_fit_result& r = results[p];
@@ -1446,6 +1574,11 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         if (cfg->lo) { r.lo_inner_iters = lo.inner_done; r.lo_iterative_iters = lo.iterative_done; }
         r.msac = is_sprt ? nanf("") : usac_msac_cost(pd.n, r.inliers, r.score, cfg->threshold);
     }
+#undef RK
+    if (trace_kernels) print_marks(c);
+    if (trace)
+        fprintf(stderr, "usac_gpu_fit[replay] P=%d K=%d rounds=%d: tables %.0f us, enqueue %.0f us, wait %.0f us, replay %.0f us, LO %.0f us (%d calls), "
+                "PROSAC mask+update %.0f us (%d)\n", P, K, n_rounds, t_tables, t_enqueue, t_wait, t_replay, t_lo, n_lo, t_mask, n_mask);
     return USAC_OK;
 }
 
@@ -1486,7 +1619,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     if (!(cfg->threshold > 0.f) || cfg->max_iterations == 0) return fail(c, USAC_ERR_ARG, "fit: threshold and max_iterations must be positive");
     const int nranks = std::max(cfg->nranks, 1), rank = cfg->rank;
     if (rank < 0 || rank >= nranks) return fail(c, USAC_ERR_ARG, "fit: rank out of range");
-    if (nranks > 1 && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_nccl_init or usac_gpu_set_allgather");
+    const bool peers_ready = c->peer_nranks == nranks && c->peer_rank == rank && c->peer_self;
+    if (nranks > 1 && !c->allgather && !peers_ready)
+        return fail(c, USAC_ERR_STATE, "fit: nranks > 1 needs usac_gpu_peer_attach, usac_gpu_nccl_init or usac_gpu_set_allgather");
     if (const char* why = check_sampler_cfg(cfg->sampler)) return fail(c, USAC_ERR_ARG, why);
     if (cfg->sampler.rng == USAC_RNG_TABLE && (!cfg->sample_table || cfg->sample_table_rows == 0)) return fail(c, USAC_ERR_ARG, "fit: empty sample table");
     if (cfg->lo != 0 && cfg->lo != 1 && cfg->lo != 2) return fail(c, USAC_ERR_ARG, "fit: lo must be 0 (none), 1 (InItLORsc) or 2 (InItFLORsc); GC / IRLS are not built");
@@ -1627,6 +1762,13 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p; a.done_out = c->d_done.p;
         a.limit_remaining = 1;
         a.items = c->d_items.p; a.item_count = c->d_item_count.p;
+        // exchange: through the peer windows when they are attached and the round fits, else through the host's hook (NCCL)
+        const bool use_peer = nranks > 1 && peers_ready && (size_t)nranks * slots * ((K + nranks - 1) / nranks) <= c->peer_cap;
+        if (nranks > 1 && !use_peer && !c->allgather) return fail(c, USAC_ERR_STATE, "fit: the round does not fit the peer windows and no all-gather hook is installed");
+        if (use_peer) {
+            a.peer_win = c->d_peer_win.p; a.peer_self = c->peer_self; a.peer_cap = c->peer_cap;
+            a.peer_counter = c->d_peer_counter.p; a.peer_error = c->d_peer_error.p;
+        }
         // One large problem (a 1M-point fit is ~1 ms of scoring per round): several rounds are enqueued back to back and the host
         // synchronises once per batch instead of once per round - a round that starts after the fit has ended solves and scores
         // nothing (limit_remaining) and select_kernel / winner_kernel skip it. With many small problems the host needs the
@@ -1658,12 +1800,13 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
                 launch_score(c, sa, slots, mblocks);
                 TK("score");
                 dim3 gr((K + 127) / 128, slots);
+                if (use_peer) { a.peer_seq = ++c->peer_seq; c->peer_rounds++; }
                 if (nchunks > 8) reduce_chunks_kernel<<<dim3(((K + nranks - 1) / nranks + 31) / 32, slots), 256, 0, c->stream>>>(a);
                 else reduce_kernel<<<gr, 128, 0, c->stream>>>(a);
                 c->last_launches++;
                 const uint2* scores = c->d_scores.p;
                 TK("reduce");
-                if (nranks > 1) {
+                if (nranks > 1 && !use_peer) {
                     const size_t bytes = (size_t)slots * (K / nranks) * sizeof(uint2);
                     int grc = c->allgather(c->allgather_user, c->d_scores.p, c->d_scores_all.p, bytes, (void*)c->stream);
                     if (grc) return fail(c, USAC_ERR_NCCL, "fit: all-gather failed");
@@ -1690,9 +1833,14 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
             CUDA_TRY(c, cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof(FitState), cudaMemcpyDeviceToHost, c->stream));
             cudaEventRecord(c->ev1, c->stream);
         }
+        if (use_peer) CUDA_TRY(c, cudaMemcpyAsync(c->h_peer_error, c->d_peer_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         const auto t_r1 = now();
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaGetLastError());
+        if (use_peer && *c->h_peer_error) {
+            cudaMemsetAsync(c->d_peer_error.p, 0, sizeof(int), c->stream);
+            return fail(c, USAC_ERR_NCCL, "fit: a rank did not publish its scores within 2 s (peer exchange)");
+        }
         t_enqueue += us(t_r0, t_r1); t_wait += us(t_r1, now()); n_rounds++;
         std::vector<int> next;
         for (int q = 0; q < slots; q++) if (!c->h_done[q]) next.push_back(active[q]);
@@ -1715,21 +1863,95 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
         r.useful_evals = s.useful_evals;
         r.msac = usac_msac_cost(c->h_prob[p].n, r.inliers, r.score, cfg->threshold);
     }
-    if (trace_kernels && c->marks_used > 1) {
-        std::map<std::string, double> tot;
-        for (size_t i = 1; i < c->marks_used; i++) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->marks[i - 1].second, c->marks[i].second);
-            tot[c->marks[i].first] += ms * 1e3;
-        }
-        std::string line = "usac_gpu_fit kernels (us, device time between launches):";
-        for (auto& kv : tot) { char buf[96]; snprintf(buf, sizeof(buf), " %s=%.0f", kv.first.c_str(), kv.second); line += buf; }
-        fprintf(stderr, "%s\n", line.c_str());
-    }
+    if (trace_kernels) print_marks(c);
     if (trace)
         fprintf(stderr, "usac_gpu_fit trace: %d problems, %d rounds: setup %.0f us, enqueue %.0f us, wait %.0f us, total %.0f us (GPU events: %.0f us, scoring %.0f us)\n",
                 P, n_rounds, us(t_begin, t_setup), t_enqueue, t_wait, us(t_begin, now()), c->last_total_ms * 1e3, c->last_score_ms * 1e3);
     return USAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Exchange over peer memory: every rank owns a window in its HBM that all ranks can write (CUDA IPC across processes, plain
+// pointers inside one process); the reduce kernels store the packed per-sample scores of a round straight into every window
+// over NVLink and select_kernel waits for the flags - no collective call, no extra launch (pipeline.cuh: peer_store /
+// peer_publish / peer_wait).
+// ------------------------------------------------------------------------------------------------------------------
+static int peer_make_window(usac_gpu_ctx* c) {
+    if (c->peer_self) return USAC_OK;
+    cudaSetDevice(c->device);
+    const unsigned cap = 1u << 17;                                  // 131072 packed scores per parity (1 MiB): rounds of up to cap samples x problems
+    const size_t bytes = USAC_PEER_HEADER_BYTES + 2ull * cap * sizeof(uint2);
+    CUDA_TRY(c, cudaMalloc(&c->peer_self, bytes));
+    CUDA_TRY(c, cudaMemset(c->peer_self, 0, bytes));
+    CUDA_TRY(c, c->d_peer_counter.ensure(1));
+    CUDA_TRY(c, c->d_peer_error.ensure(1));
+    CUDA_TRY(c, cudaMemset(c->d_peer_counter.p, 0, sizeof(unsigned)));
+    CUDA_TRY(c, cudaMemset(c->d_peer_error.p, 0, sizeof(int)));
+    if (!c->h_peer_error) CUDA_TRY(c, cudaMallocHost(&c->h_peer_error, sizeof(int)));
+    *c->h_peer_error = 0;
+    c->peer_cap = cap;
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_peer_export(usac_gpu_ctx* c, char handle_out[USAC_PEER_HANDLE_BYTES]) {
+    if (!c || !handle_out) return fail(c, USAC_ERR_ARG, "peer_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == USAC_PEER_HANDLE_BYTES, "USAC_PEER_HANDLE_BYTES is the size of a CUDA IPC handle");
+    int rc = peer_make_window(c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->peer_self));
+    memcpy(handle_out, &h, sizeof(h));
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_peer_window(usac_gpu_ctx* c, void** window_out) {
+    if (!c || !window_out) return fail(c, USAC_ERR_ARG, "peer_window: bad arguments");
+    int rc = peer_make_window(c);
+    if (rc) return rc;
+    *window_out = c->peer_self;
+    return USAC_OK;
+}
+
+static int peer_finish_attach(usac_gpu_ctx* c, const std::vector<void*>& wins, int rank, int nranks) {
+    CUDA_TRY(c, c->d_peer_win.ensure((size_t)nranks));
+    CUDA_TRY(c, cudaMemcpy(c->d_peer_win.p, wins.data(), sizeof(void*) * nranks, cudaMemcpyHostToDevice));
+    c->peer_rank = rank; c->peer_nranks = nranks;
+    return USAC_OK;
+}
+
+extern "C" int usac_gpu_peer_attach(usac_gpu_ctx* c, const char* handles, int rank, int nranks) {
+    if (!c || !handles || rank < 0 || rank >= nranks || nranks > USAC_PEER_MAX_RANKS) return fail(c, USAC_ERR_ARG, "peer_attach: bad arguments");
+    if (c->peer_nranks) return fail(c, USAC_ERR_STATE, "peer_attach: windows are already attached");
+    int rc = peer_make_window(c);
+    if (rc) return rc;
+    std::vector<void*> wins(nranks);
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { wins[r] = c->peer_self; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * USAC_PEER_HANDLE_BYTES, sizeof(h));
+        void* w = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&w, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (void* o : c->peer_opened) cudaIpcCloseMemHandle(o);
+            c->peer_opened.clear();
+            c->err = std::string("peer_attach: cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e);
+            return USAC_ERR_CUDA;
+        }
+        c->peer_opened.push_back(w);
+        wins[r] = w;
+    }
+    return peer_finish_attach(c, wins, rank, nranks);
+}
+
+extern "C" int usac_gpu_peer_attach_ptrs(usac_gpu_ctx* c, void* const* windows, int rank, int nranks) {
+    if (!c || !windows || rank < 0 || rank >= nranks || nranks > USAC_PEER_MAX_RANKS) return fail(c, USAC_ERR_ARG, "peer_attach_ptrs: bad arguments");
+    if (c->peer_nranks) return fail(c, USAC_ERR_STATE, "peer_attach_ptrs: windows are already attached");
+    int rc = peer_make_window(c);
+    if (rc) return rc;
+    if (windows[rank] != c->peer_self) return fail(c, USAC_ERR_ARG, "peer_attach_ptrs: windows[rank] must be this context's own window (usac_gpu_peer_window)");
+    std::vector<void*> wins(windows, windows + nranks);
+    return peer_finish_attach(c, wins, rank, nranks);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

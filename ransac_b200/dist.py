@@ -79,6 +79,16 @@ def broadcast_bytes(payload, src=0):
     return bytes(t.cpu().tolist())
 
 
+def allgather_bytes(payload):
+    """All-gather one fixed-size byte string per rank -> list in rank order (the IPC handles of usac_gpu_peer_export)."""
+    if not dist.is_initialized():
+        return [payload]
+    t = torch.tensor(list(payload), dtype=torch.uint8).to(_dev())
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [bytes(o.cpu().tolist()) for o in out]
+
+
 def reduce_max(values):
     t = torch.tensor(values, dtype=torch.float64, device=_dev())
     if dist.is_initialized():

@@ -47,6 +47,7 @@ public:
     void setModel(Model* m) { model = m; }
     void setTerminationCriteria(TerminationCriteria* t) { termination_criteria = t; }
     void setQuality(Quality* q) { quality = q; }
+    Quality* getQuality() { return quality; }
     RansacOutput* getRansacOutput() { return ransac_output; }
     const usac_fit_result& lastFit() const { return last_fit; }
 

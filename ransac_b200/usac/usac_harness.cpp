@@ -1,8 +1,15 @@
 // usac_harness.cpp - the reference's test harness shape (test/test.cpp:5-60: build a Model, construct Ransac(model, points),
-// run(), print RansacOutput) over the GPU plugin layer. Points come from a `*_pts.txt`-style file (first line N, then N
-// rows `x1 y1 x2 y2`, or `x y` for lines - the format of dataset/homography/sift_update/*_pts.txt).
-//   usac_harness <points.txt> <line2d|homography|fundamental|essential> <uniform|prosac|napsac> <threshold> <confidence> [seed]
-//                [--sequential|--both] [--sprt] [--lo 1|2] [--round K] [--max-iter N] [--knn K] [--report] [--runs N --csv out.csv [--gt-inliers G]]
+// run(), print RansacOutput) over the GPU plugin layer. Points come from the reference's dataset files (reader.hpp = detector/Reader.h):
+//   --format pts    first line N, then N rows `x1 y1 x2 y2` (`x y` for lines): dataset/homography/sift_update/*_pts.txt (default)
+//   --format nby6   rows `x1 y1 1 x2 y2 1` (Reader::getPointsNby6)
+//   --format nby7   rows `x1 y1 z1 x2 y2 z2 isinlier` (Reader::read_points + getInliers; the flags give the GT inlier count)
+//   --format evd    header + `x1,y1,x2,y2,FGINN,SNN,detector,descriptor,is_correct` (Reader::readEVDPointsInliers)
+//   --format line2d `width height noise a b c N` + N rows `x y` (dataset/GetImage.h:88-116; the GT line gives the GT inlier count)
+//   --gt-model F    3 x 3 ground-truth model (Reader::getMatrix3x3, the *_model.txt files): GT inliers = points under the threshold
+//   usac_harness <points file> <line2d|homography|fundamental|essential> <uniform|prosac|napsac> <threshold> <confidence> [seed]
+//                [--format F] [--gt-model file] [--read-only] [--sequential|--both] [--sprt] [--lo 1|2] [--round K] [--max-iter N] [--knn K]
+//                [--report] [--runs N --csv out.csv [--gt-inliers G]]
+// --read-only parses the input, prints `read n=.. dim=.. checksum=.. flagged_inliers=..` and exits (no GPU needed).
 // Prints one `key=value` line per result (model as IEEE bit patterns, inlier ids as a hash) for the parity tests; --report adds the
 // human-readable block of Tests::test (test/test.cpp:38-53); --runs/--csv writes one statistics row in the column layout of
 // Logging::saveHeadOfCSV / saveResultsCSV (helper/Logging.h:47-97) over N runs with seeds seed .. seed+N-1.
@@ -13,6 +20,7 @@
 #include <numeric>
 
 #include "ransac.hpp"
+#include "reader.hpp"
 
 static void report(const char* tag, Ransac& r, const Model& m);
 static void report_block(Ransac& r, const Model& m);
@@ -64,11 +72,48 @@ int main(int argc, char** argv) {
     const SAMPLER s = smp == "uniform" ? Uniform : smp == "prosac" ? Prosac : smp == "napsac" ? Napsac : NullS;
     if (e == NullE || s == NullS) { std::fprintf(stderr, "unknown estimator/sampler\n"); return 2; }
     const int dim = e == Line2d ? 2 : 4;
-    std::ifstream in(argv[1]);
-    int n = 0;
-    if (!(in >> n) || n <= 0) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
-    cv::Mat points(n, dim);
-    for (int i = 0; i < n * dim; i++) if (!(in >> points.ptr()[i])) { std::fprintf(stderr, "short points file\n"); return 2; }
+    std::string format = "pts";
+    const char* gt_model_file = nullptr;
+    bool read_only = false;
+    for (int i = 6; i < argc; i++) {
+        if (!std::strcmp(argv[i], "--format") && i + 1 < argc) format = argv[i + 1];
+        if (!std::strcmp(argv[i], "--gt-model") && i + 1 < argc) gt_model_file = argv[i + 1];
+        if (!std::strcmp(argv[i], "--read-only")) read_only = true;
+    }
+    cv::Mat points, gt_model;
+    std::vector<int> flagged;
+    int flagged_known = 0;
+    try {
+        if (format == "pts" && dim == 4) { if (!Reader::LoadPointsFromFile(points, argv[1])) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; } }
+        else if (format == "pts") {                                   // N, then N rows `x y`
+            std::ifstream in(argv[1]);
+            int n = 0;
+            if (!(in >> n) || n <= 0) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+            points = cv::Mat(n, 2);
+            for (int i = 0; i < 2 * n; i++) if (!(in >> points.ptr()[i])) { std::fprintf(stderr, "short points file\n"); return 2; }
+        }
+        else if (format == "nby6") Reader::getPointsNby6(argv[1], points);
+        else if (format == "nby7") {
+            cv::Mat p1, p2;
+            Reader::read_points(p1, p2, argv[1]);
+            Reader::getInliers(argv[1], flagged);
+            flagged_known = 1;
+            points = cv::Mat(p1.rows, 4);
+            for (int i = 0; i < p1.rows; i++) { points.at(i, 0) = p1.at(i, 0); points.at(i, 1) = p1.at(i, 1); points.at(i, 2) = p2.at(i, 0); points.at(i, 3) = p2.at(i, 1); }
+        }
+        else if (format == "evd") { Reader::readEVDPointsInliers(points, flagged, argv[1]); flagged_known = 1; }
+        else if (format == "line2d") { if (!Reader::readLine2d(points, gt_model, argv[1])) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; } }
+        else { std::fprintf(stderr, "unknown --format %s\n", format.c_str()); return 2; }
+        if (gt_model_file) Reader::getMatrix3x3(gt_model_file, gt_model);
+    } catch (const std::exception& ex) { std::fprintf(stderr, "usac_harness: %s\n", ex.what()); return 2; }
+    if (points.rows <= 0 || points.cols != dim) { std::fprintf(stderr, "%s: no %d-column points read (format %s)\n", argv[1], dim, format.c_str()); return 2; }
+    if (read_only) {
+        unsigned long long h = 1469598103934665603ull;
+        for (int i = 0; i < points.rows * points.cols; i++) { unsigned u; std::memcpy(&u, points.ptr() + i, 4); h ^= u; h *= 1099511628211ull; }
+        std::printf("read n=%d dim=%d checksum=%016llx flagged_inliers=%d gt_model=%d\n", points.rows, points.cols, h, flagged_known ? (int)flagged.size() : -1,
+                    gt_model.empty() ? 0 : gt_model.rows * gt_model.cols);
+        return 0;
+    }
     const unsigned m = e == Line2d ? 2 : e == Homography ? 4 : e == Fundamental ? 7 : 5;
     Model model((float)std::atof(argv[4]), m, (float)std::atof(argv[5]), 5, e, s);
     bool sequential = false, both = false, want_report = false;
@@ -86,12 +131,22 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--sprt")) model.setSprt(true);
         else if (!std::strcmp(argv[i], "--round") && i + 1 < argc) model.gpu_round_size = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--max-iter") && i + 1 < argc) model.max_iterations = (unsigned)std::atoi(argv[++i]);
+        else if ((!std::strcmp(argv[i], "--format") || !std::strcmp(argv[i], "--gt-model")) && i + 1 < argc) i++;
+        else if (!std::strcmp(argv[i], "--read-only")) {}
         else model.seed = std::strtoull(argv[i], nullptr, 10);
     }
     model.setCellSize(50);
     if (s == Napsac) model.setNeighborsType(knn > 0 ? Nanoflann : Grid);
     if (knn > 0) model.setKNearestNeighbors(knn);
     try {
+        if (gt_inliers == 0 && flagged_known) gt_inliers = (int)flagged.size();
+        if (gt_inliers == 0 && !gt_model.empty()) {                            // GT inliers = points of the GT model under the threshold (Quality)
+            Ransac r(&model, points);
+            Score sc;
+            r.getQuality()->getNumberInliers(&sc, gt_model);
+            gt_inliers = sc.inlier_number;
+            std::printf("gt_model inliers=%d\n", gt_inliers);
+        }
         if (runs > 0 && csv) {                                                  // Tests::getStatisticalResults, test/tests.h:148-150
             std::vector<double> inl, it, lo, us;
             int worst = 1 << 30, f10 = 0, f25 = 0, f50 = 0;

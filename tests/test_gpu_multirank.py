@@ -89,6 +89,47 @@ def test_emulated_ranks_match_single_gpu_and_oracle(cfg, world):
     assert sum(r["useful_evals"] for r in results) == ref["evals"]           # the shards partition the sequential work
 
 
+@pytest.mark.parametrize("cfg,world,batch", [(2, 2, 1), (2, 4, 3), (3, 2, 1)])
+def test_peer_windows_match_single_gpu_and_oracle(cfg, world, batch):
+    """The exchange over peer memory (usac_gpu_peer_*): ranks = threads of this process, every context owns a window, the reduce
+    kernels store into all windows and select_kernel waits for the flags. Same results as one GPU and the oracle, on every rank,
+    fit after fit (the sequence numbers keep counting), also for a batch of problems."""
+    from ransac_b200 import GpuContext
+    est = {2: O.EST_HOMOGRAPHY, 3: O.EST_FUNDAMENTAL}[cfg]
+    sets = [gen.make(cfg, seed_offset=40 + b, n=3000 + 500 * b)[0] for b in range(batch)]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    ctxs = [GpuContext(0) for _ in range(world)]
+    wins = [c.peer_window() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.set_points(est, np.concatenate(sets), [len(x) for x in sets])
+        c.peer_attach_ptrs(wins, r, world)
+    results, errors = [[None, None] for _ in range(world)], []
+
+    def run(rank):
+        try:
+            for rep in range(2):
+                results[rank][rep] = ctxs[rank].fit(thr, conf, 3000, seed=6 + rep, round_size=128, rank=rank, nranks=world)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    for c in ctxs:
+        c.close()
+    assert not errors, errors
+    for rep in range(2):
+        for b in range(batch):
+            ref = O.ransac(sets[b], est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=3000, seed=6 + rep)
+            for rank in range(world):
+                r = results[rank][rep][b]
+                for k in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+                    assert r[k] == ref[k], (rep, b, rank, k, r[k], ref[k])
+                assert np.array_equal(r["model"].view(np.uint32), np.asarray(ref["model"], np.float32).view(np.uint32))
+            assert sum(results[rank][rep][b]["useful_evals"] for rank in range(world)) == ref["evals"]
+
+
 def test_config5_emulated_ranks_full_size():
     """BASELINE config 5 at its stated size (1M correspondences, NAPSAC grid): the hypotheses of every round split over 4
     emulated ranks give the single-GPU result on every rank (which test_gpu_parity checks against the oracle)."""

@@ -48,9 +48,78 @@ def test_plugin_headers_keep_the_reference_signatures():
         assert sig in text, sig
 
 
+def fnv_floats(a):
+    h = 1469598103934665603
+    for u in np.ascontiguousarray(a, np.float32).view(np.uint32).ravel():
+        h = ((h ^ int(u)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def read_only(harness, path, est, fmt, *extra):
+    r = subprocess.run([harness, str(path), est, "uniform", "2", "0.95", "--format", fmt, "--read-only", *extra], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    return dict(kv.split("=") for kv in r.stdout.split()[1:])
+
+
+def test_harness_reads_the_reference_dataset_formats(harness, tmp_path):
+    """detector/Reader.h formats (+ the line-fitting sets of dataset/GetImage.h) through usac/reader.hpp; no GPU involved."""
+    g = np.random.default_rng(5)
+    pts = (g.random((37, 4)) * 900).astype(np.float32)
+    flags = g.random(37) < 0.4
+    rows = [f"{v:.9g}" for v in pts.ravel()]
+    # *_pts.txt
+    p = tmp_path / "a_pts.txt"
+    write_points(p, pts)
+    got = read_only(harness, p, "homography", "pts")
+    assert got["n"] == "37" and got["dim"] == "4" and got["checksum"] == fnv_floats(pts) and got["flagged_inliers"] == "-1"
+    # N x 6 and N x 7
+    p6, p7 = tmp_path / "a6.txt", tmp_path / "a7.txt"
+    p6.write_text("".join(f"{a} {b} 1 {c} {d} 1\n" for a, b, c, d in zip(*[iter(rows)] * 4)))
+    p7.write_text("".join(f"{a} {b} 1 {c} {d} 1 {int(f)}\n" for (a, b, c, d), f in zip(zip(*[iter(rows)] * 4), flags)))
+    got = read_only(harness, p6, "fundamental", "nby6")
+    assert got["n"] == "37" and got["checksum"] == fnv_floats(pts)
+    got = read_only(harness, p7, "fundamental", "nby7")
+    assert got["n"] == "37" and got["checksum"] == fnv_floats(pts) and got["flagged_inliers"] == str(int(flags.sum()))
+    # EVD tentatives
+    pe = tmp_path / "a.png_m.txt"
+    pe.write_text("x1,y1,x2,y2,FGINN_ratio,SNN_ratio,detector,descriptor,is_correct\n" +
+                  "".join(f"{a},{b},{c},{d},0.5,0.7,HessianAffine,RootSIFT,{int(f)}\n" for (a, b, c, d), f in zip(zip(*[iter(rows)] * 4), flags)))
+    got = read_only(harness, pe, "homography", "evd")
+    assert got["n"] == "37" and got["checksum"] == fnv_floats(pts) and got["flagged_inliers"] == str(int(flags.sum()))
+    # line fitting set + a 3 x 3 model file
+    pl = tmp_path / "line.txt"
+    pl.write_text("1000 1000 3.0\n0.6 -0.8 25.5\n37\n" + "".join(f"{a} {b}\n" for a, b in zip(*[iter(rows[:74])] * 2)))
+    got = read_only(harness, pl, "line2d", "line2d")
+    assert got["n"] == "37" and got["dim"] == "2" and got["checksum"] == fnv_floats(pts.ravel()[:74]) and got["gt_model"] == "3"
+    pm = tmp_path / "a_model.txt"
+    pm.write_text("1 0.1 3\n-0.1 1 4\n1e-5 2e-5 1\n")
+    got = read_only(harness, p, "homography", "pts", "--gt-model", str(pm))
+    assert got["gt_model"] == "9"
+    # wrong column count for the estimator is an error, not a silent reinterpretation
+    r = subprocess.run([harness, str(pl), "homography", "uniform", "2", "0.95", "--format", "line2d", "--read-only"], stderr=subprocess.PIPE)
+    assert r.returncode == 2
+
+
+@pytest.mark.gpu
+def test_harness_gt_model_inliers_match_oracle(harness, tmp_path):
+    """--gt-model: the "GT Inl" column of the reference's statistics = points of the ground-truth model under the threshold."""
+    from oracle import oracle as O
+    from ransac_b200 import generator as gen
+    pts, H, mask = gen.homography(n=1500, seed=3)
+    p, pm = tmp_path / "p.txt", tmp_path / "p_model.txt"
+    write_points(p, pts)
+    pm.write_text("\n".join(" ".join(f"{v:.9g}" for v in row) for row in np.asarray(H, np.float32).reshape(3, 3)) + "\n")
+    r = subprocess.run([harness, str(p), "homography", "uniform", "2", "0.95", "1", "--gt-model", str(pm)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    cnt = O.score(O.EST_HOMOGRAPHY, pts, np.asarray(H, np.float32).ravel(), 2.0)[0]
+    assert f"gt_model inliers={int(cnt)}" in r.stdout
+
+
 def parse(out):
     res = {}
     for line in out.splitlines():
+        if not line.startswith(("fused", "sequential")):
+            continue
         tag, *kv = line.split()
         d = dict(x.split("=") for x in kv)
         res[tag] = {"iterations": int(d["iterations"]), "inliers": int(d["inliers"]), "hash": d["inlier_hash"], "score": float(d["score"]),

@@ -23,9 +23,14 @@ CASES = [
     ("C2 homography N=4000 30% uniform+LO", 2, {}, dict(est=O.EST_HOMOGRAPHY, thr=2.0, conf=0.95), dict(lo=1)),
     ("C5 homography N=1M 10% NAPSAC grid", 5, {}, dict(est=O.EST_HOMOGRAPHY, thr=2.0, conf=0.95), dict(sampler="napsac", K=2048, oracle_iters=64)),
 ]
+ONLY = os.environ.get("CONFIG_TIMES_ONLY")            # substring filter on the case name, e.g. "+LO"
+NO_CPU = os.environ.get("CONFIG_TIMES_NO_CPU") == "1"  # skip the oracle leg (profiling runs)
+REPS = int(os.environ.get("CONFIG_TIMES_REPS", "9"))
 ctx = GpuContext(0)
 print(f"{'config':48s} {'GPU ms/fit':>10s} {'CPU ms/fit':>11s} {'speed-up':>8s} {'iters':>6s} {'inliers':>8s}  parity")
 for name, cfg, genkw, p, mode in CASES:
+    if ONLY and ONLY not in name:
+        continue
     pts = gen.make(cfg, **genkw)[0]
     ctx.set_points(p["est"], pts)
     kw = dict(threshold=p["thr"], confidence=p["conf"], max_iterations=10000, seed=1)
@@ -45,11 +50,14 @@ for name, cfg, genkw, p, mode in CASES:
         if mode.get("sprt") or mode.get("sampler") == "prosac":
             okw["batch"] = mode["K"]
     times = []
-    for rep in range(9):
+    for rep in range(REPS):
         t0 = time.perf_counter()
         r = ctx.fit(**kw)[0]
         times.append((time.perf_counter() - t0) * 1e3)
-    gpu_ms = float(np.median(times[2:]))
+    gpu_ms = float(np.median(times[2:] if len(times) > 2 else times))
+    if NO_CPU:
+        print(f"{name:48s} {gpu_ms:10.3f} {'-':>11s} {'-':>8s} {r['iterations']:6d} {r['inliers']:8d}  (not compared)")
+        continue
     scale = 1.0
     if "oracle_iters" in mode:                      # the full 1e10-evaluation fit takes ~1 min on one core: time a prefix and scale
         okw["max_iterations"] = mode["oracle_iters"]
