@@ -40,39 +40,62 @@ T lane_sum(int n, F value) {
     return part[0];
 }
 
-/* eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (row-major, destroyed): cyclic Jacobi, at most 12 sweeps */
+/* eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (row-major, destroyed; n odd): Jacobi rotations in the
+ * round-robin order - round r = 0..n-1 rotates the (n-1)/2 DISJOINT pairs {(r+k) mod n, (r-k) mod n}, k = 1..(n-1)/2 (index r sits
+ * out; every pair occurs once per sweep). The angles of a round come from the matrix as it is at the start of the round, then
+ * the column updates of all its pairs, then the row updates, then V - the order the device code uses, where the pairs of a
+ * round run side by side. At most 12 sweeps; rotations with |apq| <= 1e-17 sqrt(|app aqq|) are skipped and the first sweep
+ * without a rotation ends the loop. */
 void smallest_eigenvector(double* S, int n, double* vec) {
     double V[81];
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+    const int half = (n - 1) / 2;
     for (int sweep = 0; sweep < 12; sweep++) {
         int rotations = 0;                                        /* a sweep without a rotation: converged */
-        for (int p = 0; p < n - 1; p++)
-            for (int q = p + 1; q < n; q++) {
+        for (int r = 0; r < n; r++) {
+            int P[8], Q[8];
+            double C[8], Sn[8];
+            bool on[8];
+            for (int k = 1; k <= half; k++) {
+                int p = (r + k) % n, q = (r - k + n) % n;
+                if (p > q) { const int t = p; p = q; q = t; }
+                const int e = k - 1;
+                P[e] = p; Q[e] = q; on[e] = false;
                 const double apq = S[p * n + q];
                 if (apq == 0.0) continue;
-                if (apq * apq <= 1e-34 * std::fabs(S[p * n + p] * S[q * n + q])) continue;   /* |apq| <= 1e-17 sqrt(|app aqq|): nothing left to rotate */
+                if (apq * apq <= 1e-34 * std::fabs(S[p * n + p] * S[q * n + q])) continue;   /* nothing left to rotate */
                 const double theta = (S[q * n + q] - S[p * n + p]) / (2.0 * apq);
                 const double tt = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
                 const double t = theta < 0.0 ? -tt : tt;
                 const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
                 if (!std::isfinite(c) || !std::isfinite(s)) continue;
+                C[e] = c; Sn[e] = s; on[e] = true;
                 rotations++;
-                for (int k = 0; k < n; k++) {                     /* columns p, q of S */
+            }
+            for (int e = 0; e < half; e++) {                      /* columns p, q of S */
+                if (!on[e]) continue;
+                const int p = P[e], q = Q[e];
+                const double c = C[e], s = Sn[e];
+                for (int k = 0; k < n; k++) {
                     const double skp = S[k * n + p], skq = S[k * n + q];
                     S[k * n + p] = c * skp - s * skq;
                     S[k * n + q] = s * skp + c * skq;
                 }
-                for (int k = 0; k < n; k++) {                     /* rows p, q of S */
+            }
+            for (int e = 0; e < half; e++) {                      /* rows p, q of S; columns p, q of V */
+                if (!on[e]) continue;
+                const int p = P[e], q = Q[e];
+                const double c = C[e], s = Sn[e];
+                for (int k = 0; k < n; k++) {
                     const double spk = S[p * n + k], sqk = S[q * n + k];
                     S[p * n + k] = c * spk - s * sqk;
                     S[q * n + k] = s * spk + c * sqk;
-                }
-                for (int k = 0; k < n; k++) {
                     const double vkp = V[k * n + p], vkq = V[k * n + q];
                     V[k * n + p] = c * vkp - s * vkq;
                     V[k * n + q] = s * vkp + c * vkq;
                 }
             }
+        }
         if (!rotations) break;
     }
     int best = 0;

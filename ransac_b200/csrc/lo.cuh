@@ -44,9 +44,9 @@ struct LoShared {
     float part[LO_THREADS];              // error-sum partials of the 1024 scoring lanes
     float rec[USAC_REC_STRIDE];
     float model[9], best_model[9], stats[8];
-    int warp_tot[32];
+    int warp_tot[2][32];                 // inliers per warp of the current / previous block of 1024 points
     int sample[16];
-    int base, ok, cnt;
+    int ok, cnt;
     float sum;
 };
 
@@ -78,38 +78,99 @@ __device__ __forceinline__ void lo_tree256(T* tree, int count) {
     __syncthreads();
 }
 
+// The points of virtual lane l (ids[l], ids[l + 256], ...) in order, four gathers in flight: f(point) is called once per point.
+template <class F>
+__device__ __forceinline__ void lo_lane_points(const float* __restrict__ pts, const int* ids, int n, int l, F f) {
+    for (int k = l; k < n; k += 4 * REFIT_THREADS) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = k + u * REFIT_THREADS;
+            if (i < n) p[u] = reinterpret_cast<const float4*>(pts)[ids[i]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (k + u * REFIT_THREADS < n) f(p[u]);
+    }
+}
+
+// entry e = 0..44 of the upper triangle of the 9 x 9 matrix A'A, row-major: (i, j)
+__host__ __device__ constexpr int aat_row(int e) { int i = 0; while (e >= 9 - i) { e -= 9 - i; i++; } return i; }
+__host__ __device__ constexpr int aat_col(int e) { int i = 0; while (e >= 9 - i) { e -= 9 - i; i++; } return i + e; }
+
+template <int NROWS, int G, int C, int CNT>
+struct LoAatAcc {                                                      // acc[C] += term of entry G + 4 C, indices known at compile time
+    static __device__ __forceinline__ void run(double* acc, const float (&r)[2][9]) {
+        constexpr int I = aat_row(G + 4 * C), J = aat_col(G + 4 * C);
+        double a2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NROWS; q++) a2 = __dadd_rn(a2, __dmul_rn((double)r[q][I], (double)r[q][J]));
+        acc[C] = __dadd_rn(acc[C], a2);
+        LoAatAcc<NROWS, G, C + 1, CNT>::run(acc, r);
+    }
+};
+template <int NROWS, int G, int CNT>
+struct LoAatAcc<NROWS, G, CNT, CNT> { static __device__ __forceinline__ void run(double*, const float (&)[2][9]) {} };
+
+// A'A partials of virtual lane l for the entries e = G, G + 4, ... (thread group G of four): every entry still adds its terms
+// point by point in the lane's order, as one thread holding all 45 accumulators would - but 12 accumulators fit in registers.
+template <int EST, int G>
+__device__ __forceinline__ void lo_aat_group(const float* __restrict__ pts, const int* ids, int n, int l, float s1, float t1x, float t1y,
+                                             float s2, float t2x, float t2y, double* tree) {
+    constexpr int NROWS = (EST == USAC_EST_HOMOGRAPHY) ? 2 : 1;
+    constexpr int CNT = (45 - G + 3) / 4;
+    double acc[CNT];
+#pragma unroll
+    for (int c = 0; c < CNT; c++) acc[c] = 0.0;
+    lo_lane_points(pts, ids, n, l, [&](const float4& p) {
+        const float x1 = (sf(s1) * sf(p.x) + sf(t1x)).v, y1 = (sf(s1) * sf(p.y) + sf(t1y)).v;
+        const float x2 = (sf(s2) * sf(p.z) + sf(t2x)).v, y2 = (sf(s2) * sf(p.w) + sf(t2y)).v;
+        float r[2][9];
+        if (EST == USAC_EST_HOMOGRAPHY) {
+            r[0][0] = -x1; r[0][1] = -y1; r[0][2] = -1.f; r[0][3] = 0.f; r[0][4] = 0.f; r[0][5] = 0.f;
+            r[0][6] = __fmul_rn(x2, x1); r[0][7] = __fmul_rn(x2, y1); r[0][8] = x2;
+            r[1][0] = 0.f; r[1][1] = 0.f; r[1][2] = 0.f; r[1][3] = -x1; r[1][4] = -y1; r[1][5] = -1.f;
+            r[1][6] = __fmul_rn(y2, x1); r[1][7] = __fmul_rn(y2, y1); r[1][8] = y2;
+        } else {
+            r[0][0] = __fmul_rn(x2, x1); r[0][1] = __fmul_rn(x2, y1); r[0][2] = x2; r[0][3] = __fmul_rn(y2, x1); r[0][4] = __fmul_rn(y2, y1);
+            r[0][5] = y2; r[0][6] = x1; r[0][7] = y1; r[0][8] = 1.f;
+#pragma unroll
+            for (int q = 0; q < 9; q++) r[1][q] = 0.f;
+        }
+        LoAatAcc<NROWS, G, 0, CNT>::run(acc, r);
+    });
+#pragma unroll
+    for (int c = 0; c < CNT; c++) tree[(G + 4 * c) * REFIT_THREADS + l] = acc[c];
+}
+
 // Estimator::EstimateModelNonMinimalSample on `n` point ids -> sh.model, sh.ok. Same arithmetic as nonminimal_kernel (refit.cuh).
 template <int EST>
 __device__ void cta_nonminimal(const float* __restrict__ pts, const int* ids, int n, LoShared& sh) {
     const int t = threadIdx.x;
-    const bool lane_on = t < REFIT_THREADS;
+    const int l = t & (REFIT_THREADS - 1), grp = t >> 8;                // virtual lane, thread group (LO_THREADS = 4 x REFIT_THREADS)
+    static_assert(LO_THREADS == 4 * REFIT_THREADS, "four thread groups share the 256 virtual lanes");
     const float fn = (float)n;
     float* treef = reinterpret_cast<float*>(sh.tree);
     __syncthreads();                                                   // everyone has read the previous call's sh.ok / sh.model
     if (t == 0) sh.ok = 0;
     if (n < 4) { __syncthreads(); return; }                            // uniform
-    // ---- normalising transformations ----
-    if (lane_on) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = t; i < n; i += REFIT_THREADS) {
-            const float4 p = reinterpret_cast<const float4*>(pts)[ids[i]];
-            a[0] = __fadd_rn(a[0], p.x); a[1] = __fadd_rn(a[1], p.y); a[2] = __fadd_rn(a[2], p.z); a[3] = __fadd_rn(a[3], p.w);
-        }
-        for (int k = 0; k < 4; k++) treef[k * REFIT_THREADS + t] = a[k];
+    // ---- normalising transformations: group g sums coordinate g ----
+    {
+        float a = 0.f;
+        lo_lane_points(pts, ids, n, l, [&](const float4& p) { a = __fadd_rn(a, grp == 0 ? p.x : grp == 1 ? p.y : grp == 2 ? p.z : p.w); });
+        treef[grp * REFIT_THREADS + l] = a;
     }
     lo_tree256<float>(treef, 4);
     float m[4];
     for (int k = 0; k < 4; k++) m[k] = __fdiv_rn(treef[k * REFIT_THREADS], fn);
     __syncthreads();
-    if (lane_on) {
-        float d1 = 0.f, d2 = 0.f;
-        for (int i = t; i < n; i += REFIT_THREADS) {
-            const float4 p = reinterpret_cast<const float4*>(pts)[ids[i]];
-            const sf a = sf(p.x) - sf(m[0]), b = sf(p.y) - sf(m[1]), c = sf(p.z) - sf(m[2]), d = sf(p.w) - sf(m[3]);
-            d1 = __fadd_rn(d1, ssqrt(a * a + b * b).v);
-            d2 = __fadd_rn(d2, ssqrt(c * c + d * d).v);
-        }
-        treef[t] = d1; treef[REFIT_THREADS + t] = d2;
+    if (grp < 2) {                                                     // group 0: mean distance in image 1, group 1: in image 2
+        float d = 0.f;
+        const float mx = grp == 0 ? m[0] : m[2], my = grp == 0 ? m[1] : m[3];
+        lo_lane_points(pts, ids, n, l, [&](const float4& p) {
+            const sf a = sf(grp == 0 ? p.x : p.z) - sf(mx), b = sf(grp == 0 ? p.y : p.w) - sf(my);
+            d = __fadd_rn(d, ssqrt(a * a + b * b).v);
+        });
+        treef[grp * REFIT_THREADS + l] = d;
     }
     lo_tree256<float>(treef, 2);
     const float d1 = treef[0], d2 = treef[REFIT_THREADS];
@@ -118,41 +179,12 @@ __device__ void cta_nonminimal(const float* __restrict__ pts, const int* ids, in
     const float s1 = (float)(sd(SQRT2) / sd((double)__fdiv_rn(d1, fn))).v, s2 = (float)(sd(SQRT2) / sd((double)__fdiv_rn(d2, fn))).v;
     const float t1x = (-sf(m[0]) * sf(s1)).v, t1y = (-sf(m[1]) * sf(s1)).v, t2x = (-sf(m[2]) * sf(s2)).v, t2y = (-sf(m[3]) * sf(s2)).v;
     if (!isfinite(s1) || !isfinite(s2)) return;                        // uniform (every thread holds the same values)
-    // ---- A'A: one pass over the points, 45 accumulators per lane (each entry adds its terms in the same order as a pass of its own) ----
-    constexpr int NROWS = (EST == USAC_EST_HOMOGRAPHY) ? 2 : 1;
-    if (lane_on) {
-        double acc[45];
-#pragma unroll
-        for (int e = 0; e < 45; e++) acc[e] = 0.0;
-        for (int k = t; k < n; k += REFIT_THREADS) {
-            const float4 p = reinterpret_cast<const float4*>(pts)[ids[k]];
-            const float x1 = (sf(s1) * sf(p.x) + sf(t1x)).v, y1 = (sf(s1) * sf(p.y) + sf(t1y)).v;
-            const float x2 = (sf(s2) * sf(p.z) + sf(t2x)).v, y2 = (sf(s2) * sf(p.w) + sf(t2y)).v;
-            float r[2][9];
-            if (EST == USAC_EST_HOMOGRAPHY) {
-                r[0][0] = -x1; r[0][1] = -y1; r[0][2] = -1.f; r[0][3] = 0.f; r[0][4] = 0.f; r[0][5] = 0.f;
-                r[0][6] = __fmul_rn(x2, x1); r[0][7] = __fmul_rn(x2, y1); r[0][8] = x2;
-                r[1][0] = 0.f; r[1][1] = 0.f; r[1][2] = 0.f; r[1][3] = -x1; r[1][4] = -y1; r[1][5] = -1.f;
-                r[1][6] = __fmul_rn(y2, x1); r[1][7] = __fmul_rn(y2, y1); r[1][8] = y2;
-            } else {
-                r[0][0] = __fmul_rn(x2, x1); r[0][1] = __fmul_rn(x2, y1); r[0][2] = x2; r[0][3] = __fmul_rn(y2, x1); r[0][4] = __fmul_rn(y2, y1);
-                r[0][5] = y2; r[0][6] = x1; r[0][7] = y1; r[0][8] = 1.f;
-                for (int q = 0; q < 9; q++) r[1][q] = 0.f;
-            }
-            int e = 0;
-#pragma unroll
-            for (int i = 0; i < 9; i++)
-#pragma unroll
-                for (int j = i; j < 9; j++) {
-                    double a2 = 0.0;
-#pragma unroll
-                    for (int q = 0; q < NROWS; q++) a2 = __dadd_rn(a2, __dmul_rn((double)r[q][i], (double)r[q][j]));
-                    acc[e] = __dadd_rn(acc[e], a2);
-                    e++;
-                }
-        }
-#pragma unroll
-        for (int e = 0; e < 45; e++) sh.tree[e * REFIT_THREADS + t] = acc[e];
+    // ---- A'A: one pass over the points; group g accumulates the entries g, g + 4, ... of the upper triangle ----
+    switch (grp) {                                                     // warp-uniform
+        case 0: lo_aat_group<EST, 0>(pts, ids, n, l, s1, t1x, t1y, s2, t2x, t2y, sh.tree); break;
+        case 1: lo_aat_group<EST, 1>(pts, ids, n, l, s1, t1x, t1y, s2, t2x, t2y, sh.tree); break;
+        case 2: lo_aat_group<EST, 2>(pts, ids, n, l, s1, t1x, t1y, s2, t2x, t2y, sh.tree); break;
+        default: lo_aat_group<EST, 3>(pts, ids, n, l, s1, t1x, t1y, s2, t2x, t2y, sh.tree); break;
     }
     lo_tree256<double>(sh.tree, 45);
     if (t < 45) {
@@ -199,11 +231,11 @@ __device__ void cta_score(const float* __restrict__ aos, int n, const float* mod
         float rec[USAC_REC_STRIDE];
         make_record(EST, model, thr, pd, rec);
         for (int i = 0; i < USAC_REC_STRIDE; i++) sh.rec[i] = rec[i];
-        sh.base = 0;
     }
     __syncthreads();
     float acc = 0.f;
-    for (int start = 0; start < n; start += LO_THREADS) {
+    int base = 0;                                                      // inliers so far (the same value in every thread)
+    for (int start = 0, buf = 0; start < n; start += LO_THREADS, buf ^= 1) {
         const int i = start + t;
         bool in = false;
         if (i < n) {
@@ -213,14 +245,16 @@ __device__ void cta_score(const float* __restrict__ aos, int n, const float* mod
             if (in) acc = __fadd_rn(acc, e);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) sh.warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < 32; w++) { const int v = sh.warp_tot[w]; if (w < warp) before += v; total += v; }
-        if (in) ids[sh.base + before + __popc(bal & ((1u << lane) - 1))] = i;
-        __syncthreads();
-        if (t == 0) sh.base += total;
-        __syncthreads();
+        if (lane == 0) sh.warp_tot[buf][warp] = __popc(bal);
+        __syncthreads();                                               // the one barrier per block: the other buffer is free again by the next one
+        int incl = sh.warp_tot[buf][lane];                             // lane l holds warp l's count: scan over the 32 warps by shuffles
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int upto = __shfl_sync(0xffffffffu, incl, warp);        // inclusive count of warps 0 .. warp
+        const int before = upto - __popc(bal);
+        if (in) ids[base + before + __popc(bal & ((1u << lane) - 1))] = i;
+        base += total;
     }
     sh.part[t] = acc;
     __syncthreads();
@@ -235,7 +269,7 @@ __device__ void cta_score(const float* __restrict__ aos, int n, const float* mod
         }
     }
     __syncthreads();
-    if (t == 0) { sh.cnt = sh.base; sh.sum = sh.part[0]; }
+    if (t == 0) { sh.cnt = base; sh.sum = sh.part[0]; }
     __threadfence_block();
     __syncthreads();
 }
@@ -262,7 +296,7 @@ __device__ void lo_subset(unsigned long long seed, unsigned long long calls, int
 __device__ __forceinline__ bool lo_bigger(int ia, float sa, int ib, float sb) { return ia > ib || (ia == ib && sa > sb); }
 
 template <int EST>
-__global__ void __launch_bounds__(LO_THREADS) lo_kernel(const LoArgs a) {
+__global__ void __launch_bounds__(LO_THREADS, 1) lo_kernel(const LoArgs a) {
     extern __shared__ __align__(16) unsigned char lo_smem[];
     LoShared& sh = *reinterpret_cast<LoShared*>(lo_smem);
     const int t = threadIdx.x;

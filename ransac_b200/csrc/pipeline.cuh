@@ -339,7 +339,10 @@ __global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
 // Essential matrices: one WARP per sample (essential.cuh, solve_essential5_warp) - the one-thread form of the five-point solver
 // is latency bound at ~3 ms per sample, the warp form spreads its independent pieces over the lanes (bit-identical results).
 #define E5_WARPS_PER_CTA 4
-__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) solve_kernel_e5_warp(const RoundArgs a) {
+#ifndef E5_MIN_CTAS
+#define E5_MIN_CTAS 1            // resident CTAs per SM the register allocation aims at (255 registers -> 2 CTAs = 8 warps per SM)
+#endif
+__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA, E5_MIN_CTAS) solve_kernel_e5_warp(const RoundArgs a) {
     __shared__ double sm[E5_WARPS_PER_CTA][E5_WARP_DOUBLES];
     const int slot = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * E5_WARPS_PER_CTA + w;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) solve_kernel_e5_warp(co
     const int k = solve_essential5_warp(pts, s, dst, sm[w]);
     if (lane == 0) *nm = k;
 }
-__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA) estimate_kernel_e5_warp(const float* __restrict__ pts, const int* __restrict__ samples, int K,
+__global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA, E5_MIN_CTAS) estimate_kernel_e5_warp(const float* __restrict__ pts, const int* __restrict__ samples, int K,
                                                                                 float* __restrict__ models, int* __restrict__ nmodels) {
     __shared__ double sm[E5_WARPS_PER_CTA][E5_WARP_DOUBLES];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;

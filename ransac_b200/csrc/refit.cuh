@@ -40,48 +40,76 @@ __device__ __forceinline__ double refit_tree_d(double v, double* sm) {
     return r;
 }
 
-// Eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (n <= 9; S, V in shared memory): 12 cyclic Jacobi
-// sweeps, executed by the first warp - lane k owns index k of every rotation update (row/column element k), which are
-// independent of each other, so the arithmetic per element is exactly that of the sequential loops of the host restatement.
+// Eigenvector of the smallest eigenvalue of the symmetric n x n matrix S (n odd, <= 9; S, V in shared memory): at most 12 Jacobi
+// sweeps in the round-robin order, executed by the first warp. Round r rotates the (n-1)/2 disjoint pairs {(r+k) mod n, (r-k) mod n}:
+// their angles are computed side by side (one lane each) from the matrix at the start of the round, then lane (pair, k) updates
+// element k of the pair's two columns, then of its two rows and of V - 9 dependent steps per sweep instead of 36 (the angle is
+// a chain of three divisions and two square roots in double). Every element sees exactly the operations of the sequential loops
+// of the host restatement, which uses the same round order.
 __device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, double* V) {
-    const int k = threadIdx.x & 31;
-    for (int i = k; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    const int lane = threadIdx.x & 31;
+    const int half = (n - 1) / 2;                                        // n odd (9): disjoint pairs per round
+    for (int i = lane; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < 12; sweep++) {
         int rotations = 0;                                               // a sweep without a rotation: converged (uniform over the warp)
-        for (int p = 0; p < n - 1; p++)
-            for (int q = p + 1; q < n; q++) {
+        for (int r = 0; r < n; r++) {
+            // lane e < half computes the angle of pair e of this round from the matrix as it stands
+            int p = 0, q = 0;
+            double c = 1.0, s = 0.0;
+            bool on = false;
+            if (lane < half) {
+                p = (r + lane + 1) % n; q = (r - lane - 1 + n) % n;
+                if (p > q) { const int t = p; p = q; q = t; }
                 const sd apq(S[p * n + q]);
-                if (apq.v == 0.0) continue;                              // uniform: every lane reads the same element
-                if ((apq * apq).v <= (sd(1e-34) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v) continue;   // |apq| <= 1e-17 sqrt(|app aqq|)
-                const sd theta = (sd(S[q * n + q]) - sd(S[p * n + p])) / (sd(2.0) * apq);
-                const sd tt = sd(1.0) / (sd(fabs(theta.v)) + dsqrt(theta * theta + sd(1.0)));
-                const sd t = theta.v < 0.0 ? -tt : tt;
-                const sd c = sd(1.0) / dsqrt(t * t + sd(1.0)), s = t * c;
-                __syncwarp();                                            // everyone has read S[p][q], S[p][p], S[q][q]
-                if (!dfinite(c.v) || !dfinite(s.v)) continue;
-                rotations++;
-                if (k < n) {
-                    const sd a(S[k * n + p]), b(S[k * n + q]);
-                    S[k * n + p] = (c * a - s * b).v;
-                    S[k * n + q] = (s * a + c * b).v;
+                if (apq.v != 0.0 && !((apq * apq).v <= (sd(1e-34) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v)) {
+                    const sd theta = (sd(S[q * n + q]) - sd(S[p * n + p])) / (sd(2.0) * apq);
+                    const sd tt = sd(1.0) / (sd(fabs(theta.v)) + dsqrt(theta * theta + sd(1.0)));
+                    const sd t = theta.v < 0.0 ? -tt : tt;
+                    const sd cc = sd(1.0) / dsqrt(t * t + sd(1.0)), ss = t * cc;
+                    if (dfinite(cc.v) && dfinite(ss.v)) { c = cc.v; s = ss.v; on = true; }
                 }
-                __syncwarp();
-                if (k < n) {
-                    const sd a(S[p * n + k]), b(S[q * n + k]);
-                    S[p * n + k] = (c * a - s * b).v;
-                    S[q * n + k] = (s * a + c * b).v;
-                    const sd va(V[k * n + p]), vb(V[k * n + q]);
-                    V[k * n + p] = (c * va - s * vb).v;
-                    V[k * n + q] = (s * va + c * vb).v;
-                }
-                __syncwarp();
             }
+            const unsigned live = __ballot_sync(0xffffffffu, on);
+            __syncwarp();                                                // every angle has been computed from the old matrix
+            rotations += __popc(live);
+            if (!live) continue;                                         // uniform
+            // element updates: lane = (pair e, index k), half * n of them in passes of the whole warp
+            for (int base = 0; base < half * n; base += 32) {            // columns p, q of S
+                const int w = base + lane;
+                const bool act = w < half * n;
+                const int e = act ? w / n : 0, k = act ? w % n : 0;
+                const int pe = __shfl_sync(0xffffffffu, p, e), qe = __shfl_sync(0xffffffffu, q, e);
+                const double ce = __shfl_sync(0xffffffffu, c, e), se = __shfl_sync(0xffffffffu, s, e);
+                if (act && ((live >> e) & 1u)) {
+                    const sd a(S[k * n + pe]), b(S[k * n + qe]);
+                    S[k * n + pe] = (sd(ce) * a - sd(se) * b).v;
+                    S[k * n + qe] = (sd(se) * a + sd(ce) * b).v;
+                }
+            }
+            __syncwarp();
+            for (int base = 0; base < half * n; base += 32) {            // rows p, q of S; columns p, q of V
+                const int w = base + lane;
+                const bool act = w < half * n;
+                const int e = act ? w / n : 0, k = act ? w % n : 0;
+                const int pe = __shfl_sync(0xffffffffu, p, e), qe = __shfl_sync(0xffffffffu, q, e);
+                const double ce = __shfl_sync(0xffffffffu, c, e), se = __shfl_sync(0xffffffffu, s, e);
+                if (act && ((live >> e) & 1u)) {
+                    const sd a(S[pe * n + k]), b(S[qe * n + k]);
+                    S[pe * n + k] = (sd(ce) * a - sd(se) * b).v;
+                    S[qe * n + k] = (sd(se) * a + sd(ce) * b).v;
+                    const sd va(V[k * n + pe]), vb(V[k * n + qe]);
+                    V[k * n + pe] = (sd(ce) * va - sd(se) * vb).v;
+                    V[k * n + qe] = (sd(se) * va + sd(ce) * vb).v;
+                }
+            }
+            __syncwarp();
+        }
         if (!rotations) break;
     }
     int best = 0;
     for (int i = 1; i < n; i++) if (S[i * n + i] < S[best * n + best]) best = i;
-    if (k < n) vec[k] = V[k * n + best];
+    if (lane < n) vec[lane] = V[lane * n + best];
     __syncwarp();
 }
 

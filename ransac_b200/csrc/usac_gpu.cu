@@ -1372,7 +1372,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
     int G = 1;
     if (is_sprt && !is_prosac && cfg->sampler.sampler == USAC_SAMPLER_UNIFORM) {
         const char* e = getenv("USAC_GPU_SOLVE_AHEAD");
-        G = e ? std::max(1, atoi(e)) : (c->est == USAC_EST_ESSENTIAL ? 4 : 2);
+        G = e ? std::max(1, atoi(e)) : (c->est == USAC_EST_ESSENTIAL ? 8 : 2);
         while (G > 1 && (size_t)K * G > 8192) G--;
     }
     const int KB = K * G;                                         // samples per solved block
