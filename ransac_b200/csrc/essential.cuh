@@ -251,9 +251,10 @@ __device__ void stage_sort(double* roots, int& nroots) {                 // asce
     }
 }
 
-// stage 5: one root z -> x, y (Gauss-Jordan on [M(z) | last column]), eight Gauss-Newton steps, E, cheirality vote
-__device__ bool stage_root(const double (*C)[20], const double (*L)[4], const double* X, double z, double* E) {
-    const double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
+// stage 5: one root z -> x, y (Gauss-Jordan on [M(z) | last column]), eight Gauss-Newton steps, E, cheirality vote.
+// In pieces, so that the warp form can spread the Gauss-Newton rows of all roots over its lanes: the pieces do the same
+// operations in the same order whoever calls them.
+__device__ bool stage_root_init(const double (*C)[20], double z, double* u) {
     double Mz[100];
     for (int r = 0; r < 10; r++)
         for (int c = 0; c < 10; c++) Mz[r * 10 + c] = horner(&C[r][COL_FIRST[c]], COL_DEG[c], z);
@@ -271,39 +272,50 @@ __device__ bool stage_root(const double (*C)[20], const double (*L)[4], const do
             for (int j = k + 1; j < 10; j++) Mz[r * 10 + j] = sub(Mz[r * 10 + j], mul(f, Mz[k * 10 + j]));
         }
     }
-    double u[3] = {-Mz[7 * 10 + 9], -Mz[8 * 10 + 9], z};
-    for (int it = 0; it < 8; it++) {                                  // Gauss-Newton on the ten constraints
-        double pw[3][4];
-        for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
-        double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
-        for (int r = 0; r < 10; r++) {
-            double val = 0.0, g[3] = {0, 0, 0};
-            for (int m = 0; m < 20; m++) {
-                const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
-                const double c = C[r][m];
-                val = add(val, mul(c, mul(mul(pw[0][e[0]], pw[1][e[1]]), pw[2][e[2]])));
-                for (int a = 0; a < 3; a++) {
-                    if (e[a] == 0) continue;
-                    double t = (double)e[a];
-                    for (int b = 0; b < 3; b++) t = mul(t, pw[b][b == a ? e[b] - 1 : e[b]]);
-                    g[a] = add(g[a], mul(c, t));
-                }
-            }
-            JtJ[0] = add(JtJ[0], mul(g[0], g[0])); JtJ[1] = add(JtJ[1], mul(g[0], g[1])); JtJ[2] = add(JtJ[2], mul(g[0], g[2]));
-            JtJ[3] = add(JtJ[3], mul(g[1], g[1])); JtJ[4] = add(JtJ[4], mul(g[1], g[2])); JtJ[5] = add(JtJ[5], mul(g[2], g[2]));
-            Jtr[0] = add(Jtr[0], mul(g[0], val)); Jtr[1] = add(Jtr[1], mul(g[1], val)); Jtr[2] = add(Jtr[2], mul(g[2], val));
+    u[0] = -Mz[7 * 10 + 9]; u[1] = -Mz[8 * 10 + 9]; u[2] = z;
+    return true;
+}
+// value and gradient of constraint row `Cr` (20 monomial coefficients) at u: out = {val, g0, g1, g2}
+__device__ void stage_gn_row(const double* Cr, const double* u, double* out) {
+    double pw[3][4];
+    for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
+    double val = 0.0, g[3] = {0, 0, 0};
+    for (int m = 0; m < 20; m++) {
+        const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
+        const double c = Cr[m];
+        val = add(val, mul(c, mul(mul(pw[0][e[0]], pw[1][e[1]]), pw[2][e[2]])));
+        for (int a = 0; a < 3; a++) {
+            if (e[a] == 0) continue;
+            double t = (double)e[a];
+            for (int b = 0; b < 3; b++) t = mul(t, pw[b][b == a ? e[b] - 1 : e[b]]);
+            g[a] = add(g[a], mul(c, t));
         }
-        const double a = JtJ[0], b = JtJ[1], c = JtJ[2], d = JtJ[3], e = JtJ[4], f = JtJ[5];
-        const double c00 = sub(mul(d, f), mul(e, e)), c01 = sub(mul(c, e), mul(b, f)), c02 = sub(mul(b, e), mul(c, d));
-        const double c11 = sub(mul(a, f), mul(c, c)), c12 = sub(mul(b, c), mul(a, e)), c22 = sub(mul(a, d), mul(b, b));
-        const double det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
-        if (!(fabs(det) > 0.0) || !dfinite(det)) break;
-        const double dx = dvd(add(add(mul(c00, Jtr[0]), mul(c01, Jtr[1])), mul(c02, Jtr[2])), det);
-        const double dy = dvd(add(add(mul(c01, Jtr[0]), mul(c11, Jtr[1])), mul(c12, Jtr[2])), det);
-        const double dz = dvd(add(add(mul(c02, Jtr[0]), mul(c12, Jtr[1])), mul(c22, Jtr[2])), det);
-        if (!dfinite(dx) || !dfinite(dy) || !dfinite(dz)) break;
-        u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
     }
+    out[0] = val; out[1] = g[0]; out[2] = g[1]; out[3] = g[2];
+}
+// one Gauss-Newton update from the ten rows (rows[r] = {val, g0, g1, g2}, added in row order); false = the iteration stops here
+__device__ bool stage_gn_step(const double* rows, double* u) {
+    double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
+    for (int r = 0; r < 10; r++) {
+        const double val = rows[4 * r], g[3] = {rows[4 * r + 1], rows[4 * r + 2], rows[4 * r + 3]};
+        JtJ[0] = add(JtJ[0], mul(g[0], g[0])); JtJ[1] = add(JtJ[1], mul(g[0], g[1])); JtJ[2] = add(JtJ[2], mul(g[0], g[2]));
+        JtJ[3] = add(JtJ[3], mul(g[1], g[1])); JtJ[4] = add(JtJ[4], mul(g[1], g[2])); JtJ[5] = add(JtJ[5], mul(g[2], g[2]));
+        Jtr[0] = add(Jtr[0], mul(g[0], val)); Jtr[1] = add(Jtr[1], mul(g[1], val)); Jtr[2] = add(Jtr[2], mul(g[2], val));
+    }
+    const double a = JtJ[0], b = JtJ[1], c = JtJ[2], d = JtJ[3], e = JtJ[4], f = JtJ[5];
+    const double c00 = sub(mul(d, f), mul(e, e)), c01 = sub(mul(c, e), mul(b, f)), c02 = sub(mul(b, e), mul(c, d));
+    const double c11 = sub(mul(a, f), mul(c, c)), c12 = sub(mul(b, c), mul(a, e)), c22 = sub(mul(a, d), mul(b, b));
+    const double det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
+    if (!(fabs(det) > 0.0) || !dfinite(det)) return false;
+    const double dx = dvd(add(add(mul(c00, Jtr[0]), mul(c01, Jtr[1])), mul(c02, Jtr[2])), det);
+    const double dy = dvd(add(add(mul(c01, Jtr[0]), mul(c11, Jtr[1])), mul(c12, Jtr[2])), det);
+    const double dz = dvd(add(add(mul(c02, Jtr[0]), mul(c12, Jtr[1])), mul(c22, Jtr[2])), det);
+    if (!dfinite(dx) || !dfinite(dy) || !dfinite(dz)) return false;
+    u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
+    return true;
+}
+__device__ bool stage_root_finish(const double (*L)[4], const double* X, const double* u, double* E) {
+    const double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
     bool finite = true;
     for (int e = 0; e < 9; e++) {
         double v = mul(L[e][0], u[0]);
@@ -362,6 +374,16 @@ __device__ bool stage_root(const double (*C)[20], const double (*L)[4], const do
     }
     return false;
 }
+__device__ bool stage_root(const double (*C)[20], const double (*L)[4], const double* X, double z, double* E) {
+    double u[3];
+    if (!stage_root_init(C, z, u)) return false;
+    for (int it = 0; it < 8; it++) {                                  // Gauss-Newton on the ten constraints
+        double rows[40];
+        for (int r = 0; r < 10; r++) stage_gn_row(C[r], u, rows + 4 * r);
+        if (!stage_gn_step(rows, u)) break;
+    }
+    return stage_root_finish(L, X, u, E);
+}
 
 }  // namespace e5
 
@@ -394,7 +416,7 @@ __device__ __noinline__ int solve_essential5(const float* __restrict__ pts, cons
 
 // one warp per sample: `sm` points to E5_WARP_DOUBLES doubles of shared memory owned by this warp. Every lane returns the
 // model count; lane 0 .. (the lane that owns the winning root) writes `out`.
-#define E5_WARP_DOUBLES (20 + 36 + 200 + 22 + 22 + 242 + 24 + 24 + 20)
+#define E5_WARP_DOUBLES (20 + 36 + 200 + 22 + 22 + 242 + 24 + 24 + 20 + 60 + 800)
 __device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s, float* out, double* sm) {
     using namespace e5;
     const int lane = threadIdx.x & 31;
@@ -407,6 +429,8 @@ __device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s
     double* prev = sm + 542;                                           // 2 x 12 roots of the previous level
     double* cur = sm + 566;                                            // 2 x 12
     double* roots = sm + 590;                                          // 20
+    double* U = sm + 610;                                              // 20 x 3 Gauss-Newton iterates of the roots
+    double* rows = sm + 670;                                           // 20 roots x 10 constraint rows x {val, g0, g1, g2}
     __shared__ int sh_i[8][8];                                         // per warp: ok, deg0, deg1, nprev0, nprev1, nroots
     int* si = sh_i[(threadIdx.x >> 5) & 7];
     if (lane == 0) si[0] = stage_constraints(pts, s, X, L, C) ? 1 : 0;
@@ -476,8 +500,27 @@ __device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s
     }
     __syncwarp();
     const int nroots = si[5];
+    // stage 5 with the Gauss-Newton rows of ALL roots spread over the lanes (lane <-> (root, row), 10 rows per root), each root's
+    // own lane adds its ten rows in order and updates its iterate - the arithmetic of stage_root, ~4 dependent rows instead of 10
+    double u[3] = {0, 0, 0};
+    bool alive = lane < nroots;
+    if (alive) alive = stage_root_init(C, roots[lane], u);
+    bool iterating = alive;
+    for (int it = 0; it < 8; it++) {
+        const unsigned going = __ballot_sync(0xffffffffu, iterating);
+        if (!going) break;                                             // uniform
+        if (iterating) { U[3 * lane] = u[0]; U[3 * lane + 1] = u[1]; U[3 * lane + 2] = u[2]; }
+        __syncwarp();
+        for (int base = 0; base < 10 * nroots; base += 32) {
+            const int w = base + lane;
+            if (w < 10 * nroots && ((going >> (w / 10)) & 1u)) stage_gn_row(C[w % 10], U + 3 * (w / 10), rows + 4 * w);
+        }
+        __syncwarp();
+        if (iterating) iterating = stage_gn_step(rows + 40 * lane, u);
+        __syncwarp();
+    }
     double E[9];
-    const bool ok = lane < nroots && stage_root(C, L, X, roots[lane], E);
+    const bool ok = alive && stage_root_finish(L, X, u, E);
     const unsigned win = __ballot_sync(0xffffffffu, ok);
     if (!win) return 0;
     if (lane == __ffs(win) - 1) for (int e = 0; e < 9; e++) out[e] = (float)E[e];

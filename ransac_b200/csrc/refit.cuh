@@ -62,11 +62,14 @@ __device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, d
                 p = (r + lane + 1) % n; q = (r - lane - 1 + n) % n;
                 if (p > q) { const int t = p; p = q; q = t; }
                 const sd apq(S[p * n + q]);
-                if (apq.v != 0.0 && !((apq * apq).v <= (sd(1e-34) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v)) {
-                    const sd theta = (sd(S[q * n + q]) - sd(S[p * n + p])) / (sd(2.0) * apq);
-                    const sd tt = sd(1.0) / (sd(fabs(theta.v)) + dsqrt(theta * theta + sd(1.0)));
-                    const sd t = theta.v < 0.0 ? -tt : tt;
-                    const sd cc = sd(1.0) / dsqrt(t * t + sd(1.0)), ss = t * cc;
+                if (apq.v != 0.0 && !((apq * apq).v <= (sd(1e-24) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v)) {
+                    // t = sgn(d) b / (|d| + sqrt(d^2 + b^2)), c = sqrt(w) (1 / w), w = t^2 + 1: three dependent div / sqrt, not five
+                    const sd d = sd(S[q * n + q]) - sd(S[p * n + p]), b = sd(2.0) * apq;
+                    const sd rr = dsqrt(d * d + b * b);
+                    const sd t0 = b / (sd(fabs(d.v)) + rr);
+                    const sd t = d.v < 0.0 ? -t0 : t0;
+                    const sd w = t * t + sd(1.0);
+                    const sd cc = dsqrt(w) * (sd(1.0) / w), ss = t * cc;
                     if (dfinite(cc.v) && dfinite(ss.v)) { c = cc.v; s = ss.v; on = true; }
                 }
             }
