@@ -29,19 +29,22 @@ __device__ __constant__ signed char QL[10][4] = {{0, 2, 5, 4}, {3, 1, 7, 6}, {12
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+// one copy of the IEEE division sequence: the solver is ~11 000 instructions when everything is inlined, more than the instruction
+// cache holds - the warps of an SM are at different places of it and 'no instruction' was the top stall reason (ncu)
+__device__ __noinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
 
-__device__ void acc_ll(double* q, const double* a, const double* b, double s) {
+__device__ __noinline__ void acc_ll(double* q, const double* a, const double* b, double s) {
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++) { const int k = LL[i][j]; q[k] = add(q[k], mul(mul(a[i], b[j]), s)); }
 }
-__device__ void acc_ql(double* c, const double* q, const double* l, double s) {
+__device__ __noinline__ void acc_ql(double* c, const double* q, const double* l, double s) {
     for (int i = 0; i < 10; i++)
         for (int j = 0; j < 4; j++) { const int k = QL[i][j]; c[k] = add(c[k], mul(mul(q[i], l[j]), s)); }
 }
 
-__device__ double det_lu(double* a, int n) {
+__device__ __noinline__ double det_lu(double* a, int n) {
     double det = 1.0;
+#pragma unroll 1
     for (int k = 0; k < n; k++) {
         int piv = k;
         double best = fabs(a[k * n + k]);
@@ -58,18 +61,18 @@ __device__ double det_lu(double* a, int n) {
     return det;
 }
 
-__device__ double horner(const double* c, int deg, double x) {
+__device__ __noinline__ double horner(const double* c, int deg, double x) {
     double v = c[deg];
     for (int i = deg - 1; i >= 0; i--) v = add(mul(v, x), c[i]);
     return v;
 }
-__device__ double horner_rev(const double* c, int deg, double w) {
+__device__ __noinline__ double horner_rev(const double* c, int deg, double w) {
     double v = c[0];
     for (int i = 1; i <= deg; i++) v = add(mul(v, w), c[i]);
     return v;
 }
 
-__device__ double bisect(const double* c, int deg, double l, double r, double pl) {
+__device__ __noinline__ double bisect(const double* c, int deg, double l, double r, double pl) {
     if (pl == 0.0) return l;
     const bool neg_left = pl < 0.0;
     for (int it = 0; it < 200; it++) {
@@ -117,7 +120,8 @@ __device__ int real_roots(const double* c, int deg, double* roots) {
 
 // Gauss-Jordan null space of the 5 x 9 design matrix (rows x 9, row-major, destroyed): same operations as gauss_jordan9
 // and as the host restatement; basis vector q has v[5+q] = 1, v[i<5] = -A[i][5+q].
-__device__ bool null_space5(double* A, double* basis) {
+__device__ __noinline__ bool null_space5(double* A, double* basis) {
+#pragma unroll 1
     for (int k = 0; k < 5; k++) {
         int piv = k;
         double best = fabs(A[k * 9 + k]);
@@ -151,9 +155,12 @@ __device__ bool null_space5(double* A, double* basis) {
 namespace e5 {
 
 // stage 1: points -> X = [x1[5] y1[5] x2[5] y2[5]], L[9][4] (E_ij as linear forms), C[10][20] (the ten cubic constraints)
-__device__ bool stage_constraints(const float* __restrict__ pts, const int* s, double* X, double (*L)[4], double (*C)[20]) {
+// stage 1 in pieces (the warp form runs the nine Q blocks and the ten constraint rows on separate lanes; the one-thread form calls
+// them in a loop - the same operations in the same order per block / row)
+__device__ __noinline__ bool stage_basis(const float* __restrict__ pts, const int* s, double* X, double (*L)[4]) {
     double A[45];
     double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
+#pragma unroll 1
     for (int i = 0; i < 5; i++) {
         const float4 p = reinterpret_cast<const float4*>(pts)[s[i]];
         x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w;
@@ -163,8 +170,10 @@ __device__ bool stage_constraints(const float* __restrict__ pts, const int* s, d
     }
     double Bs[36];
     if (!null_space5(A, Bs)) return false;
+#pragma unroll 1
     for (int a = 3; a >= 0; a--) {                                        // modified Gram-Schmidt, last vector first
         double* v = Bs + 9 * a;
+#pragma unroll 1
         for (int b = 3; b > a; b--) {
             const double* u = Bs + 9 * b;
             double dot = 0.0;
@@ -178,34 +187,50 @@ __device__ bool stage_constraints(const float* __restrict__ pts, const int* s, d
         for (int e = 0; e < 9; e++) v[e] = mul(v[e], inv);
     }
     for (int e = 0; e < 9; e++) for (int q = 0; q < 4; q++) L[e][q] = Bs[q * 9 + e];
-    for (int r = 0; r < 10; r++) for (int m = 0; m < 20; m++) C[r][m] = 0.0;
-    double Q[3][3][10];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int m = 0; m < 10; m++) Q[i][j][m] = 0.0;
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++)
-            for (int k = 0; k < 3; k++) acc_ll(Q[i][j], L[3 * i + k], L[3 * j + k], 1.0);
-    double tr[10];
-    for (int m = 0; m < 10; m++) tr[m] = add(add(Q[0][0][m], Q[1][1][m]), Q[2][2][m]);
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-            double* c = C[3 * i + j];
-            for (int k = 0; k < 3; k++) acc_ql(c, Q[i][k], L[3 * k + j], 2.0);
-            acc_ql(c, tr, L[3 * i + j], -1.0);
-        }
-    double m0[10], m1[10], m2[10];
-    for (int m = 0; m < 10; m++) { m0[m] = 0.0; m1[m] = 0.0; m2[m] = 0.0; }
-    acc_ll(m0, L[4], L[8], 1.0); acc_ll(m0, L[5], L[7], -1.0);
-    acc_ll(m1, L[3], L[8], 1.0); acc_ll(m1, L[5], L[6], -1.0);
-    acc_ll(m2, L[3], L[7], 1.0); acc_ll(m2, L[4], L[6], -1.0);
-    acc_ql(C[9], m0, L[0], 1.0); acc_ql(C[9], m1, L[1], -1.0); acc_ql(C[9], m2, L[2], 1.0);
+    return true;
+}
+// Q[i][j] = sum_k L[3i+k] x L[3j+k] (quadratic forms of E E'): block b = 3 i + j -> Qb[10]
+__device__ __noinline__ void stage_q_block(const double (*L)[4], int b, double* Qb) {
+    const int i = b / 3, j = b % 3;
+    for (int m = 0; m < 10; m++) Qb[m] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) acc_ll(Qb, L[3 * i + k], L[3 * j + k], 1.0);
+}
+// constraint row r < 9 (2 E E' E - tr(E E') E, entry (i, j) = (r / 3, r % 3)) or r = 9 (det E): Cr[20]
+__device__ __noinline__ void stage_c_row(const double (*L)[4], const double* Q /* [9][10] */, const double* tr, int r, double* Cr) {
+    for (int m = 0; m < 20; m++) Cr[m] = 0.0;
+    if (r < 9) {
+        const int i = r / 3, j = r % 3;
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) acc_ql(Cr, Q + 10 * (3 * i + k), L[3 * k + j], 2.0);
+        acc_ql(Cr, tr, L[3 * i + j], -1.0);
+    } else {
+        double m0[10], m1[10], m2[10];
+        for (int m = 0; m < 10; m++) { m0[m] = 0.0; m1[m] = 0.0; m2[m] = 0.0; }
+        acc_ll(m0, L[4], L[8], 1.0); acc_ll(m0, L[5], L[7], -1.0);
+        acc_ll(m1, L[3], L[8], 1.0); acc_ll(m1, L[5], L[6], -1.0);
+        acc_ll(m2, L[3], L[7], 1.0); acc_ll(m2, L[4], L[6], -1.0);
+        acc_ql(Cr, m0, L[0], 1.0); acc_ql(Cr, m1, L[1], -1.0); acc_ql(Cr, m2, L[2], 1.0);
+    }
+}
+__device__ bool stage_constraints(const float* __restrict__ pts, const int* s, double* X, double (*L)[4], double (*C)[20]) {
+    if (!stage_basis(pts, s, X, L)) return false;
+    double Q[90], tr[10];
+#pragma unroll 1
+    for (int b = 0; b < 9; b++) stage_q_block(L, b, Q + 10 * b);
+    for (int m = 0; m < 10; m++) tr[m] = add(add(Q[m], Q[40 + m]), Q[80 + m]);
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) stage_c_row(L, Q, tr, r, C[r]);
     return true;
 }
 
 // stage 2: det M(z) (pass 0) or det(M(1/w) diag(w^deg)) (pass 1) at node t of the 11 equispaced nodes in [-1, 1]
-__device__ double stage_det(const double (*C)[20], int pass, int t) {
+__device__ __noinline__ double stage_det(const double (*C)[20], int pass, int t) {
     double Mz[100];
     const double z = dvd((double)(t - 5), 5.0);
+#pragma unroll 1
     for (int r = 0; r < 10; r++)
+#pragma unroll 1
         for (int c = 0; c < 10; c++)
             Mz[r * 10 + c] = pass == 0 ? horner(&C[r][COL_FIRST[c]], COL_DEG[c], z) : horner_rev(&C[r][COL_FIRST[c]], COL_DEG[c], z);
     return det_lu(Mz, 10);
@@ -213,13 +238,16 @@ __device__ double stage_det(const double (*C)[20], int pass, int t) {
 
 // stage 3: 11 determinant values -> monomial coefficients (Newton divided differences); returns the degree after trimming,
 // 0 when there is nothing to solve, -1 when a coefficient is not finite (the solver then returns no model)
-__device__ int stage_coefficients(double* dd, double* coef) {
+__device__ __noinline__ int stage_coefficients(double* dd, double* coef) {
     double zs[11];
     for (int t = 0; t < 11; t++) zs[t] = dvd((double)(t - 5), 5.0);
+#pragma unroll 1
     for (int lev = 1; lev < 11; lev++)
+#pragma unroll 1
         for (int t = 10; t >= lev; t--) dd[t] = dvd(sub(dd[t], dd[t - 1]), sub(zs[t], zs[t - lev]));
     for (int i = 0; i < 11; i++) coef[i] = 0.0;
     coef[0] = dd[10];
+#pragma unroll 1
     for (int t = 9; t >= 0; t--) {
         for (int i = 10; i >= 1; i--) coef[i] = sub(coef[i - 1], mul(coef[i], zs[t]));
         coef[0] = sub(dd[t], mul(coef[0], zs[t]));
@@ -254,10 +282,13 @@ __device__ void stage_sort(double* roots, int& nroots) {                 // asce
 // stage 5: one root z -> x, y (Gauss-Jordan on [M(z) | last column]), eight Gauss-Newton steps, E, cheirality vote.
 // In pieces, so that the warp form can spread the Gauss-Newton rows of all roots over its lanes: the pieces do the same
 // operations in the same order whoever calls them.
-__device__ bool stage_root_init(const double (*C)[20], double z, double* u) {
+__device__ __noinline__ bool stage_root_init(const double (*C)[20], double z, double* u) {
     double Mz[100];
+#pragma unroll 1
     for (int r = 0; r < 10; r++)
+#pragma unroll 1
         for (int c = 0; c < 10; c++) Mz[r * 10 + c] = horner(&C[r][COL_FIRST[c]], COL_DEG[c], z);
+#pragma unroll 1
     for (int k = 0; k < 9; k++) {
         int piv = k;
         double best = fabs(Mz[k * 10 + k]);
@@ -276,10 +307,11 @@ __device__ bool stage_root_init(const double (*C)[20], double z, double* u) {
     return true;
 }
 // value and gradient of constraint row `Cr` (20 monomial coefficients) at u: out = {val, g0, g1, g2}
-__device__ void stage_gn_row(const double* Cr, const double* u, double* out) {
+__device__ __noinline__ void stage_gn_row(const double* Cr, const double* u, double* out) {
     double pw[3][4];
     for (int a = 0; a < 3; a++) { pw[a][0] = 1.0; pw[a][1] = u[a]; pw[a][2] = mul(u[a], u[a]); pw[a][3] = mul(pw[a][2], u[a]); }
     double val = 0.0, g[3] = {0, 0, 0};
+#pragma unroll 1
     for (int m = 0; m < 20; m++) {
         const int e[3] = {MONO[m][0], MONO[m][1], MONO[m][2]};
         const double c = Cr[m];
@@ -294,7 +326,7 @@ __device__ void stage_gn_row(const double* Cr, const double* u, double* out) {
     out[0] = val; out[1] = g[0]; out[2] = g[1]; out[3] = g[2];
 }
 // one Gauss-Newton update from the ten rows (rows[r] = {val, g0, g1, g2}, added in row order); false = the iteration stops here
-__device__ bool stage_gn_step(const double* rows, double* u) {
+__device__ __noinline__ bool stage_gn_step(const double* rows, double* u) {
     double JtJ[6] = {0, 0, 0, 0, 0, 0}, Jtr[3] = {0, 0, 0};
     for (int r = 0; r < 10; r++) {
         const double val = rows[4 * r], g[3] = {rows[4 * r + 1], rows[4 * r + 2], rows[4 * r + 3]};
@@ -314,7 +346,7 @@ __device__ bool stage_gn_step(const double* rows, double* u) {
     u[0] = sub(u[0], dx); u[1] = sub(u[1], dy); u[2] = sub(u[2], dz);
     return true;
 }
-__device__ bool stage_root_finish(const double (*L)[4], const double* X, const double* u, double* E) {
+__device__ __noinline__ bool stage_root_finish(const double (*L)[4], const double* X, const double* u, double* E) {
     const double *x1 = X, *y1 = X + 5, *x2 = X + 10, *y2 = X + 15;
     bool finite = true;
     for (int e = 0; e < 9; e++) {
@@ -352,6 +384,7 @@ __device__ bool stage_root_finish(const double (*L)[4], const double* X, const d
         tE[3 + c] = sub(mul(tv[2], En[0 + c]), mul(tv[0], En[6 + c]));
         tE[6 + c] = sub(mul(tv[0], En[3 + c]), mul(tv[1], En[0 + c]));
     }
+#pragma unroll 1
     for (int cam = 0; cam < 4; cam++) {
         double R[9], t[3];
         const double rs = (cam < 2) ? -1.0 : 1.0, ts = (cam & 1) ? -1.0 : 1.0;
@@ -433,9 +466,19 @@ __device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s
     double* rows = sm + 670;                                           // 20 roots x 10 constraint rows x {val, g0, g1, g2}
     __shared__ int sh_i[8][8];                                         // per warp: ok, deg0, deg1, nprev0, nprev1, nroots
     int* si = sh_i[(threadIdx.x >> 5) & 7];
-    if (lane == 0) si[0] = stage_constraints(pts, s, X, L, C) ? 1 : 0;
+    if (lane == 0) si[0] = stage_basis(pts, s, X, L) ? 1 : 0;
     __syncwarp();
     if (!si[0]) return 0;
+    {                                                                  // the nine Q blocks, then the ten constraint rows, one lane each
+        double* Q = rows;                                              // 90 + 10 doubles of the region stage 5 uses later
+        double* tr = rows + 90;
+        if (lane < 9) stage_q_block(L, lane, Q + 10 * lane);
+        __syncwarp();
+        if (lane < 10) tr[lane] = add(add(Q[lane], Q[40 + lane]), Q[80 + lane]);
+        __syncwarp();
+        if (lane < 10) stage_c_row(L, Q, tr, lane, C[lane]);
+        __syncwarp();
+    }
     if (lane < 22) dd[lane] = stage_det(C, lane / 11, lane % 11);
     __syncwarp();
     if (lane < 2) {
