@@ -44,7 +44,7 @@ T lane_sum(int n, F value) {
  * round-robin order - round r = 0..n-1 rotates the (n-1)/2 DISJOINT pairs {(r+k) mod n, (r-k) mod n}, k = 1..(n-1)/2 (index r sits
  * out; every pair occurs once per sweep). The angles of a round come from the matrix as it is at the start of the round, then
  * the column updates of all its pairs, then the row updates, then V - the order the device code uses, where the pairs of a
- * round run side by side. At most 12 sweeps; rotations with |apq| <= 1e-12 sqrt(|app aqq|) are skipped and the first sweep
+ * round run side by side. At most 12 sweeps; rotations with |apq| <= 1e-12 max(|app|, |aqq|) are skipped and the first sweep
  * without a rotation ends the loop. */
 void smallest_eigenvector(double* S, int n, double* vec) {
     double V[81];
@@ -63,7 +63,11 @@ void smallest_eigenvector(double* S, int n, double* vec) {
                 P[e] = p; Q[e] = q; on[e] = false;
                 const double apq = S[p * n + q];
                 if (apq == 0.0) continue;
-                if (apq * apq <= 1e-24 * std::fabs(S[p * n + p] * S[q * n + q])) continue;   /* |apq| <= 1e-12 sqrt(|app aqq|): the result is rounded to float */
+                {   /* |apq| <= 1e-12 max(|app|, |aqq|): what the EIGENVECTOR needs (it is rounded to float); a bound relative to
+                     * sqrt(|app aqq|) would keep polishing the pairs of the near-null direction for the sake of its eigenvalue */
+                    const double big = std::fmax(std::fabs(S[p * n + p]), std::fabs(S[q * n + q]));
+                    if (apq * apq <= 1e-24 * (big * big)) continue;
+                }
                 /* tan of the rotation angle in the hypot form, t = sgn(d) b / (|d| + sqrt(d^2 + b^2)) with d = aqq - app, b = 2 apq,
                  * and c = sqrt(w) (1 / w), w = t^2 + 1: three dependent divisions / square roots instead of five */
                 const double d = S[q * n + q] - S[p * n + p], b = 2.0 * apq;

@@ -62,7 +62,8 @@ __device__ void refit_smallest_eigenvector_warp(double* S, int n, double* vec, d
                 p = (r + lane + 1) % n; q = (r - lane - 1 + n) % n;
                 if (p > q) { const int t = p; p = q; q = t; }
                 const sd apq(S[p * n + q]);
-                if (apq.v != 0.0 && !((apq * apq).v <= (sd(1e-24) * sd(fabs((sd(S[p * n + p]) * sd(S[q * n + q])).v))).v)) {
+                const sd big(fmax(fabs(S[p * n + p]), fabs(S[q * n + q])));       // |apq| <= 1e-12 max(|app|, |aqq|): enough for the eigenvector
+                if (apq.v != 0.0 && !((apq * apq).v <= (sd(1e-24) * (big * big)).v)) {
                     // t = sgn(d) b / (|d| + sqrt(d^2 + b^2)), c = sqrt(w) (1 / w), w = t^2 + 1: three dependent div / sqrt, not five
                     const sd d = sd(S[q * n + q]) - sd(S[p * n + p]), b = sd(2.0) * apq;
                     const sd rr = dsqrt(d * d + b * b);

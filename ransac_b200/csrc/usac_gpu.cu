@@ -711,7 +711,8 @@ static void plan_chunks(const usac_gpu_ctx* c, int slots, int mblocks, int max_p
     const long long warps = (long long)c->prop.multiProcessorCount * std::max(USAC_SCORE_GRID_CTAS, USAC_SQ_MIN_CTAS) * (USAC_SCORE_THREADS / 32);
     const long long base = (long long)slots * mblocks * (USAC_SCORE_THREADS / 32);
     // a work item costs ~2 us before its first trip (draw, record load, first tile): items of a large problem stay >= 8 tiles
-    const int min_tiles = max_pairs >= 65536 ? 8 : 2;
+    static const int min_tiles_env = [] { const char* e = getenv("USAC_GPU_MIN_TILES"); return e ? atoi(e) : 0; }();   // tuning knob
+    const int min_tiles = min_tiles_env > 0 ? min_tiles_env : (max_pairs >= 65536 ? 8 : 2);
     const int max_chunks = std::min(65535, std::max(1, max_pairs / (min_tiles * USAC_TILE_PAIRS)));
     int nc = (int)std::min<long long>((per_warp * warps + base - 1) / base, max_chunks);
     nc = std::max(nc, 1);
