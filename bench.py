@@ -212,6 +212,10 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    from ransac_b200 import dist as D0
+    # several ranks on one host: bind each to the CPUs next to its GPU before any pinned allocation (staging buffers on the GPU's own
+    # NUMA node); a single rank keeps every host core (the cpu_baseline leg uses them)
+    numa_cpus = D0.bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.problems
@@ -365,6 +369,20 @@ def run_native(args):
     timed_e2e(2)
     ms_e2e, stats_e2e = timed_e2e(args.steps)
     useful_e2e = sum(s[0] for s in stats_e2e)
+    # the upload alone, all ranks at once (what the host memory system and the PCIe tree give `world` GPUs together): the floor of an
+    # end-to-end step, since every step uploads every point set
+    scratch = torch.empty_like(host, device="cuda")
+    evu0, evu1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        scratch.copy_(host, non_blocking=True)
+        barrier()
+        evu0.record(stream)
+        for _ in range(5):
+            scratch.copy_(host, non_blocking=True)
+        evu1.record(stream)
+    barrier()
+    h2d_only_ms = evu0.elapsed_time(evu1) / 5
+    del scratch
     # results: one 176-byte FitState record per problem at the end + one `done` int per still-active problem per round
     d2h_step = B * 176 + sum(s[6] for s in stats_e2e) / args.steps * B * 4   # (upper bound: every problem active in every round)
 
@@ -376,6 +394,10 @@ def run_native(args):
         pipe_ctx, pipe_ctx2 = [], []
         c5 = c5_leg(args, rank, world, local, max(5, args.steps), 3)
 
+    h2d_all = torch.tensor([h2d_only_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d_all, op=dist.ReduceOp.MAX)
+    h2d_only_ms = float(h2d_all.item())
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([useful, useful_e2e, executed_p, launches], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -435,7 +457,10 @@ def run_native(args):
                            "evals_executed_per_s": executed_all / (ms_all * 1e-3), "useful_fraction": useful / max(executed_p, 1)},
                 "clocks": clk, "gpu_launches": int(launches_all),
                 "e2e": {"value": useful_e2e_all / (ms_e2e_all * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": B * N_POINTS * 16,
-                        "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e_all / args.steps, "ms_per_fit": ms_e2e_all / args.steps / B},
+                        "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e_all / args.steps, "ms_per_fit": ms_e2e_all / args.steps / B,
+                        "h2d_only_ms_per_step": h2d_only_ms, "h2d_only_gb_per_s_per_gpu": B * N_POINTS * 16 / (h2d_only_ms * 1e-3) / 1e9,
+                        "h2d_note": "the step's uploads alone, all ranks at once (max over ranks): the floor of an end-to-end step; "
+                                    "ranks are bound to the CPUs next to their GPU before pinned memory is allocated: " + str(numa_cpus)},
                 "roofline": roofline}
         if c5 is not None:
             line["config"]["c5"] = c5

@@ -21,6 +21,31 @@ def init(backend=None):
     return rank, world
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE it allocates pinned
+    host memory, so that the staging buffers of the end-to-end path live on the GPU's own NUMA node instead of wherever the
+    launcher happened to start the rank (first-touch placement). Returns the cpulist string, or None when nothing was done."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:   # noqa: BLE001 - no sysfs entry / not permitted: leave the placement to the launcher
+        return None
+
+
 def _dev():
     return torch.device("cuda", torch.cuda.current_device()) if dist.is_initialized() and dist.get_backend() == "nccl" else torch.device("cpu")
 
