@@ -1358,6 +1358,163 @@ static void print_marks(usac_gpu_ctx* c) {
     fprintf(stderr, "%s\n", line.c_str());
 }
 
+// models (slot, q) of a round -> packed [n][9] (the winners of the problems of a batched SPRT round)
+__global__ void gather_models_kernel(const float* __restrict__ models_raw, const int2* __restrict__ picks, int n, int KS, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 9) return;
+    const int2 pk = picks[i / 9];
+    out[i] = models_raw[((size_t)pk.x * KS + pk.y) * 9 + i % 9];
+}
+
+// SPRT rounds for SEVERAL problems in flight (uniform / NAPSAC sampler, no LO): one set of launches per round for all problems
+// that are still searching, then the host replays every problem's K hypotheses (the same replay as below, problem by problem -
+// it needs libm for the SPRT bound) and the models of the new best hypotheses come back through one gather. Per problem the
+// result is that of the one-problem-at-a-time path (rounds of K, test frozen within a round).
+static int fit_sprt_batch(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results, int K) {
+    const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
+    const float log_1_p = (float)logf(1 - cfg->confidence);
+    const int KS = K * S;
+    const unsigned before_sprt = cfg->max_hypothesis_test_before_sprt ? cfg->max_hypothesis_test_before_sprt : 20u;
+    int rc = ensure_round_buffers(c, P, K, 1, 1);
+    if (rc) return rc;
+    CUDA_TRY(c, c->h_rp_nmodels.ensure((size_t)P * K));
+    CUDA_TRY(c, c->h_rp_res.ensure((size_t)P * KS));
+    CUDA_TRY(c, c->h_rp_models.ensure((size_t)P * 9));
+    CUDA_TRY(c, c->h_rp_scores.ensure((size_t)P));                    // int2 picks (slot, q)
+    CUDA_TRY(c, c->d_model_scores.ensure((size_t)P));                 // the same on the device
+    CUDA_TRY(c, c->d_q_models.ensure((size_t)P * 9));
+    std::vector<SprtHost> sprt(P);
+    std::vector<int> active(P);
+    for (int p = 0; p < P; p++) {
+        init_state(c->h_state[p], c->h_prob[p], c->est, cfg->max_iterations, 0);
+        sprt[p].init(c->est, (unsigned)c->h_prob[p].n, (unsigned)m, cfg->max_iterations);
+        active[p] = p;
+    }
+    while (!active.empty()) {
+        const int slots = (int)active.size();
+        for (int q = 0; q < slots; q++) {
+            const int p = active[q];
+            FitState& hs = c->h_state[p];
+            const SprtTestH& t = sprt[p].current();
+            hs.sprt_eps = t.epsilon; hs.sprt_delta = t.delta; hs.sprt_A = t.A; hs.sprt_cursor = sprt[p].cursor;
+            c->h_active[q] = p;
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof(FitState) * P, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_active.p, c->h_active, sizeof(int) * slots, cudaMemcpyHostToDevice, c->stream));
+        RoundArgs a;
+        fill_round_args(c, a, cfg->sampler, K);
+        a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
+        a.table_rows = cfg->sample_table_rows; a.nchunks = 1; a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
+        a.before_sprt = before_sprt;
+        launch_sampler(c, a, slots);
+        switch (c->est) {
+            case USAC_EST_LINE2D: launch_solve<USAC_EST_LINE2D>(c, a, slots); break;
+            case USAC_EST_HOMOGRAPHY: launch_solve<USAC_EST_HOMOGRAPHY>(c, a, slots); break;
+            case USAC_EST_FUNDAMENTAL: launch_solve<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
+            default: launch_solve<USAC_EST_ESSENTIAL>(c, a, slots); break;
+        }
+        prepare_kernel<<<slots, 256, 0, c->stream>>>(a);
+        c->last_launches++;
+        switch (c->est) {
+            case USAC_EST_LINE2D: rc = launch_walk<USAC_EST_LINE2D>(c, a, slots); break;
+            case USAC_EST_HOMOGRAPHY: rc = launch_walk<USAC_EST_HOMOGRAPHY>(c, a, slots); break;
+            case USAC_EST_FUNDAMENTAL: rc = launch_walk<USAC_EST_FUNDAMENTAL>(c, a, slots); break;
+            default: rc = launch_walk<USAC_EST_ESSENTIAL>(c, a, slots); break;
+        }
+        if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_rp_res.p, c->d_sprt_res.p, sizeof(SprtModelResult) * (size_t)slots * KS, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_rp_nmodels.p, c->d_nmodels.p, sizeof(int) * (size_t)slots * K, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));              // the host sync of the round
+        CUDA_TRY(c, cudaGetLastError());
+
+        int npicks = 0;
+        int2* picks = c->h_rp_scores.p;
+        std::vector<int> pick_problem;
+        std::vector<int> next;
+        for (int slot = 0; slot < slots; slot++) {
+            const int p = active[slot];
+            FitState& hs = c->h_state[p];
+            SprtHost& sp = sprt[p];
+            const unsigned n = (unsigned)c->h_prob[p].n;
+            const SprtModelResult* h_res = c->h_rp_res.p + (size_t)slot * KS;
+            const int* h_nmodels = c->h_rp_nmodels.p + (size_t)slot * K;
+            // ---- replay the round in hypothesis order (ransac.cpp:58-139), as fit_host_replay does ----
+            const unsigned long long hyp0 = hs.samples_drawn;
+            const unsigned iters_round_start = hs.iters;
+            long long last_improving = -1;
+            unsigned long long rej_inl = 0, rej_pts = 0, evals = 0, useful = 0;
+            bool stopped = false, done = false;
+            int best_q = -1;
+            for (int j = 0; j < K; j++) {
+                if (!stopped && !(hs.iters < hs.max_iters)) { stopped = true; done = true; }
+                for (int i = 0; i < h_nmodels[j]; i++) {
+                    const int q = j * S + i;
+                    const SprtModelResult& r = h_res[q];
+                    const unsigned long long cost = (unsigned long long)r.tested_pts + ((!r.good && hyp0 + j < before_sprt) ? (unsigned long long)(n - r.tested_pts) : 0ull);
+                    evals += cost;
+                    if (stopped) continue;
+                    useful += cost;
+                    if (r.good) { if (r.tested_inl > hs.best_cnt) last_improving = r.tested_inl; }
+                    else { rej_inl += (unsigned long long)r.tested_inl; rej_pts += (unsigned long long)r.tested_pts; }
+                    if (!r.good && hs.iters >= before_sprt) { hs.iters++; continue; }       // ransac.cpp:77-85
+                    const int inl = r.full_inl;
+                    const float score = (float)inl;                                          // sprt.hpp:240-241
+                    if (inl > hs.best_cnt || (inl == hs.best_cnt && score > hs.best_sum)) {   // Score::bigger
+                        hs.best_cnt = inl; hs.best_sum = score; hs.best_hyp = (long long)(hyp0 + j); hs.best_midx = i;
+                        best_q = q;
+                        hs.max_iters = standard_termination_value((unsigned)inl, n, m, log_1_p, cfg->max_iterations);
+                        hs.max_iters = std::min(hs.max_iters, sp.upper_bound(inl));           // ransac.cpp:129-133
+                    }
+                }
+                if (!stopped) hs.iters++;
+            }
+            {                                                        // one re-design per round (state is frozen within a round)
+                const SprtTestH t = sp.current();
+                double eps = t.epsilon, delta = t.delta;
+                bool redesign = false;
+                if (last_improving >= 0) { eps = (float)last_improving / n; redesign = true; }
+                if (rej_pts > 0) {
+                    const float delta_estimated = (float)rej_inl / (unsigned)rej_pts;
+                    if (delta_estimated > 0 && std::fabs(t.delta - delta_estimated) / t.delta > 0.05) { delta = delta_estimated; redesign = true; }
+                }
+                if (redesign) sp.push(eps, delta, (int)iters_round_start);
+                sp.cursor = (unsigned)(((unsigned long long)sp.cursor + 32ull * (unsigned long long)KS) % n);
+                hs.sprt_ntests = (int)sp.hist.size();
+            }
+            hs.samples_drawn += (unsigned)K;
+            hs.rounds++;
+            hs.evals += evals;
+            hs.useful_evals += useful;
+            if (best_q >= 0) { picks[npicks] = make_int2(slot, best_q); pick_problem.push_back(p); npicks++; }
+            if (!done && hs.iters < hs.max_iters) next.push_back(p);
+            else hs.done = 1;
+        }
+        if (npicks) {                                                // the models of this round's new best hypotheses, one gather
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_model_scores.p, picks, sizeof(int2) * npicks, cudaMemcpyHostToDevice, c->stream));
+            gather_models_kernel<<<(npicks * 9 + 255) / 256, 256, 0, c->stream>>>(c->d_models_raw.p, c->d_model_scores.p, npicks, KS, c->d_q_models.p);
+            c->last_launches++;
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_rp_models.p, c->d_q_models.p, sizeof(float) * 9 * npicks, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < npicks; i++) {
+                FitState& hs = c->h_state[pick_problem[i]];
+                for (int k = 0; k < 9; k++) hs.best_model[k] = 0.f;
+                for (int k = 0; k < w; k++) hs.best_model[k] = c->h_rp_models.p[(size_t)i * 9 + k];
+            }
+        }
+        active.swap(next);
+    }
+    for (int p = 0; p < P; p++) {
+        const FitState& hs = c->h_state[p];
+        usac_fit_result& r = results[p];
+        memset(&r, 0, sizeof(r));
+        for (int i = 0; i < w; i++) r.model[i] = hs.best_model[i];
+        r.inliers = hs.best_cnt; r.score = hs.best_sum; r.iterations = hs.iters; r.samples_drawn = hs.samples_drawn;
+        r.best_hyp = hs.best_hyp; r.best_model_idx = hs.best_midx; r.rounds = hs.rounds; r.evals = hs.evals; r.useful_evals = hs.useful_evals;
+        r.msac = nanf("");
+    }
+    return USAC_OK;
+}
+
 static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_result* results, int K) {
     const int P = c->P, m = usac_sample_size(c->est), S = usac_models_per_sample(c->est), w = c->est == USAC_EST_LINE2D ? 3 : 9;
     const bool is_prosac = cfg->sampler.sampler == USAC_SAMPLER_PROSAC, is_sprt = cfg->sprt != 0;
@@ -1699,7 +1856,9 @@ extern "C" int usac_gpu_fit(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_r
     if (host_replay) {
         c->score_events_used = 0; c->last_launches = 0; c->last_score_launches = 0;
         cudaEventRecord(c->ev0, c->stream);
-        rc = fit_host_replay(c, cfg, results, K);
+        static const bool batch_off = getenv("USAC_GPU_SPRT_BATCH") && atoi(getenv("USAC_GPU_SPRT_BATCH")) == 0;   // A/B knob
+        const bool batch = !batch_off && c->P > 1 && cfg->sprt && !cfg->lo && cfg->sampler.sampler != USAC_SAMPLER_PROSAC && cfg->sampler.rng != USAC_RNG_TABLE;
+        rc = batch ? fit_sprt_batch(c, cfg, results, K) : fit_host_replay(c, cfg, results, K);
         cudaEventRecord(c->ev1, c->stream);
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         collect_timing(c);

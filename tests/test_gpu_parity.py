@@ -463,6 +463,26 @@ def test_fit_sprt_matches_oracle(ctx, cfg, K, max_it):
         assert_fit_equal_sprt(r, ref)
 
 
+@pytest.mark.parametrize("cfg,K", [(2, 128), (3, 64), (4, 64)])
+def test_fit_sprt_batch_of_problems_matches_oracle(ctx, cfg, K):
+    """Several problems in flight under SPRT (fit_sprt_batch): one set of launches per round for every problem that is still
+    searching, the host replays each problem's round; every problem must end exactly where the one-problem run (= the oracle) ends,
+    whatever the others do (ragged sizes, some finish after one round, some run to max_iterations)."""
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    sizes = [1500, 700, 2200, 64, 1500] if cfg != 4 else [1500, 900, 2000]
+    ratios = [0.5, 0.3, 0.2, 0.6, 0.05]
+    sets = [gen.make(cfg, seed_offset=60 + i, n=n, inlier_ratio=ratios[i])[0] for i, n in enumerate(sizes)]
+    ctx.set_points(est, np.concatenate(sets), sizes)
+    for p, n in enumerate(sizes):
+        ctx.set_sprt_pool(p, O.sprt_pool(3, n))
+    max_it = 1200 if cfg != 4 else 400
+    res = ctx.fit(thr, conf, max_it, seed=3, round_size=K, sprt=True)
+    for p, pts in enumerate(sets):
+        ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=max_it, seed=3, sprt=True, batch=K)
+        assert_fit_equal_sprt(res[p], ref)
+
+
 @pytest.mark.parametrize("sprt", [False, True])
 def test_fit_prosac_termination_matches_oracle(ctx, sprt):
     """BASELINE config 3: fundamental, PROSAC sampler (+ SPRT) on quality-sorted correspondences."""
