@@ -683,7 +683,7 @@ def main():
     ap.add_argument("--latency", action="store_true", help="also measure the single-fit latency")
     ap.add_argument("--no-epipolar", action="store_true", help="skip the roofline_f / roofline_e legs (Sampson / essential scoring kernels)")
     ap.add_argument("--no-c5", action="store_true", help="skip the second leg (config.c5: the hypothesis-sharded 1M-point fit)")
-    ap.add_argument("--pipe", type=int, default=4, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
+    ap.add_argument("--pipe", type=int, default=2, help="contexts/streams the e2e arm splits a step over (upload of one part overlaps the fit of another)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: batch of independent N=4000 fits (default); c5: one 1M-point fit, hypotheses sharded")
     ap.add_argument("--c5-points", type=int, default=1000000)
     ap.add_argument("--c5-round", type=int, default=0, help="samples per round of the c5 leg (0 = 5000)")

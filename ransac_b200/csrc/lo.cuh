@@ -222,6 +222,21 @@ __device__ void cta_nonminimal(const float* __restrict__ pts, const int* ids, in
     __syncthreads();
 }
 
+// Estimator::EstimateModelNonMinimalSample as a kernel of its own (usac_gpu_estimate_nonminimal, the final refit): the CTA-wide
+// form above - one pass for the 45 sums of A'A instead of nonminimal_kernel's 45 (same sums, same order, same bits).
+template <int EST>
+__global__ void __launch_bounds__(LO_THREADS, 1) nonminimal_cta_kernel(const float* __restrict__ pts, const int* __restrict__ ids, int n,
+                                                                       float* __restrict__ model_out, int* __restrict__ ok_out) {
+    extern __shared__ __align__(16) unsigned char lo_smem[];
+    LoShared& sh = *reinterpret_cast<LoShared*>(lo_smem);
+    cta_nonminimal<EST>(pts, ids, n, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ok_out = sh.ok;
+        if (sh.ok) for (int i = 0; i < 9; i++) model_out[i] = sh.model[i];
+    }
+}
+
 // Quality::getNumberInliers(score, model, thr, get_inliers = true, ids) (quality.hpp:60-101): sh.cnt, sh.sum, ids in ascending order.
 // Same arithmetic as inliers_sum_kernel (score.cuh).
 template <int EST>

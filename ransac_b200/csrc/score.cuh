@@ -573,6 +573,67 @@ __global__ void __launch_bounds__(1024) inliers_kernel(const float* __restrict__
     if (threadIdx.x == 0) *count = base;
 }
 
+// The same list for large problems (1M points = 977 blocks of the loop above, one after the other: 1.5 ms) in three small launches:
+// flags + per-block counts over a grid, one CTA scanning the block counts, and the scatter from the stored flags. Every decision is
+// the same strict_error comparison, so the list is identical to the one-CTA kernel's.
+template <int EST>
+__global__ void __launch_bounds__(1024) inliers_flags_kernel(const float* __restrict__ aos, int n, const float* __restrict__ rec, float thr,
+                                                             unsigned* __restrict__ ballots, int* __restrict__ block_counts) {
+    __shared__ int warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    bool in = false;
+    if (i < n) {
+        float e;
+        if (EST == USAC_EST_LINE2D) { const float2 p = reinterpret_cast<const float2*>(aos)[i]; e = strict_error<EST>(rec, p.x, p.y, 0.f, 0.f); }
+        else { const float4 p = reinterpret_cast<const float4*>(aos)[i]; e = strict_error<EST>(rec, p.x, p.y, p.z, p.w); }
+        in = e < thr;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) { ballots[blockIdx.x * 32 + warp] = bal; warp_tot[warp] = __popc(bal); }
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) block_counts[blockIdx.x] = v;
+    }
+}
+// exclusive scan of the block counts in place (one CTA), total -> *count
+__global__ void __launch_bounds__(1024) inliers_scan_kernel(int* __restrict__ block_counts, int nblocks, int* __restrict__ count) {
+    __shared__ int sm[33];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nblocks ? block_counts[b] : 0;
+        int total;
+        const int off = block_exclusive_scan(v, &total, sm);
+        if (b < nblocks) block_counts[b] = base + off;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+__global__ void __launch_bounds__(1024) inliers_scatter_kernel(const unsigned* __restrict__ ballots, const int* __restrict__ block_offsets, int n,
+                                                               int* __restrict__ ids) {
+    __shared__ int warp_off[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {                                                  // exclusive scan of the 32 warp counts of this block
+        const int v = __popc(ballots[blockIdx.x * 32 + lane]);
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        warp_off[lane] = incl - v;
+    }
+    __syncthreads();
+    const unsigned bal = ballots[blockIdx.x * 32 + warp];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    if (i < n && ((bal >> lane) & 1u)) ids[block_offsets[blockIdx.x] + warp_off[warp] + __popc(bal & ((1u << lane) - 1))] = i;
+}
+
 // Quality::getNumberInliers(score, model, thr, get_inliers = true, ids) (quality.hpp:60-101) for local optimisation: ids in
 // ascending order, count, and the error sum as a lane sum (thread t adds the errors of its inliers t, t+1024, ... in order,
 // then a fixed binary tree over the 1024 lanes) - the order the parity tests' host restatement uses. stat = {count, sum bits}.
