@@ -44,6 +44,8 @@ def _worker(rank, world, port, out):
     assert D.reduce_max([10.0 + rank])[0] == 10.0 + world - 1
     uid = D.broadcast_bytes(bytes(range(128)) if rank == 0 else None)
     assert uid == bytes(range(128))
+    handles = D.allgather_bytes(bytes([rank + 1]) * 64)              # the exchange of the peer-window IPC handles (usac_gpu_peer_export)
+    assert handles == [bytes([r + 1]) * 64 for r in range(world)]
     # --- hypothesis sharding of one round: each rank scores samples j % R == rank ---------------------------------
     pts, _, _ = gen.homography(n=600, seed=21)
     K, n, m = 64, len(pts), 4
@@ -86,3 +88,12 @@ def test_shard_range_covers_everything():
             assert ranges[0][0] == 0 and ranges[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
             assert max(h - l for l, h in ranges) - min(h - l for l, h in ranges) <= 1
+
+
+def test_bind_to_gpu_numa_is_harmless_without_a_gpu():
+    import os
+
+    from ransac_b200 import dist as D
+    before = os.sched_getaffinity(0)
+    assert D.bind_to_gpu_numa(0) is None or isinstance(D.bind_to_gpu_numa(0), str)
+    assert os.sched_getaffinity(0) <= before

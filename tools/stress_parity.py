@@ -84,6 +84,38 @@ for case in range(CASES):
     except Exception as e:   # noqa: BLE001
         bad.append((tag, ["exception"], {"error": repr(e)}))
 
+# batches of ragged problems in flight: the plain path (device-side select) and the SPRT batch path (host replay per problem)
+for case in range(max(4, CASES // 15)):
+    cfg = int(g.choice([1, 2, 3, 4]))
+    est = EST[cfg]
+    B = int(g.integers(2, 9))
+    sizes = [int(g.integers(100, 3000)) for _ in range(B)]
+    sets = [gen.make(cfg, seed_offset=5000 + 31 * case + i, n=sizes[i], inlier_ratio=float(g.choice([0.05, 0.3, 0.6])))[0] for i in range(B)]
+    sizes = [len(x) for x in sets]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    seed, K, max_it = int(g.integers(1, 1000)), int(g.choice([16, 100, 256])), int(g.choice([300, 1000]))
+    sprt = bool(g.random() < 0.6)
+    ctx.set_points(est, np.concatenate(sets), sizes)
+    kw = dict(threshold=thr, confidence=conf, max_iterations=max_it, seed=seed, round_size=K)
+    okw = dict(threshold=thr, confidence=conf, max_iterations=max_it, seed=seed, rng=O.RNG_PHILOX)
+    if sprt:
+        for p_ in range(B):
+            ctx.set_sprt_pool(p_, O.sprt_pool(seed, sizes[p_]))
+        kw["sprt"] = True; okw.update(sprt=True, batch=min(K, max_it))
+    tag = f"batch {case}: cfg {cfg} sizes {sizes} sprt {sprt} K {K} max_it {max_it} seed {seed}"
+    try:
+        res = ctx.fit(**kw)
+        for p_ in range(B):
+            ref = O.ransac(sets[p_], est, **okw)
+            keys = ["inliers", "iterations", "best_hyp", "best_model_idx"] + (["samples_drawn", "evals"] if sprt else [])
+            diff = [k for k in keys if res[p_][k] != ref[k]]
+            if not np.array_equal(bits(res[p_]["model"]), bits(ref["model"])):
+                diff.append("model")
+            if diff:
+                bad.append((tag + f" problem {p_}", diff, {k: (res[p_][k], ref[k]) for k in diff if k != "model"}))
+    except Exception as e:   # noqa: BLE001
+        bad.append((tag, ["exception"], {"error": repr(e)}))
+
 # the ordered inlier list across the multi-launch switch (32768 points) and at sizes that are not multiples of 1024
 for n in (32767, 32768, 40001, 131073):
     pts, H, mask = gen.homography(n=n, inlier_ratio=0.3, seed=n)
@@ -97,7 +129,7 @@ for n in (32767, 32768, 40001, 131073):
     if rf["inliers"] != orf["inliers"] or not np.array_equal(bits(rf["model"]), bits(np.asarray(orf["model"], np.float32))):
         bad.append((f"refit n={n}", ["refit"], {"inliers": (rf["inliers"], orf["inliers"])}))
 ctx.close()
-print(f"stress_parity: {CASES} fits + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches")
+print(f"stress_parity: {CASES} fits + {max(4, CASES // 15)} ragged batches + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches")
 for b in bad:
     print("MISMATCH", b)
 sys.exit(1 if bad else 0)
