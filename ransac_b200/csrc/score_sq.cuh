@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SQ_MIN_CTAS) score_sq
                 else { A = tp[2 * j]; B = tp[2 * j + 1]; }
             };
             int j = 0;
+            const float zb = fm.reject_bound();                                     // proven outlier <=> reject(...) > zb
 #pragma unroll 1
             for (; j + USAC_PPI <= np; j += USAC_PPI) {
                 float2 z[USAC_PPI];
@@ -214,13 +215,13 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SQ_MIN_CTAS) score_sq
                 }
                 bool lane_any = false;
 #pragma unroll
-                for (int q = 0; q < USAC_PPI; q++) lane_any = lane_any || !(z[q].x > 0.f) || !(z[q].y > 0.f);
+                for (int q = 0; q < USAC_PPI; q++) lane_any = lane_any || !(z[q].x > zb) || !(z[q].y > zb);
                 // one vote for the whole trip: in most trips every point is a proven outlier for every model of the warp
-                if (!USAC_SQ_TRIPVOTE || (EST != USAC_EST_HOMOGRAPHY && USAC_SQ_TRIPVOTE == 2) || __any_sync(0xffffffffu, lane_any && live)) {
+                if (!USAC_SQ_TRIPVOTE || ((EST != USAC_EST_HOMOGRAPHY || USAC_SQ_H_XONLY) && USAC_SQ_TRIPVOTE == 2) || __any_sync(0xffffffffu, lane_any && live)) {
 #pragma unroll
                     for (int q = 0; q < USAC_PPI; q++) {                           // everything that is not a proven outlier goes to the queue
-                        sq_push(!(z[q].x > 0.f) && live, qaddr, ebase + 2 * q);
-                        sq_push(!(z[q].y > 0.f) && live, qaddr, ebase + 2 * q + 1);
+                        sq_push(!(z[q].x > zb) && live, qaddr, ebase + 2 * q);
+                        sq_push(!(z[q].y > zb) && live, qaddr, ebase + 2 * q + 1);
                     }
                     if (__any_sync(0xffffffffu, qaddr > q_limit)) drain();           // rare: some lane's queue is nearly full
                 }
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(USAC_SCORE_THREADS, USAC_SQ_MIN_CTAS) score_sq
                         float4 A, B;
                         load_pair(j + q, A, B);
                         const float2 z = fm.reject(A, B);
-                        sq_push(!(z.x > 0.f) && live, qaddr, ebase + 2 * q);
-                        sq_push(!(z.y > 0.f) && live, qaddr, ebase + 2 * q + 1);
+                        sq_push(!(z.x > zb) && live, qaddr, ebase + 2 * q);
+                        sq_push(!(z.y > zb) && live, qaddr, ebase + 2 * q + 1);
                     }
                 }
                 if (__any_sync(0xffffffffu, qaddr > q_limit)) drain();
