@@ -551,10 +551,10 @@ def c5_leg(args, rank, world, local, steps, warmup):
             except Exception as e:   # noqa: BLE001
                 print(f"bench.py: peer windows unavailable on rank {rank}: {e}", file=sys.stderr)
                 ok = 0.0
-            all_ok, any_ok = -D.reduce_max([-ok])[0] >= 1.0, D.reduce_max([ok])[0] >= 1.0
-            if any_ok and not all_ok:
-                raise SystemExit("bench.py: peer windows attached on some ranks only")
-            if all_ok:
+            all_ok = -D.reduce_max([-ok])[0] >= 1.0
+            if not all_ok:
+                ctx.peer_detach()                                     # every rank goes back to the NCCL hook
+            else:
                 exchange = "peer windows over NVLink (stores from the reduce kernel + flags, no collective call)"
     bracket(step, warmup)
     clocks = ClockSampler(local)

@@ -189,6 +189,8 @@ int usac_gpu_peer_export(usac_gpu_ctx* ctx, char handle_out[USAC_PEER_HANDLE_BYT
 int usac_gpu_peer_attach(usac_gpu_ctx* ctx, const char* handles /* nranks x USAC_PEER_HANDLE_BYTES */, int rank, int nranks);
 int usac_gpu_peer_window(usac_gpu_ctx* ctx, void** window_out);
 int usac_gpu_peer_attach_ptrs(usac_gpu_ctx* ctx, void* const* windows /* [nranks], windows[rank] = own */, int rank, int nranks);
+/* back to the all-gather hook (every rank must do the same before the next fit, e.g. when the attach failed on one of them) */
+int usac_gpu_peer_detach(usac_gpu_ctx* ctx);
 
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 /* device time (ms, CUDA events on ctx's stream) and launch count of the kernels of the last usac_gpu_fit/score call */

@@ -214,6 +214,9 @@ class GpuContext:
         assert len(blob) == nranks * self.PEER_HANDLE_BYTES
         self._check(self.L.usac_gpu_peer_attach(self.h, bytes(blob), rank, nranks), "peer_attach")
 
+    def peer_detach(self):
+        self._check(self.L.usac_gpu_peer_detach(self.h), "peer_detach")
+
     def peer_window(self):
         p = C.c_void_p()
         self._check(self.L.usac_gpu_peer_window(self.h, C.byref(p)), "peer_window")

@@ -100,6 +100,7 @@ def load():
     L.usac_gpu_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.usac_gpu_peer_export.argtypes = [vp, C.c_char_p]
     L.usac_gpu_peer_attach.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.usac_gpu_peer_detach.argtypes = [vp]
     L.usac_gpu_peer_window.argtypes = [vp, C.POINTER(C.c_void_p)]
     L.usac_gpu_peer_attach_ptrs.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int]
     L.usac_gpu_last_timing.argtypes = [vp, fp, fp, ip, ip]

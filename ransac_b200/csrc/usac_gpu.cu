@@ -2125,6 +2125,16 @@ extern "C" int usac_gpu_peer_attach(usac_gpu_ctx* c, const char* handles, int ra
     return peer_finish_attach(c, wins, rank, nranks);
 }
 
+extern "C" int usac_gpu_peer_detach(usac_gpu_ctx* c) {
+    if (!c) return USAC_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* w : c->peer_opened) cudaIpcCloseMemHandle(w);
+    c->peer_opened.clear();
+    c->peer_rank = -1; c->peer_nranks = 0;                           // the window itself stays (it may be exported again)
+    return USAC_OK;
+}
+
 extern "C" int usac_gpu_peer_attach_ptrs(usac_gpu_ctx* c, void* const* windows, int rank, int nranks) {
     if (!c || !windows || rank < 0 || rank >= nranks || nranks > USAC_PEER_MAX_RANKS) return fail(c, USAC_ERR_ARG, "peer_attach_ptrs: bad arguments");
     if (c->peer_nranks) return fail(c, USAC_ERR_STATE, "peer_attach_ptrs: windows are already attached");

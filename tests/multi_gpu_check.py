@@ -40,6 +40,7 @@ def main():
     D.barrier()
     # (2) peer windows: attached windows take precedence over the hook; two fits (the sequence numbers keep counting)
     ctx.peer_attach(D.allgather_bytes(ctx.peer_export()), rank, world)
+    D.barrier()                                                       # nobody waits for a rank that is still mapping windows
     for rep in range(2):
         check(ctx.fit(2.0, 0.95, 4000, seed=3, round_size=512, rank=rank, nranks=world)[0], f"peer {rep}")
     D.barrier()
