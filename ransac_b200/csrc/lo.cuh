@@ -310,6 +310,63 @@ __device__ void lo_subset(unsigned long long seed, unsigned long long calls, int
 
 __device__ __forceinline__ bool lo_bigger(int ia, float sa, int ib, float sb) { return ia > ib || (ia == ib && sa > sb); }
 
+// One inner iteration of InnerLocalOptimization::GetModelScore (inner_local_optimization.hpp:85-131 with the iterative stage,
+// iterative_local_optimization.hpp:61-135) from the state (best score, pool A of `avail` inliers, running threshold, call counter).
+// Returns 1 when the inner loop ends here (`break`), else 0; `improved` = the candidate (sh.model, B[0 .. lo_inl)) beats the best.
+template <int EST>
+__device__ int lo_inner_iteration(const LoArgs& a, const ProblemDesc& pd, LoShared& sh, const int* A, int* B, int best_inl, float best_sum, int avail,
+                                  float& lo_thr, unsigned long long& calls, unsigned& inner_done, unsigned& iterative_done,
+                                  bool& improved, int& lo_inl, float& lo_sum) {
+    const int t = threadIdx.x;
+    improved = false; lo_inl = 0; lo_sum = 0.f;
+    if (avail > a.sample_limit) {
+        if (t == 0) lo_subset(a.seed, calls, a.sample_limit, avail, A, sh.sample);
+        calls++;
+        __syncthreads();
+        cta_nonminimal<EST>(a.aos, sh.sample, a.sample_limit, sh);
+        if (!sh.ok) return 0;                                          // continue
+    } else {
+        cta_nonminimal<EST>(a.aos, A, avail, sh);
+        if (!sh.ok) return 1;                                          // break
+    }
+    lo_thr = (unsigned)a.mult * lo_thr;                                 // inner_local_optimization.hpp:101
+    cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, B, sh);
+    lo_inl = sh.cnt;
+    lo_sum = sh.sum;
+    if (lo_inl <= a.m) return 0;                                       // continue
+    // ---- IterativeLocalOptimization::GetModelScore ----
+    for (int k = 0; k < a.iter_iters; k++) {
+        lo_thr -= a.step;
+        if (lo_inl <= a.m) break;
+        if (a.kind == 2) {                                             // GetScoreLimited
+            if (lo_inl > a.sample_limit) {
+                if (t == 0) lo_subset(a.seed, calls, a.sample_limit, lo_inl, B, sh.sample);
+                calls++;
+                __syncthreads();
+                cta_nonminimal<EST>(a.aos, sh.sample, a.sample_limit, sh);
+                if (!sh.ok) continue;
+            } else {
+                cta_nonminimal<EST>(a.aos, B, lo_inl, sh);
+                if (!sh.ok) break;
+            }
+            cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, B, sh);
+            lo_inl = sh.cnt; lo_sum = sh.sum;
+        } else {                                                       // GetScoreUnlimited
+            cta_nonminimal<EST>(a.aos, B, lo_inl, sh);
+            if (!sh.ok) break;
+            cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, B, sh);
+            lo_inl = sh.cnt; lo_sum = sh.sum;
+            if (lo_bigger(best_inl, best_sum, lo_inl, lo_sum)) break;
+        }
+        iterative_done++;
+    }
+    bool fail = false;
+    if (fabsf(lo_thr - a.theta) > 0.00001) { fail = true; lo_thr = a.theta; }
+    improved = !fail && lo_bigger(lo_inl, lo_sum, best_inl, best_sum);
+    inner_done++;
+    return 0;
+}
+
 template <int EST>
 __global__ void __launch_bounds__(LO_THREADS, 1) lo_kernel(const LoArgs a) {
     extern __shared__ __align__(16) unsigned char lo_smem[];
@@ -328,50 +385,11 @@ __global__ void __launch_bounds__(LO_THREADS, 1) lo_kernel(const LoArgs a) {
         cta_score<EST>(a.aos, a.n, sh.best_model, a.theta, pd, a.A, sh);   // quality->getInliers(best_model)
         int avail = min(best_inl, sh.cnt);                             // ids present in A (never index past the list)
         for (int it = 0; it < a.inner_iters; it++) {
-            if (avail > a.sample_limit) {
-                if (t == 0) lo_subset(a.seed, calls, a.sample_limit, avail, a.A, sh.sample);
-                calls++;
-                __syncthreads();
-                cta_nonminimal<EST>(a.aos, sh.sample, a.sample_limit, sh);
-                if (!sh.ok) continue;
-            } else {
-                cta_nonminimal<EST>(a.aos, a.A, avail, sh);
-                if (!sh.ok) break;
-            }
-            lo_thr = (unsigned)a.mult * lo_thr;                         // inner_local_optimization.hpp:101
-            cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, a.B, sh);
-            int lo_inl = sh.cnt;
-            float lo_sum = sh.sum;
-            if (lo_inl <= a.m) continue;
-            // ---- IterativeLocalOptimization::GetModelScore ----
-            for (int k = 0; k < a.iter_iters; k++) {
-                lo_thr -= a.step;
-                if (lo_inl <= a.m) break;
-                if (a.kind == 2) {                                     // GetScoreLimited
-                    if (lo_inl > a.sample_limit) {
-                        if (t == 0) lo_subset(a.seed, calls, a.sample_limit, lo_inl, a.B, sh.sample);
-                        calls++;
-                        __syncthreads();
-                        cta_nonminimal<EST>(a.aos, sh.sample, a.sample_limit, sh);
-                        if (!sh.ok) continue;
-                    } else {
-                        cta_nonminimal<EST>(a.aos, a.B, lo_inl, sh);
-                        if (!sh.ok) break;
-                    }
-                    cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, a.B, sh);
-                    lo_inl = sh.cnt; lo_sum = sh.sum;
-                } else {                                               // GetScoreUnlimited
-                    cta_nonminimal<EST>(a.aos, a.B, lo_inl, sh);
-                    if (!sh.ok) break;
-                    cta_score<EST>(a.aos, a.n, sh.model, lo_thr, pd, a.B, sh);
-                    lo_inl = sh.cnt; lo_sum = sh.sum;
-                    if (lo_bigger(best_inl, best_sum, lo_inl, lo_sum)) break;
-                }
-                iterative_done++;
-            }
-            bool fail = false;
-            if (fabsf(lo_thr - a.theta) > 0.00001) { fail = true; lo_thr = a.theta; }
-            if (!fail && lo_bigger(lo_inl, lo_sum, best_inl, best_sum)) {
+            bool improved;
+            int lo_inl;
+            float lo_sum;
+            if (lo_inner_iteration<EST>(a, pd, sh, a.A, a.B, best_inl, best_sum, avail, lo_thr, calls, inner_done, iterative_done, improved, lo_inl, lo_sum)) break;
+            if (improved) {
                 __syncthreads();
                 if (t < 9) sh.best_model[t] = sh.model[t];
                 for (int i = t; i < lo_inl; i += LO_THREADS) a.A[i] = a.B[i];
@@ -379,7 +397,6 @@ __global__ void __launch_bounds__(LO_THREADS, 1) lo_kernel(const LoArgs a) {
                 __threadfence_block();
                 __syncthreads();
             }
-            inner_done++;
         }
     }
     __syncthreads();
@@ -387,5 +404,173 @@ __global__ void __launch_bounds__(LO_THREADS, 1) lo_kernel(const LoArgs a) {
         for (int i = 0; i < 9; i++) a.io->model[i] = sh.best_model[i];
         a.io->inliers = best_inl; a.io->score = best_sum; a.io->lo_thr = lo_thr; a.io->calls = calls;
         a.io->inner_done = inner_done; a.io->iterative_done = iterative_done;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// The same LO call with its inner iterations executed SPECULATIVELY side by side. An inner iteration changes the state the next one
+// starts from only when it improves the best model (rare: a few of the 20) - otherwise the next iteration's inputs are known in
+// advance: the same pool A, the running threshold back at theta, the call counter advanced by the iteration's subset draws. So a
+// WAVE runs all remaining iterations at once, one CTA each, on those predicted inputs; a commit kernel then walks them in order,
+// accepts every iteration whose assumed inputs equal the actual state, stops at the first improvement (which it applies: model,
+// pool, counters) or misprediction, and the next wave starts behind it. Every accepted iteration ran the sequential code on the
+// sequential inputs, so the result is that of lo_kernel bit for bit; an LO call costs (improvements + 1) waves of ~5 dependent
+// fit-and-score steps instead of 20 x 5.
+// ------------------------------------------------------------------------------------------------------------------------------
+struct LoWaveState {
+    float best_model[9];
+    int best_inl;
+    float best_sum;
+    int avail;
+    float lo_thr;
+    unsigned long long calls;
+    unsigned inner_done, iterative_done;
+    int next_it, finished;
+};
+struct LoSpec {                   // one speculatively executed inner iteration
+    unsigned long long calls_in, calls_out;
+    float lo_thr_in, lo_thr_out;
+    int status, improved, lo_inl;
+    float lo_sum;
+    float model[9];
+    unsigned d_inner, d_iter;
+};
+#define LO_WAVE_VARIANTS 6       // predicted running thresholds tried per iteration (grid.y of the wave)
+struct LoWaveArgs {
+    LoArgs a;
+    LoWaveState* ws;
+    LoSpec* spec;                 // [inner_iters][LO_WAVE_VARIANTS]
+    int* Bwave;                   // [inner_iters][LO_WAVE_VARIANTS][n] candidate inlier lists
+};
+
+// best model -> pool A, avail (quality->getInliers(best_model)); state from the io record
+template <int EST>
+__global__ void __launch_bounds__(LO_THREADS, 1) lo_pool_kernel(const LoWaveArgs w) {
+    extern __shared__ __align__(16) unsigned char lo_smem[];
+    LoShared& sh = *reinterpret_cast<LoShared*>(lo_smem);
+    const LoArgs& a = w.a;
+    const int t = threadIdx.x;
+    const ProblemDesc pd = a.prob[a.problem];
+    if (t < 9) sh.best_model[t] = a.io->model[t];
+    __syncthreads();
+    cta_score<EST>(a.aos, a.n, sh.best_model, a.theta, pd, a.A, sh);
+    if (t == 0) {
+        LoWaveState& s = *w.ws;
+        for (int i = 0; i < 9; i++) s.best_model[i] = a.io->model[i];
+        s.best_inl = a.io->inliers; s.best_sum = a.io->score; s.avail = min(a.io->inliers, sh.cnt);
+        s.lo_thr = a.io->lo_thr; s.calls = a.io->calls; s.inner_done = 0; s.iterative_done = 0; s.next_it = 0; s.finished = 0;
+    }
+}
+
+// subset draws an iteration is expected to make (the prediction of the next iteration's call counter)
+__device__ __forceinline__ int lo_expected_draws(const LoArgs& a, int avail) {
+    return (avail > a.sample_limit ? 1 : 0) + (a.kind == 2 ? a.iter_iters : 0);
+}
+// the running threshold after an iteration that goes through all its steps (the statements of lo_inner_iteration, one rounding each)
+__device__ __forceinline__ float lo_thr_after_full_iteration(const LoArgs& a, float x) {
+    x = __fmul_rn((float)(unsigned)a.mult, x);
+    for (int k = 0; k < a.iter_iters; k++) x = __fsub_rn(x, a.step);
+    if (fabsf(__fsub_rn(x, a.theta)) > 0.00001) x = a.theta;
+    return x;
+}
+// Predicted running threshold of iteration next_it + b, variant v. An iteration leaves either the value of the full path or theta
+// (reset after an early exit of the iterative stage), so the candidates are: v = 0 the full-path chain from the actual value,
+// v = j + 1 the full-path chain restarted from theta j iterations ago. Returns false for a variant that repeats an earlier one.
+__device__ __forceinline__ bool lo_predicted_threshold(const LoArgs& a, float actual, int b, int v, float& out) {
+    float cand[LO_WAVE_VARIANTS];
+    int nc = 0;
+    {
+        float x = actual;
+        for (int i = 0; i < b; i++) x = lo_thr_after_full_iteration(a, x);
+        cand[nc++] = x;
+    }
+    if (b > 0) {
+        float x = a.theta;
+        for (int j = 0; j < LO_WAVE_VARIANTS - 1 && j < b; j++) {       // restarted from theta j iterations ago
+            if (j > 0) x = lo_thr_after_full_iteration(a, x);
+            cand[nc++] = x;
+        }
+    }
+    if (v >= nc) return false;
+    for (int i = 0; i < v; i++) if (__float_as_uint(cand[i]) == __float_as_uint(cand[v])) return false;
+    out = cand[v];
+    return true;
+}
+
+template <int EST>
+__global__ void __launch_bounds__(LO_THREADS, 1) lo_wave_kernel(const LoWaveArgs w) {
+    extern __shared__ __align__(16) unsigned char lo_smem[];
+    LoShared& sh = *reinterpret_cast<LoShared*>(lo_smem);
+    const LoArgs& a = w.a;
+    const ProblemDesc pd = a.prob[a.problem];
+    const LoWaveState s = *w.ws;                                     // written by the previous kernel in the stream
+    const int b = blockIdx.x, v = blockIdx.y;                        // iteration s.next_it + b, threshold variant v
+    LoSpec& o = w.spec[b * LO_WAVE_VARIANTS + v];
+    float lo_thr;
+    const bool run = !s.finished && s.next_it + b < a.inner_iters && lo_predicted_threshold(a, s.lo_thr, b, v, lo_thr);
+    if (!run) {                                                      // uniform over the CTA
+        if (threadIdx.x == 0) o.status = -1;                         // nothing ran here
+        return;
+    }
+    unsigned long long calls = s.calls + (unsigned long long)b * (unsigned long long)lo_expected_draws(a, s.avail);
+    const unsigned long long calls_in = calls;
+    const float lo_thr_in = lo_thr;
+    unsigned d_inner = 0, d_iter = 0;
+    bool improved;
+    int lo_inl;
+    float lo_sum;
+    int* B = w.Bwave + ((size_t)b * LO_WAVE_VARIANTS + v) * a.n;
+    const int status = lo_inner_iteration<EST>(a, pd, sh, a.A, B, s.best_inl, s.best_sum, s.avail, lo_thr, calls, d_inner, d_iter, improved, lo_inl, lo_sum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        o.calls_in = calls_in; o.calls_out = calls; o.lo_thr_in = lo_thr_in; o.lo_thr_out = lo_thr;
+        o.status = status; o.improved = improved ? 1 : 0; o.lo_inl = lo_inl; o.lo_sum = lo_sum;
+        for (int i = 0; i < 9; i++) o.model[i] = sh.model[i];
+        o.d_inner = d_inner; o.d_iter = d_iter;
+    }
+}
+
+// walk the wave in iteration order (one CTA): accept, apply the first improvement, stop at a misprediction
+__global__ void __launch_bounds__(LO_THREADS) lo_commit_kernel(const LoWaveArgs w) {
+    __shared__ int s_copy_from, s_copy_n;
+    const LoArgs& a = w.a;
+    LoWaveState& s = *w.ws;
+    if (threadIdx.x == 0) {
+        s_copy_from = -1; s_copy_n = 0;
+        if (!s.finished) {
+            int it = s.next_it;
+            const int it0 = it;
+            for (; it < a.inner_iters; it++) {
+                int hit = -1;                                          // the variant that ran on the actual inputs
+                for (int v = 0; v < LO_WAVE_VARIANTS && hit < 0; v++) {
+                    const LoSpec& c = w.spec[(it - it0) * LO_WAVE_VARIANTS + v];
+                    if (c.status >= 0 && c.calls_in == s.calls && __float_as_uint(c.lo_thr_in) == __float_as_uint(s.lo_thr)) hit = v;
+                }
+                if (hit < 0) break;                                    // ran on other inputs: the next wave starts here
+                const LoSpec& o = w.spec[(it - it0) * LO_WAVE_VARIANTS + hit];
+                s.calls = o.calls_out; s.lo_thr = o.lo_thr_out; s.inner_done += o.d_inner; s.iterative_done += o.d_iter;
+                if (o.status) { s.finished = 1; it++; break; }         // the inner loop's `break`
+                if (o.improved) {
+                    for (int i = 0; i < 9; i++) s.best_model[i] = o.model[i];
+                    s.best_inl = o.lo_inl; s.best_sum = o.lo_sum; s.avail = o.lo_inl;
+                    s_copy_from = (it - it0) * LO_WAVE_VARIANTS + hit; s_copy_n = o.lo_inl;
+                    it++;
+                    break;                                             // the later iterations of the wave saw the old state
+                }
+            }
+            s.next_it = it;
+            if (it >= a.inner_iters) s.finished = 1;
+        }
+    }
+    __syncthreads();
+    if (s_copy_from >= 0) {
+        const int* B = w.Bwave + (size_t)s_copy_from * a.n;
+        for (int i = threadIdx.x; i < s_copy_n; i += blockDim.x) a.A[i] = B[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s.finished) {
+        for (int i = 0; i < 9; i++) a.io->model[i] = s.best_model[i];
+        a.io->inliers = s.best_inl; a.io->score = s.best_sum; a.io->lo_thr = s.lo_thr; a.io->calls = s.calls;
+        a.io->inner_done = s.inner_done; a.io->iterative_done = s.iterative_done;
     }
 }
