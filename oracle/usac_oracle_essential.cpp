@@ -102,18 +102,35 @@ static double horner_rev(const double* c, int deg, double w) {   /* c[0] w^deg +
     return v;
 }
 
-/* root of p (degree deg) in [l, r] with p(l), p(r) of opposite sign (or zero): bisection to the last bit, <= 200 steps */
-static double bisect(const double* c, int deg, double l, double r, double pl) {
+/* root of p (degree deg, derivative dc of degree deg-1) in [l, r] with p(l), p(r) of opposite sign (or zero): Newton steps kept inside
+ * the bracket, a bisection step whenever Newton leaves it or stops halving it (the classical safeguarded iteration), until the step is
+ * below two ulps of the root; <= 200 steps. ~7 evaluations of p and p' instead of ~55 evaluations of p for plain bisection. */
+static double bisect(const double* c, const double* dc, int deg, double l, double r, double pl) {
     if (pl == 0.0) return l;
-    const bool neg_left = pl < 0.0;
+    double xl = pl < 0.0 ? l : r, xh = pl < 0.0 ? r : l;          /* p(xl) < 0 < p(xh) */
+    double x = 0.5 * (l + r), dxold = std::fabs(r - l), dx = dxold;
+    double f = horner(c, deg, x), df = horner(dc, deg - 1, x);
     for (int it = 0; it < 200; it++) {
-        double m = 0.5 * (l + r);
-        if (m == l || m == r) break;
-        double pm = horner(c, deg, m);
-        if (pm == 0.0) return m;
-        if ((pm < 0.0) == neg_left) l = m; else r = m;
+        if (f == 0.0) return x;
+        const double a = (x - xh) * df - f, b = (x - xl) * df - f;
+        const bool newton = (a * b <= 0.0) && (std::fabs(2.0 * f) <= std::fabs(dxold * df));   /* false for NaN: bisect */
+        dxold = dx;
+        if (!newton) {
+            dx = 0.5 * (xh - xl);
+            x = xl + dx;
+            if (xl == x) return x;
+        } else {
+            dx = f / df;
+            const double t = x;
+            x = x - dx;
+            if (t == x) return x;
+        }
+        if (std::fabs(dx) <= 4.4e-16 * std::fabs(x)) return x;
+        f = horner(c, deg, x);
+        df = horner(dc, deg - 1, x);
+        if (f < 0.0) xl = x; else xh = x;
     }
-    return 0.5 * (l + r);
+    return x;
 }
 
 /* real roots of c[0..deg] (ascending powers, c[deg] != 0) in ascending order: the roots of p' bracket the roots of p */
@@ -140,7 +157,7 @@ static int real_roots(const double* c, int deg, double* roots) {
             double right = s < nprev ? prev[s] : bound;
             double pr = horner(p, d, right);
             if (pl == 0.0) { cur[ncur++] = left; }
-            else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { cur[ncur++] = bisect(p, d, left, right, pl); }
+            else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { cur[ncur++] = bisect(p, der[d - 1], d, left, right, pl); }
             left = right; pl = pr;
         }
         if (pl == 0.0) cur[ncur++] = left;

@@ -72,17 +72,33 @@ __device__ __noinline__ double horner_rev(const double* c, int deg, double w) {
     return v;
 }
 
-__device__ __noinline__ double bisect(const double* c, int deg, double l, double r, double pl) {
+// safeguarded Newton (see the host restatement): Newton steps inside the bracket, bisection when Newton leaves it or stops halving it
+__device__ __noinline__ double bisect(const double* c, const double* dc, int deg, double l, double r, double pl) {
     if (pl == 0.0) return l;
-    const bool neg_left = pl < 0.0;
+    double xl = pl < 0.0 ? l : r, xh = pl < 0.0 ? r : l;
+    double x = mul(0.5, add(l, r)), dxold = fabs(sub(r, l)), dx = dxold;
+    double f = horner(c, deg, x), df = horner(dc, deg - 1, x);
     for (int it = 0; it < 200; it++) {
-        const double m = mul(0.5, add(l, r));
-        if (m == l || m == r) break;
-        const double pm = horner(c, deg, m);
-        if (pm == 0.0) return m;
-        if ((pm < 0.0) == neg_left) l = m; else r = m;
+        if (f == 0.0) return x;
+        const double a = sub(mul(sub(x, xh), df), f), b = sub(mul(sub(x, xl), df), f);
+        const bool newton = (mul(a, b) <= 0.0) && (fabs(mul(2.0, f)) <= fabs(mul(dxold, df)));
+        dxold = dx;
+        if (!newton) {
+            dx = mul(0.5, sub(xh, xl));
+            x = add(xl, dx);
+            if (xl == x) return x;
+        } else {
+            dx = dvd(f, df);
+            const double t = x;
+            x = sub(x, dx);
+            if (t == x) return x;
+        }
+        if (fabs(dx) <= mul(4.4e-16, fabs(x))) return x;
+        f = horner(c, deg, x);
+        df = horner(dc, deg - 1, x);
+        if (f < 0.0) xl = x; else xh = x;
     }
-    return mul(0.5, add(l, r));
+    return x;
 }
 
 __device__ int real_roots(const double* c, int deg, double* roots) {
@@ -107,7 +123,7 @@ __device__ int real_roots(const double* c, int deg, double* roots) {
             const double right = s < nprev ? prev[s] : bound;
             const double pr = horner(p, d, right);
             if (pl == 0.0) { cur[ncur++] = left; }
-            else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { cur[ncur++] = bisect(p, d, left, right, pl); }
+            else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { cur[ncur++] = bisect(p, der[d - 1], d, left, right, pl); }
             left = right; pl = pr;
         }
         if (pl == 0.0) cur[ncur++] = left;
@@ -520,7 +536,7 @@ __device__ int solve_essential5_warp(const float* __restrict__ pts, const int* s
                 const double left = k == 0 ? -bound : P[k - 1], right = k < np ? P[k] : bound;
                 const double pl = horner(p, d, left), pr = horner(p, d, right);
                 if (pl == 0.0) { has = true; val = left; }
-                else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { has = true; val = bisect(p, d, left, right, pl); }
+                else if (pr != 0.0 && ((pl < 0.0) != (pr < 0.0))) { has = true; val = bisect(p, p - 11, d, left, right, pl); }
             } else if (horner(p, d, bound) == 0.0) { has = true; val = bound; }   // the closing `if (pl == 0.0)` of real_roots
         }
         const unsigned bal = __ballot_sync(0xffffffffu, has);
