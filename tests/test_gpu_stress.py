@@ -15,3 +15,13 @@ def test_randomised_parity_sweep():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_parity.py"), "150", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=900)
     assert r.returncode == 0 and ", 0 mismatches" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.gpu
+def test_randomised_parity_sweep_fallback_paths():
+    """The same sweep through the fallback paths: LO as one CTA (taken when the candidate lists of the speculative waves would not fit)
+    and SPRT batches one problem at a time."""
+    env = dict(os.environ, USAC_GPU_LO_SEQ="1", USAC_GPU_SPRT_BATCH="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_parity.py"), "60", "11"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=900, env=env)
+    assert r.returncode == 0 and ", 0 mismatches" in r.stdout, r.stdout[-4000:]
