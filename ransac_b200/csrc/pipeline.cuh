@@ -50,6 +50,8 @@ struct RoundArgs {
     unsigned peer_cap;           // uint2 entries per parity buffer
     unsigned* peer_counter;      // CTAs of the reduce kernel that have stored their part
     int* peer_error;             // set when a wait timed out
+    unsigned long long hyp_base_p1;   // 0: the hypothesis id of sample j is FitState::samples_drawn + j; else (hyp_base_p1 - 1) + j (solve-ahead
+                                      // blocks launched before the state has advanced that far)
 };
 
 // Exchange window of one rank: flags[2][64] (sequence number last published by rank r, per parity), then two buffers of
@@ -194,7 +196,7 @@ __global__ void napsac_seed_kernel(const RoundArgs a) {
     if (j >= a.K) return;
     const int pid = a.active[slot];
     const ProblemDesc pd = a.prob[pid];
-    const uint64_t hyp = (uint64_t)a.state[pid].samples_drawn + j;
+    const uint64_t hyp = (a.hyp_base_p1 ? (uint64_t)(a.hyp_base_p1 - 1) : (uint64_t)a.state[pid].samples_drawn) + j;
     int p = 0;
     if (a.neighbors == USAC_NEIGH_KNN) {
         philox_unique(a.seed, hyp, 4, pd.n, 1, &p);
@@ -236,7 +238,7 @@ __global__ void sample_kernel(const RoundArgs a) {
     const int pid = a.active[slot];
     const ProblemDesc pd = a.prob[pid];
     FitState& st = a.state[pid];
-    const uint64_t hyp = (uint64_t)st.samples_drawn + j;
+    const uint64_t hyp = (a.hyp_base_p1 ? (uint64_t)(a.hyp_base_p1 - 1) : (uint64_t)st.samples_drawn) + j;
     int s[8];
     const int m = a.m, n = pd.n;
     if (a.rng == USAC_RNG_TABLE && pid == 0 && hyp < a.table_rows) {

@@ -100,6 +100,8 @@ struct usac_gpu_ctx {
     DevBuf<SprtModelResult> d_sprt_res;
     DevBuf<SprtCarry> d_sprt_carry;          // walks handed from sprt_walk_kernel to sprt_tail_kernel
     DevBuf<unsigned> d_sprt_count;
+    cudaStream_t stream2 = nullptr;           // solve-ahead blocks of the SPRT replay path run here, beside the rounds of the previous block
+    cudaEvent_t ev_block[2] = {nullptr, nullptr};
     DevBuf<int> d_lo_bwave;                   // speculative LO waves (lo.cuh): candidate inlier lists, per-iteration records, state
     DevBuf<LoSpec> d_lo_spec;
     DevBuf<LoWaveState> d_lo_ws;
@@ -222,6 +224,8 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int i = 0; i < 2; i++) if (c->ev_block[i]) cudaEventDestroy(c->ev_block[i]);
     for (void* w : c->peer_opened) cudaIpcCloseMemHandle(w);
     if (c->peer_self) cudaFree(c->peer_self);
     if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
@@ -1608,8 +1612,15 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         while (G > 1 && (size_t)K * G > 8192) G--;
     }
     const int KB = K * G;                                         // samples per solved block
-    int rc = ensure_round_buffers(c, 1, KB, 1, 1);
+    // ... and the NEXT block is solved on a second stream while this block's rounds run (walks, copies, the host replay): two sets of
+    // sample / model / record buffers, used alternately
+    const bool overlap = G > 1 && !(getenv("USAC_GPU_SOLVE_OVERLAP") && atoi(getenv("USAC_GPU_SOLVE_OVERLAP")) == 0);
+    int rc = ensure_round_buffers(c, 1, overlap ? 2 * KB : KB, 1, 1);
     if (rc) return rc;
+    if (overlap && !c->stream2) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_block[i], cudaEventDisableTiming));
+    }
     CUDA_TRY(c, c->d_model_scores.ensure(KS));
     CUDA_TRY(c, c->h_rp_nmodels.ensure(K));
     CUDA_TRY(c, c->h_rp_res.ensure(KS));
@@ -1645,6 +1656,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
         if (cfg->lo) { rc = lo.init(c, p, cfg); if (rc) return rc; }
         bool done = false;
         int block_round = 0;                                       // rounds since the first solved block of this problem
+        int prelaunched = -1;                                      // index of the block that has been solved ahead on stream2
         t_tables += us(t_p0, now());
         while (!done && hs.iters < hs.max_iters) {
             const auto t_r0 = now();
@@ -1664,12 +1676,18 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
             RK("start");
             // ---- sample + solve + records: once per block of G rounds ----
             const int g = block_round % G;                       // this round's position in the solved block
-            if (g == 0) {
+            const int blk = block_round / G, par = overlap ? (blk & 1) : 0;
+            auto launch_block = [&](int parity, unsigned long long hyp_base_p1) {   // sample + solve + records of one block of G rounds
                 RoundArgs b;
                 fill_round_args(c, b, cfg->sampler, KB);
                 b.thr = cfg->threshold; b.confidence = cfg->confidence; b.max_iterations = cfg->max_iterations;
                 b.table_rows = cfg->sample_table_rows; b.nchunks = nchunks; b.sprt = cfg->sprt; b.pool = c->d_pool.p; b.sprt_res = c->d_sprt_res.p;
                 b.before_sprt = before_sprt;
+                b.hyp_base_p1 = hyp_base_p1;
+                b.samples = c->d_samples.p + (size_t)parity * KB * m; b.nmodels = c->d_nmodels.p + (size_t)parity * KB;
+                b.offsets = c->d_offsets.p + (size_t)parity * KB; b.models_raw = c->d_models_raw.p + (size_t)parity * KB * S * 9;
+                b.recs = c->d_recs.p + (size_t)parity * KB * S * USAC_REC_STRIDE; b.mvalid = c->d_mvalid.p + parity;
+                b.seeds = c->d_seeds.p + (size_t)parity * KB;
                 launch_sampler(c, b, 1);
                 RK("sample");
                 switch (c->est) {
@@ -1682,6 +1700,22 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 prepare_kernel<<<1, KB >= 1024 ? 1024 : 256, 0, c->stream>>>(b);
                 c->last_launches++;
                 RK("prepare");
+            };
+            if (g == 0) {
+                if (prelaunched == blk) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_block[par], 0));   // solved beside the previous block's rounds
+                else launch_block(par, 0);
+                // the next block, on the second stream (its hypothesis ids are known: K per round) - unless this block will most likely end
+                // the fit: iterations per sample so far (1 + rejected models, ransac.cpp:77-85) x the samples of one block
+                const double per_sample = hs.samples_drawn ? (double)hs.iters / (double)hs.samples_drawn : 1.0;
+                const bool likely_more = (double)(hs.max_iters - hs.iters) > 0.9 * per_sample * (double)KB;
+                if (overlap && likely_more) {
+                    cudaStream_t main_stream = c->stream;
+                    c->stream = c->stream2;
+                    launch_block(par ^ 1, (unsigned long long)hs.samples_drawn + (unsigned long long)KB + 1ull);
+                    c->stream = main_stream;
+                    CUDA_TRY(c, cudaEventRecord(c->ev_block[par ^ 1], c->stream2));
+                    prelaunched = blk + 1;
+                }
             }
             block_round++;
             // this round's view of the block: samples [g K, (g + 1) K); record offsets stay relative to the block
@@ -1690,8 +1724,9 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
             a.thr = cfg->threshold; a.confidence = cfg->confidence; a.max_iterations = cfg->max_iterations;
             a.table_rows = cfg->sample_table_rows; a.nchunks = nchunks; a.sprt = cfg->sprt; a.pool = c->d_pool.p; a.sprt_res = c->d_sprt_res.p;
             a.before_sprt = before_sprt;
-            a.nmodels = c->d_nmodels.p + (size_t)g * K; a.offsets = c->d_offsets.p + (size_t)g * K;
-            a.models_raw = c->d_models_raw.p + (size_t)g * KS * 9;
+            a.nmodels = c->d_nmodels.p + (size_t)par * KB + (size_t)g * K; a.offsets = c->d_offsets.p + (size_t)par * KB + (size_t)g * K;
+            a.models_raw = c->d_models_raw.p + ((size_t)par * KB * S + (size_t)g * KS) * 9;
+            a.recs = c->d_recs.p + (size_t)par * KB * S * USAC_REC_STRIDE; a.mvalid = c->d_mvalid.p + par;
             if (is_sprt) {
                 switch (c->est) {
                     case USAC_EST_LINE2D: rc = launch_walk<USAC_EST_LINE2D>(c, a, 1); break;
@@ -1799,6 +1834,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
             t_replay += us(t_r2, now()) - t_lo_round - t_mask_round;
         }
         hs.done = 1;
+        if (overlap && prelaunched > (block_round - 1) / G) CUDA_TRY(c, cudaStreamSynchronize(c->stream2));   // solved ahead and never used (rare: see likely_more): its buffers are free again
         usac_fit_result& r = results[p];
         memset(&r, 0, sizeof(r));
         for (int i = 0; i < w; i++) r.model[i] = hs.best_model[i];
