@@ -201,14 +201,21 @@ __global__ void napsac_seed_kernel(const RoundArgs a) {
     if (a.neighbors == USAC_NEIGH_KNN) {
         philox_unique(a.seed, hyp, 4, pd.n, 1, &p);
     } else {
-        int tries = 0;
-        for (; tries < pd.n; tries++) {
-            philox_unique(a.seed, hyp, 16 + (uint32_t)tries, pd.n, 1, &p);
-            const int c = a.cell_of_point[pd.grid_off + p];
-            const int cnt = a.cell_start[pd.cell_start_off + c + 1] - a.cell_start[pd.cell_start_off + c] - 1;
-            if (cnt >= a.m) break;
+        // napsac_sampler.hpp:100-128: redraw the seed until its cell holds enough neighbours; a call that finds none in n draws switches
+        // the sampler to uniform sampling FOR THE REST OF THE RUN (do_uniform). The hypothesis id of the first such call lives in the
+        // last entry of the cursor segment (0xffffffff = none): every sample from that id on is uniform, whatever its own search says.
+        unsigned* first_uniform = a.cursors + pd.cursor_off + 3 * (size_t)pd.n;
+        if ((unsigned long long)hyp >= (unsigned long long)*reinterpret_cast<volatile unsigned*>(first_uniform)) p = -1;
+        else {
+            int tries = 0;
+            for (; tries < pd.n; tries++) {
+                philox_unique(a.seed, hyp, 16 + (uint32_t)tries, pd.n, 1, &p);
+                const int c = a.cell_of_point[pd.grid_off + p];
+                const int cnt = a.cell_start[pd.cell_start_off + c + 1] - a.cell_start[pd.cell_start_off + c] - 1;
+                if (cnt >= a.m) break;
+            }
+            if (tries == pd.n) { p = -1; atomicMin(first_uniform, (unsigned)hyp); }
         }
-        if (tries == pd.n) p = -1;           // no usable neighbourhood anywhere: uniform fallback for this sample
     }
     a.seeds[(size_t)slot * a.K + j] = p;
     // how often the round uses each seed point (second half of the cursor segment, all zero between rounds): a seed used once -
@@ -226,7 +233,9 @@ __global__ void napsac_commit_kernel(const RoundArgs a) {
     const int p = a.seeds[(size_t)slot * a.K + j];
     if (p >= 0) {
         const ProblemDesc pd = a.prob[pid];
-        atomicAdd(&a.cursors[pd.cursor_off + p], (unsigned)(a.m - 1));
+        const uint64_t hyp = (a.hyp_base_p1 ? (uint64_t)(a.hyp_base_p1 - 1) : (uint64_t)a.state[pid].samples_drawn) + j;
+        const bool uniform_by_now = a.neighbors != USAC_NEIGH_KNN && hyp >= (uint64_t)a.cursors[pd.cursor_off + 3 * (size_t)pd.n];
+        if (!uniform_by_now) atomicAdd(&a.cursors[pd.cursor_off + p], (unsigned)(a.m - 1));   // a sample drawn uniformly consumed no neighbours
         a.cursors[pd.cursor_off + pd.n + p] = 0u;                     // use count and first user back to zero for the next round
         a.cursors[pd.cursor_off + 2 * (size_t)pd.n + p] = 0u;
     }
@@ -270,7 +279,8 @@ __global__ void sample_kernel(const RoundArgs a) {
     } else if (a.sampler == USAC_SAMPLER_NAPSAC) {
         const int* seeds = a.seeds + (size_t)slot * a.K;
         const int p = seeds[j];
-        if (p < 0) {
+        const bool uniform_by_now = a.neighbors != USAC_NEIGH_KNN && hyp >= (uint64_t)a.cursors[pd.cursor_off + 3 * (size_t)n];   // do_uniform
+        if (p < 0 || uniform_by_now) {
             philox_unique(a.seed, hyp, 0, n, m, s);
         } else {
             unsigned c = a.cursors[pd.cursor_off + p];

@@ -490,7 +490,7 @@ extern "C" int usac_gpu_set_neighbors_knn(usac_gpu_ctx* c, int problem, const in
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (fresh) u.knn += (size_t)d.n * k;
     d.knn_off = off;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)d.n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)d.n + 1, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -584,7 +584,7 @@ extern "C" int usac_gpu_build_neighbors_knn(usac_gpu_ctx* c, int problem, int k)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     d.knn_off = knn_off;
     if (knn_fresh) u.knn += (size_t)n * k;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n + 1, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_KNN; d.knn = k;
     return push_desc(c);
 }
@@ -642,7 +642,7 @@ extern "C" int usac_gpu_set_neighbors_grid(usac_gpu_ctx* c, int problem, int cel
     d.cell_start_off = (long long)u.cell_start;
     u.grid += (size_t)n;
     u.cell_start += (size_t)n + 1;
-    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n, &d.cursor_off, c->stream));
+    if (d.cursor_off < 0) CUDA_TRY(c, append_segment(c->d_cursors, u.cursors, (const unsigned*)nullptr, 3 * (size_t)n + 1, &d.cursor_off, c->stream));
     d.neigh_type = USAC_NEIGH_GRID;
     return push_desc(c);
 }
@@ -1046,7 +1046,11 @@ static int setup_sampler_side(usac_gpu_ctx* c, const usac_sampler_cfg& s, bool r
         for (int p = 0; p < c->P; p++) {
             const ProblemDesc& d = c->h_prob[p];
             if (s.neighbors == USAC_NEIGH_KNN ? d.knn_off < 0 : d.grid_off < 0) return fail(c, USAC_ERR_STATE, "NAPSAC: neighbourhood of a problem was not set");
-            if (reset_cursors) CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off, 0, sizeof(unsigned) * d.n, c->stream));
+            if (reset_cursors) {
+                CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off, 0, sizeof(unsigned) * d.n, c->stream));
+                // last entry of the segment: the first hypothesis that found no usable neighbourhood (from there on the sampler is uniform)
+                CUDA_TRY(c, cudaMemsetAsync(c->d_cursors.p + d.cursor_off + 3 * (size_t)d.n, 0xFF, sizeof(unsigned), c->stream));
+            }
         }
     }
     return USAC_OK;

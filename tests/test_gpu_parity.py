@@ -284,6 +284,29 @@ def test_napsac_sampler_matches_oracle(ctx):
     assert np.array_equal(got, ref)
 
 
+def test_napsac_grid_switches_to_uniform_for_the_rest_of_the_run(ctx):
+    """napsac_sampler.hpp:100-128: a call that finds no seed with enough cell neighbours in n draws sets do_uniform, and EVERY later
+    call samples uniformly. Sparse data with a single usable cell: the switch happens somewhere inside the table (found by the randomised
+    sweep of round 2: the device used to fall back for that one sample only)."""
+    from ransac_b200.api import NEIGH_GRID, SAMPLER_NAPSAC
+    g = np.random.default_rng(77)
+    pts = (g.random((900, 4)) * 1000).astype(np.float32)
+    pts[:6] = np.float32([310.0, 420.0, 615.0, 120.0]) + (g.random((6, 4)) * 5).astype(np.float32)    # the one cell with >= 4 neighbours
+    ctx.set_points(O.EST_HOMOGRAPHY, pts)
+    ctx.set_neighbors_grid(0, 50)
+    ref = O.Sampler(O.SAMPLER_NAPSAC, O.RNG_PHILOX, len(pts), 4, 5, points=pts, cell_size=50).table(4000)
+    in_cell = np.isin(ref, np.arange(6)).all(axis=1)
+    assert in_cell[:20].all() and not in_cell[-500:].any()            # NAPSAC at first, uniform at the end: the switch is inside the table
+    for K in (4000, 256, 1):                                          # one round, several rounds, sample by sample
+        got = np.concatenate([ctx.sample(min(K, 4000 - h), sampler=SAMPLER_NAPSAC, seed=5, neighbors=NEIGH_GRID, first_hyp=h)
+                              for h in range(0, 4000 if K > 1 else 600, K)])
+        assert np.array_equal(got, ref[:len(got)]), K
+    r = ctx.fit(2.0, 0.95, 3000, sampler=SAMPLER_NAPSAC, neighbors=NEIGH_GRID, seed=5, round_size=128)[0]
+    o = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_GRID, cell_size=50,
+                 threshold=2.0, confidence=0.95, max_iterations=3000, seed=5)
+    assert_fit_equal(r, o, O.EST_HOMOGRAPHY)
+
+
 def knn_rows_bruteforce(pts, rows, k):
     """numpy restatement of orc_knn_build for a subset of query rows (float32, column order, (distance, index) ties)."""
     out = np.empty((len(rows), k), np.int32)

@@ -25,6 +25,7 @@ def bits(a):
     return a.view(np.uint32)
 
 
+ONLY = set(int(x) for x in os.environ.get("STRESS_ONLY_CASES", "").split(",") if x)   # re-run single cases of a sweep (same random stream)
 ctx = GpuContext(0)
 bad, t0 = [], time.time()
 for case in range(CASES):
@@ -62,6 +63,8 @@ for case in range(CASES):
     if sprt or sampler == "prosac" or lo:
         okw["batch"] = min(K, max_it)          # usac_gpu_fit never draws more than max_iterations samples per round
     tag = f"case {case}: cfg {cfg} n {n} ratio {ratio} {sampler} sprt {sprt} lo {lo} K {K} max_it {max_it} seed {seed}"
+    if ONLY and case not in ONLY:
+        continue
     try:
         r = ctx.fit(**kw)[0]
         ref = O.ransac(pts, est, **okw)
@@ -71,6 +74,16 @@ for case in range(CASES):
             diff.append("model")
         if diff:
             bad.append((tag, diff, {k: (r[k], ref[k]) for k in diff if k != "model"}))
+            if os.environ.get("STRESS_DEBUG"):
+                kw2 = {k: v for k, v in kw.items() if k not in ("lo", "sprt")}
+                okw2 = {k: v for k, v in okw.items() if k not in ("lo", "sprt", "batch")}
+                r2, ref2 = ctx.fit(**kw2)[0], O.ransac(pts, est, **okw2)
+                print("DEBUG", tag, "neighbors", kw.get("neighbors"), "| with flags: gpu", {k: r[k] for k in ("inliers", "iterations", "best_hyp", "rounds", "samples_drawn")},
+                      "oracle", {k: ref[k] for k in ("inliers", "iterations", "best_hyp")}, "| plain fit: gpu", {k: r2[k] for k in ("inliers", "iterations", "best_hyp")},
+                      "oracle", {k: ref2[k] for k in ("inliers", "iterations", "best_hyp")})
+                for K2 in (1, 16, 512):
+                    r3 = ctx.fit(**dict(kw, round_size=K2))[0]
+                    print("DEBUG   same flags, round size", K2, {k: r3[k] for k in ("inliers", "iterations", "best_hyp", "rounds")})
         # Quality::getInliers and the refit loop on the result
         if r["inliers"] > 0 and cfg != 1:
             ids = ctx.get_inliers(r["model"], thr)
