@@ -97,6 +97,76 @@ for case in range(CASES):
     except Exception as e:   # noqa: BLE001
         bad.append((tag, ["exception"], {"error": repr(e)}))
 
+# the plug-in entry points one by one: minimal solvers (model bits), Quality counts, per-point errors (bits), sampler tables, non-minimal fits
+N_API = 0 if ONLY else max(6, CASES // 10)
+for case in range(N_API):
+    cfg = int(g.choice([1, 2, 3, 4]))
+    est = EST[cfg]
+    n = int(g.integers(50, 5000)) | 1
+    pts, _, mask = gen.make(cfg, seed_offset=9000 + case, n=n, inlier_ratio=float(g.choice([0.2, 0.5, 0.8])))
+    n = len(pts)
+    thr = gen.CONFIGS[cfg]["threshold"]
+    m = O.SAMPLE_SIZE[est]
+    tag = f"api {case}: cfg {cfg} n {n}"
+    try:
+        ctx.set_points(est, pts)
+        inl = np.where(mask)[0]
+        samples = np.stack([(g.choice(inl, m, replace=False) if (i % 2 == 0 and len(inl) >= m) else g.choice(n, m, replace=False)) for i in range(40)]).astype(np.int32)
+        models, nm = ctx.estimate(samples)
+        w = 3 if cfg == 1 else 9
+        allm = []
+        for i, smp in enumerate(samples):
+            ref = O.solve_minimal(est, pts, smp)
+            if nm[i] != len(ref) or not np.array_equal(bits(models[i, :nm[i], :w]), bits(ref[:, :w])):
+                bad.append((tag, ["estimate"], {"sample": i, "count": (int(nm[i]), len(ref))}))
+                break
+            allm.extend(ref[:, :w])
+        if allm:
+            allm = np.stack(allm)
+            cnt, sm = ctx.score(allm, thr)
+            for i, mod in enumerate(allm):
+                oc = O.score(est, pts, mod, thr)
+                # counts exact; the MSAC cost sum + (n - inliers) thr within 1e-4 relative (BASELINE.json). The raw sum of a model that fits only
+                # its own sample is rounding noise of the evaluator (~1e-3 px per point at coordinates ~1000) and is not compared.
+                msac_g, msac_o = sm[i] + (n - cnt[i]) * thr, oc[1] + (n - oc[0]) * thr
+                if cnt[i] != oc[0] or abs(msac_g - msac_o) > 1e-4 * abs(msac_o):
+                    bad.append((tag, ["score"], {"model": i, "count": (int(cnt[i]), int(oc[0])), "sum": (float(sm[i]), float(oc[1]))}))
+                    break
+            e = ctx.errors(allm[0])
+            if not np.array_equal(bits(e), bits(O.errors(est, pts, allm[0]))):
+                bad.append((tag, ["errors"], {}))
+        if cfg != 1 and len(inl) >= 30:
+            ids = np.sort(g.choice(inl, int(g.integers(8, min(len(inl), 2000))), replace=False)).astype(np.int32)
+            got, ref = ctx.estimate_nonminimal(ids), O.nonminimal(est, pts, ids)
+            if (got is None) != (ref is None) or (got is not None and not np.array_equal(bits(got), bits(np.asarray(ref, np.float32)))):
+                bad.append((tag, ["estimate_nonminimal"], {"count": len(ids)}))
+        # sampler tables: PROSAC, and NAPSAC over a grid (with the switch to uniform on sparse data), in chunks of random size
+        for kind in ("prosac", "napsac"):
+            if cfg == 1:
+                continue
+            seed = int(g.integers(1, 1000))
+            T = 600
+            if kind == "prosac":
+                ref = O.Sampler(O.SAMPLER_PROSAC, O.RNG_PHILOX, n, m, seed).table(T)
+                skw = dict(sampler=capi.SAMPLER_PROSAC)
+            else:
+                ctx.set_neighbors_grid(0, 50)
+                ref = O.Sampler(O.SAMPLER_NAPSAC, O.RNG_PHILOX, n, m, seed, points=pts, cell_size=50).table(T)
+                skw = dict(sampler=capi.SAMPLER_NAPSAC, neighbors=capi.NEIGH_GRID)
+            if kind == "prosac":
+                got = ctx.sample(T, seed=seed, **skw)              # the PROSAC state is a function of the counter: one call
+            else:
+                chunk, parts, h = int(g.choice([1, 37, 600])), [], 0
+                while h < (T if chunk > 1 else 120):
+                    k = min(chunk, T - h)
+                    parts.append(ctx.sample(k, seed=seed, first_hyp=h, **skw))
+                    h += k
+                got = np.concatenate(parts)
+            if not np.array_equal(got, ref[:len(got)]):
+                bad.append((tag, ["sample " + kind], {"first difference": int(np.argmax((got != ref[:len(got)]).any(axis=1)))}))
+    except Exception as e:   # noqa: BLE001
+        bad.append((tag, ["exception"], {"error": repr(e)}))
+
 # batches of ragged problems in flight: the plain path (device-side select) and the SPRT batch path (host replay per problem)
 for case in range(max(4, CASES // 15)):
     cfg = int(g.choice([1, 2, 3, 4]))
@@ -142,7 +212,7 @@ for n in (32767, 32768, 40001, 131073):
     if rf["inliers"] != orf["inliers"] or not np.array_equal(bits(rf["model"]), bits(np.asarray(orf["model"], np.float32))):
         bad.append((f"refit n={n}", ["refit"], {"inliers": (rf["inliers"], orf["inliers"])}))
 ctx.close()
-print(f"stress_parity: {CASES} fits + {max(4, CASES // 15)} ragged batches + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches")
+print(f"stress_parity: {CASES} fits + {N_API} API sweeps + {max(4, CASES // 15)} ragged batches + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches")
 for b in bad:
     print("MISMATCH", b)
 sys.exit(1 if bad else 0)
