@@ -130,6 +130,48 @@ def test_peer_windows_match_single_gpu_and_oracle(cfg, world, batch):
             assert sum(results[rank][rep][b]["useful_evals"] for rank in range(world)) == ref["evals"]
 
 
+@pytest.mark.parametrize("sparse", [False, True])
+def test_peer_windows_napsac_grid(sparse):
+    """NAPSAC over a grid with the hypotheses sharded over 3 ranks (peer windows): every rank computes the seeds / cursors of ALL samples
+    and solves its own; `sparse` = data with one usable cell, where the sampler switches to uniform sampling part-way (do_uniform)."""
+    from ransac_b200 import GpuContext
+    from ransac_b200.api import NEIGH_GRID, SAMPLER_NAPSAC
+    world = 3
+    if sparse:
+        g = np.random.default_rng(78)
+        pts = (g.random((900, 4)) * 1000).astype(np.float32)
+        pts[:6] = np.float32([310.0, 420.0, 615.0, 120.0]) + (g.random((6, 4)) * 5).astype(np.float32)
+    else:
+        pts = gen.homography(n=20000, inlier_ratio=0.1, clustered=True, seed=31)[0]
+    ctxs = [GpuContext(0) for _ in range(world)]
+    wins = [c.peer_window() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.set_points(O.EST_HOMOGRAPHY, pts)
+        c.set_neighbors_grid(0, 50)
+        c.peer_attach_ptrs(wins, r, world)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            results[rank] = ctxs[rank].fit(2.0, 0.95, 1500, sampler=SAMPLER_NAPSAC, neighbors=NEIGH_GRID, seed=4, round_size=129, rank=rank, nranks=world)[0]
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    for c in ctxs:
+        c.close()
+    assert not errors, errors
+    ref = O.ransac(pts, O.EST_HOMOGRAPHY, sampler=O.SAMPLER_NAPSAC, rng=O.RNG_PHILOX, neighbors=O.NEIGH_GRID, cell_size=50,
+                   threshold=2.0, confidence=0.95, max_iterations=1500, seed=4)
+    for r in results:
+        for k in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+            assert r[k] == ref[k], (k, r[k], ref[k])
+        assert np.array_equal(r["model"].view(np.uint32), np.asarray(ref["model"], np.float32).view(np.uint32))
+
+
 def test_config5_emulated_ranks_full_size():
     """BASELINE config 5 at its stated size (1M correspondences, NAPSAC grid): the hypotheses of every round split over 4
     emulated ranks give the single-GPU result on every rank (which test_gpu_parity checks against the oracle)."""
