@@ -27,11 +27,13 @@ def bits(a):
 
 ONLY = set(int(x) for x in os.environ.get("STRESS_ONLY_CASES", "").split(",") if x)   # re-run single cases of a sweep (same random stream)
 ctx = GpuContext(0)
-bad, t0 = [], time.time()
+bad, ties, t0 = [], [], time.time()
 for case in range(CASES):
     cfg = int(g.choice([1, 2, 2, 3, 3, 4]))
     est = EST[cfg]
     n = int(g.integers(200, 6000)) | 1
+    if case % 10 == 9:                                     # tiny problems: down to the minimal sample itself
+        n = int(O.SAMPLE_SIZE[est] + g.choice([0, 1, 2, 5, 11, 30, 57, 70]))
     ratio = float(g.choice([0.15, 0.3, 0.5, 0.7]))
     pts = gen.make(cfg, seed_offset=1000 + case, n=n, inlier_ratio=ratio)[0]
     if len(pts) != n:
@@ -53,8 +55,12 @@ for case in range(CASES):
             ctx.set_neighbors_grid(0, 50)
             kw.update(sampler=capi.SAMPLER_NAPSAC, neighbors=capi.NEIGH_GRID); okw.update(sampler=O.SAMPLER_NAPSAC, neighbors=O.NEIGH_GRID, cell_size=50)
         else:
-            ctx.build_neighbors_knn(0, 7)
-            kw.update(sampler=capi.SAMPLER_NAPSAC, neighbors=capi.NEIGH_KNN); okw.update(sampler=O.SAMPLER_NAPSAC, neighbors=O.NEIGH_KNN, knn_table=O.knn_build(pts, 7))
+            kk = min(7, n - 1)
+            if kk < O.SAMPLE_SIZE[est] - 1:
+                sampler = "uniform"
+            else:
+                ctx.build_neighbors_knn(0, kk)
+                kw.update(sampler=capi.SAMPLER_NAPSAC, neighbors=capi.NEIGH_KNN); okw.update(sampler=O.SAMPLER_NAPSAC, neighbors=O.NEIGH_KNN, knn_table=O.knn_build(pts, kk))
     if sprt:
         ctx.set_sprt_pool(0, O.sprt_pool(seed, n))
         kw["sprt"] = True; okw["sprt"] = True
@@ -72,6 +78,14 @@ for case in range(CASES):
         diff = [k for k in keys if r[k] != ref[k]]
         if not np.array_equal(bits(r["model"]), bits(ref["model"])):
             diff.append("model")
+        if diff and set(diff) <= {"best_hyp", "best_model_idx", "model"} and not sprt and not lo:
+            # Score::bigger breaks ties between equal inlier counts by the error SUM, which the device accumulates in another order than
+            # the host restatement (1e-4 relative, BASELINE.json): two hypotheses whose sums agree to rounding noise (the same points drawn
+            # twice, a tiny problem) may swap. Accepted when the device's winner, scored by the oracle, has the oracle's count and its sum.
+            oc = O.score(est, pts, r["model"], thr)
+            if oc[0] == ref["inliers"] and abs(oc[1] - ref["score"]) <= 1e-4 * abs(ref["score"]) + 1e-4 * thr:
+                ties.append(tag)
+                diff = []
         if diff:
             bad.append((tag, diff, {k: (r[k], ref[k]) for k in diff if k != "model"}))
             if os.environ.get("STRESS_DEBUG"):
@@ -212,7 +226,7 @@ for n in (32767, 32768, 40001, 131073):
     if rf["inliers"] != orf["inliers"] or not np.array_equal(bits(rf["model"]), bits(np.asarray(orf["model"], np.float32))):
         bad.append((f"refit n={n}", ["refit"], {"inliers": (rf["inliers"], orf["inliers"])}))
 ctx.close()
-print(f"stress_parity: {CASES} fits + {N_API} API sweeps + {max(4, CASES // 15)} ragged batches + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches")
+print(f"stress_parity: {CASES} fits + {N_API} API sweeps + {max(4, CASES // 15)} ragged batches + 4 large inlier lists in {time.time() - t0:.1f} s, {len(bad)} mismatches ({len(ties)} tie(s) between equal counts broken by sums that agree to rounding noise)")
 for b in bad:
     print("MISMATCH", b)
 sys.exit(1 if bad else 0)
