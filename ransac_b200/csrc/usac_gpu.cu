@@ -102,6 +102,7 @@ struct usac_gpu_ctx {
     DevBuf<unsigned> d_sprt_count;
     cudaStream_t stream2 = nullptr;           // solve-ahead blocks of the SPRT replay path run here, beside the rounds of the previous block
     cudaEvent_t ev_block[2] = {nullptr, nullptr};
+    cudaEvent_t ev_round = nullptr;
     DevBuf<int> d_lo_bwave;                   // speculative LO waves (lo.cuh): candidate inlier lists, per-iteration records, state
     DevBuf<LoSpec> d_lo_spec;
     DevBuf<LoWaveState> d_lo_ws;
@@ -226,6 +227,7 @@ extern "C" void usac_gpu_destroy(usac_gpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     for (int i = 0; i < 2; i++) if (c->ev_block[i]) cudaEventDestroy(c->ev_block[i]);
+    if (c->ev_round) cudaEventDestroy(c->ev_round);
     for (void* w : c->peer_opened) cudaIpcCloseMemHandle(w);
     if (c->peer_self) cudaFree(c->peer_self);
     if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
@@ -1015,7 +1017,7 @@ static int ensure_round_buffers(usac_gpu_ctx* c, int slots, int K, int nchunks, 
     CUDA_TRY(c, c->d_samples.ensure(sk * m));
     CUDA_TRY(c, c->d_nmodels.ensure(sk));
     CUDA_TRY(c, c->d_offsets.ensure(sk));
-    CUDA_TRY(c, c->d_mvalid.ensure(slots));
+    CUDA_TRY(c, c->d_mvalid.ensure((size_t)slots + 1));          // + 1: the second buffer set of the solve-ahead path
     CUDA_TRY(c, c->d_models_raw.ensure(sk * S * 9));
     CUDA_TRY(c, c->d_recs.ensure(sk * S * USAC_REC_STRIDE));
     CUDA_TRY(c, c->d_part_cnt.ensure(sk * S * nchunks));
@@ -1624,6 +1626,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
     if (overlap && !c->stream2) {
         CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_block[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_round, cudaEventDisableTiming));
     }
     CUDA_TRY(c, c->d_model_scores.ensure(KS));
     CUDA_TRY(c, c->h_rp_nmodels.ensure(K));
@@ -1677,6 +1680,7 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 rc = ensure_round_buffers(c, 1, K, nchunks, 1);
                 if (rc) return rc;
             }
+            if (overlap) CUDA_TRY(c, cudaEventRecord(c->ev_round, c->stream));   // everything up to this round's state upload
             RK("start");
             // ---- sample + solve + records: once per block of G rounds ----
             const int g = block_round % G;                       // this round's position in the solved block
@@ -1713,6 +1717,9 @@ static int fit_host_replay(usac_gpu_ctx* c, const usac_fit_cfg* cfg, usac_fit_re
                 const double per_sample = hs.samples_drawn ? (double)hs.iters / (double)hs.samples_drawn : 1.0;
                 const bool likely_more = (double)(hs.max_iters - hs.iters) > 0.9 * per_sample * (double)KB;
                 if (overlap && likely_more) {
+                    // the second stream starts behind everything the main stream had been given when this round began (the descriptors, the
+                    // active list, the SPRT pool of a first fit: a kernel of the block must not run ahead of those uploads)
+                    CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_round, 0));
                     cudaStream_t main_stream = c->stream;
                     c->stream = c->stream2;
                     launch_block(par ^ 1, (unsigned long long)hs.samples_drawn + (unsigned long long)KB + 1ull);

@@ -4,8 +4,11 @@
 //                    usac_gpu_refit, then the final inlier list;
 //   run_sequential() the reference's one-hypothesis-at-a-time loop (ransac.cpp:58-139) over the virtual plugin interfaces -
 //                    Sampler, Estimator, Quality, SPRT, TerminationCriteria / ProsacTerminationCriteria, LocalOptimization -
-//                    each call forwarding to the C ABI: the drop-in at plugin granularity. run() with Model::gpu_round_size = 1
-//                    gives the same results (batch(1) == sequential); larger rounds freeze the SPRT test within a round.
+//                    each call forwarding to the C ABI: the drop-in at plugin granularity. Without SPRT, run() with
+//                    Model::gpu_round_size = 1 is the same loop (and without PROSAC every round size is). With SPRT a round freezes
+//                    the test and starts model q of the round at pool offset cursor + 32 q (the oracle's batch = K form), while
+//                    the sequential walk starts where the last one stopped: about one SPRT fit in ten ends differently even at
+//                    K = 1 (tools/stress_harness.py holds each form to its own oracle loop).
 #pragma once
 #include <chrono>
 

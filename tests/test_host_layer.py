@@ -167,7 +167,10 @@ def test_fused_equals_sequential_equals_oracle(harness, tmp_path, cfg, est_name,
 def test_sprt_prosac_lo_through_the_plugin_classes(harness, tmp_path, est_name, sampler, flags):
     """BASELINE configs 3 and 4 through the usac/ C++ surface: Ransac's constructor wires SPRT (pool upload), ProsacTerminationCriteria
     (shared stopping length / largest sample size) and InnerLocalOptimization through the init* factories (ransac.hpp:41-93, init.cpp:3-83).
-    run() with rounds of one sample == run_sequential() over the virtual plugin calls == the oracle's sequential loop + refit."""
+    run_sequential() over the virtual plugin calls == the oracle's sequential loop + refit (the reference's semantics); run() with rounds
+    of one sample == the oracle's rounds of one (batch = 1). Without SPRT those are one loop; with SPRT a round starts its walks at
+    cursor + 32 q instead of where the last walk stopped, so the two can end differently (tools/stress_harness.py: ~1 fit in 10) - on
+    these five inputs they do not, which the test also states."""
     from oracle import oracle as O
     from ransac_b200 import generator as gen
     est = {"homography": O.EST_HOMOGRAPHY, "fundamental": O.EST_FUNDAMENTAL, "essential": O.EST_ESSENTIAL}[est_name]
@@ -191,12 +194,13 @@ def test_sprt_prosac_lo_through_the_plugin_classes(harness, tmp_path, est_name, 
     assert abs(f["score"] - s["score"]) <= 1e-4 * abs(s["score"])
     assert np.array_equal(f["model"], s["model"])
     sprt, lo = "--sprt" in flags, int(flags[flags.index("--lo") + 1]) if "--lo" in flags else 0
-    ref = O.ransac(pts, est, sampler=O.SAMPLER_PROSAC if sampler == "prosac" else O.SAMPLER_UNIFORM, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95,
-                   max_iterations=max_it, seed=7, sprt=sprt, lo=lo)
-    fin = O.refit(est, pts, ref["model"], ref["inliers"], thr)
-    assert f["iterations"] == ref["iterations"] and f["inliers"] == fin["inliers"]
-    assert np.array_equal(f["model"], np.asarray(fin["model"], np.float32).view(np.uint32))
-    assert f["hash"] == fnv(fin["ids"][:fin["inliers"]])
+    for got_form, batch in ((s, 0), (f, 1)):
+        ref = O.ransac(pts, est, sampler=O.SAMPLER_PROSAC if sampler == "prosac" else O.SAMPLER_UNIFORM, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95,
+                       max_iterations=max_it, seed=7, sprt=sprt, lo=lo, batch=batch)
+        fin = O.refit(est, pts, ref["model"], ref["inliers"], thr)
+        assert got_form["iterations"] == ref["iterations"] and got_form["inliers"] == fin["inliers"]
+        assert np.array_equal(got_form["model"], np.asarray(fin["model"], np.float32).view(np.uint32))
+        assert got_form["hash"] == fnv(fin["ids"][:fin["inliers"]])
 
 
 def test_init_factories_and_classes_keep_the_reference_signatures():
