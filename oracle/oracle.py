@@ -33,7 +33,7 @@ class Config(C.Structure):
                 ("confidence", C.c_float), ("max_iterations", C.c_uint), ("sprt", C.c_int), ("batch", C.c_int),
                 ("neighbors", C.c_int), ("knn", C.c_int), ("cell_size", C.c_int), ("seed", C.c_uint64),
                 ("sample_table", C.POINTER(C.c_int)), ("sample_table_rows", C.c_uint),
-                ("knn_table", C.POINTER(C.c_int)), ("lo", C.c_int)]
+                ("knn_table", C.POINTER(C.c_int)), ("lo", C.c_int), ("ref_thin_svd", C.c_int)]
 
 
 class Result(C.Structure):
@@ -63,6 +63,8 @@ def lib():
         L.orc_inv3x3.restype = C.c_int
         L.orc_solve_minimal.argtypes = [C.c_int, fp, ip, fp]
         L.orc_solve_minimal.restype = C.c_int
+        L.orc_solve_homography_dlt4p_thin.argtypes = [fp, ip, fp]
+        L.orc_solve_homography_dlt4p_thin.restype = C.c_int
         L.orc_solve_cubic.argtypes = [dp, dp]
         L.orc_solve_cubic.restype = C.c_int
         L.orc_fundamental_is_valid.argtypes = [fp, fp, ip]
@@ -167,6 +169,15 @@ def solve_minimal(est, points, sample):
     k = lib().orc_solve_minimal(est, _f(p), _i(s), _f(out))
     w = 3 if est == EST_LINE2D else 9
     return out[:k * w].reshape(k, w).copy() if est != EST_LINE2D else out[:3 * k].reshape(k, 3).copy()
+
+
+def solve_homography_dlt4p_thin(points, sample):
+    """SURVEY Appendix B quirk 1: the reference's DLt::DLT4p (8th singular vector of the raw 8 x 9 system) -> (k, 9), k in {0, 1}"""
+    p, _ = _pts(points)
+    s = np.ascontiguousarray(sample, dtype=np.int32)
+    out = np.zeros(9, np.float32)
+    k = lib().orc_solve_homography_dlt4p_thin(_f(p), _i(s), _f(out))
+    return out.reshape(1, 9)[:k].copy()
 
 
 def essential5_candidates(points, sample):
@@ -287,13 +298,15 @@ def sprt_pool(seed, n):
 
 
 def ransac(points, est, sampler=SAMPLER_UNIFORM, rng=RNG_PHILOX, threshold=2.0, confidence=0.95, max_iterations=10000,
-           sprt=False, batch=0, seed=1, neighbors=NEIGH_NONE, knn=5, cell_size=50, sample_table=None, knn_table=None, lo=0):
+           sprt=False, batch=0, seed=1, neighbors=NEIGH_NONE, knn=5, cell_size=50, sample_table=None, knn_table=None, lo=0,
+           ref_thin_svd=False):
     p, n = _pts(points)
     cfg = Config()
     cfg.estimator, cfg.sampler, cfg.rng = est, sampler, rng
     cfg.threshold, cfg.confidence, cfg.max_iterations = threshold, confidence, max_iterations
     cfg.sprt, cfg.batch, cfg.neighbors, cfg.knn, cfg.cell_size, cfg.seed = int(sprt), batch, neighbors, knn, cell_size, seed
     cfg.lo = lo
+    cfg.ref_thin_svd = int(ref_thin_svd)     # the reference's DLT4p instead of the normalised DLT
     keep = []
     if sample_table is not None:
         t = np.ascontiguousarray(sample_table, dtype=np.int32)

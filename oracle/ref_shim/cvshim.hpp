@@ -469,9 +469,74 @@ template <class T> void put(Mat& dst, int r, int c, const T* src, size_t ld) {
     for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) dst.ptr<T>(i)[j] = src[(size_t)i * ld + j];
 }
 
+// The thin SVD of a WIDE matrix (m < n; the 8 x 9 system of DLt::DLT4p, dlt.cpp:43) the way cv::SVD does it: OpenCV transposes a
+// wide matrix and orthogonalises the m ROWS of A (stored in T, dot products and angles in double); row i ends as sigma_i v_i', so
+// the right singular vectors are the normalised rows themselves and not a product of rotations. That matters for DLT4p: its rows
+// all have the scale of the largest entries (1e6 for pixel coordinates), its columns range from 1 to 1e6, and the vector it
+// takes belongs to sigma_8 ~ 0.1. Rotating columns in float32 (jacobi_svd above) loses that vector (30 % off cv2.SVDecomp on the
+// same matrices); rotating rows reproduces OpenCV's to ~1e-5 (tests/golden/cv_primitives.npz, test_ref_build.py).
+template <class T>
+void jacobi_svd_wide(const Mat& A, std::vector<T>& w, std::vector<T>& vt, std::vector<T>& u) {
+    const int m = A.rows, n = A.cols;
+    std::vector<T> a((size_t)m * n), g((size_t)m * m, T(0));
+    for (int r = 0; r < m; r++) for (int c = 0; c < n; c++) a[(size_t)r * n + c] = (T)A.get(r, c);
+    for (int i = 0; i < m; i++) g[(size_t)i * m + i] = 1;
+    const double eps = sizeof(T) == 4 ? 2.0 * FLT_EPSILON : 10.0 * DBL_EPSILON;
+    for (int sweep = 0; sweep < std::max(n, 30); sweep++) {
+        bool changed = false;
+        for (int p = 0; p < m - 1; p++)
+            for (int q = p + 1; q < m; q++) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int c = 0; c < n; c++) {
+                    const double x = a[(size_t)p * n + c], y = a[(size_t)q * n + c];
+                    alpha += x * x; beta += y * y; gamma += x * y;
+                }
+                if (gamma == 0 || std::fabs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+                changed = true;
+                const double zeta = (beta - alpha) / (2 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
+                const double c = 1 / std::sqrt(1 + t * t), sn = c * t;
+                for (int k = 0; k < n; k++) {
+                    const double x = a[(size_t)p * n + k], y = a[(size_t)q * n + k];
+                    a[(size_t)p * n + k] = (T)(c * x - sn * y);
+                    a[(size_t)q * n + k] = (T)(sn * x + c * y);
+                }
+                for (int k = 0; k < m; k++) {                     // U = (product of the row rotations)': its columns p, q turn the same way
+                    const double x = g[(size_t)k * m + p], y = g[(size_t)k * m + q];
+                    g[(size_t)k * m + p] = (T)(c * x - sn * y);
+                    g[(size_t)k * m + q] = (T)(sn * x + c * y);
+                }
+            }
+        if (!changed) break;
+    }
+    std::vector<double> norm(m);
+    std::vector<int> order(m);
+    for (int i = 0; i < m; i++) {
+        double s2 = 0;
+        for (int c = 0; c < n; c++) s2 += (double)a[(size_t)i * n + c] * a[(size_t)i * n + c];
+        norm[i] = std::sqrt(s2);
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return norm[x] > norm[y]; });
+    w.assign(m, T(0)); vt.assign((size_t)m * n, T(0)); u.assign((size_t)m * m, T(0));
+    for (int i = 0; i < m; i++) {
+        const int j = order[i];
+        w[i] = (T)norm[j];
+        for (int c = 0; c < n; c++) vt[(size_t)i * n + c] = norm[j] > 0 ? (T)(a[(size_t)j * n + c] / norm[j]) : T(c == i);
+        for (int r = 0; r < m; r++) u[(size_t)r * m + i] = g[(size_t)r * m + j];
+    }
+}
+
 template <class T> void svd_t(const Mat& A, Mat& w, Mat& u, Mat& vt, bool full) {
     std::vector<T> ws, vts, us;
     const int m = A.rows, n = A.cols, k = std::min(m, n);
+    if (!full && m < n) {
+        jacobi_svd_wide<T>(A, ws, vts, us);
+        put<T>(w, m, 1, ws.data(), 1);
+        put<T>(vt, m, n, vts.data(), n);
+        put<T>(u, m, m, us.data(), m);
+        return;
+    }
     jacobi_svd<T>(A, ws, vts, us, full ? m : k);
     put<T>(w, k, 1, ws.data(), 1);
     put<T>(vt, full ? n : k, n, vts.data(), n);

@@ -428,6 +428,66 @@ static int solve_fundamental7(const float* pts, const int* s, float* out) {
     return valid;
 }
 
+/* SURVEY.md Appendix B, quirk 1 (documented switch, orc_config::ref_thin_svd / orc_solve_homography_dlt4p_thin): what the reference's
+ * own minimal homography solver computes. DLt::DLT4p (dlt.cpp:7-53) stacks the 8 x 9 system from RAW pixel coordinates in float32
+ * (:17-41), calls cv::SVD::compute on it and takes vt.row(vt.rows - 1) (:43-48). For an 8 x 9 matrix OpenCV's SVD is THIN: vt is
+ * 8 x 9, its last row is the right singular vector of the SMALLEST OF THE 8 singular values - not the null vector (the 9th, which a
+ * thin SVD never returns). H = that row / h33 (:50). The product path and the oracle's default solve the normalised DLT for the true
+ * null vector (what BASELINE.json names); this function exists so that the difference is a switch one can turn, not a silent fix.
+ * Numerics: one-sided (Hestenes) Jacobi in double on the 8 rows of A - rotating pairs of rows until they are mutually orthogonal
+ * leaves sigma_i v_i' in row i; the row of smallest norm, normalised, is the wanted vector (sign cancels in the division by h33). */
+static int solve_homography4_thin_svd(const float* pts, const int* s, float* out) {
+    double R[8][9];
+    for (int i = 0; i < 4; i++) {
+        const float* p = pts + 4 * (size_t)s[i];
+        const float x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+        const float r0[9] = {-x1, -y1, -1.f, 0.f, 0.f, 0.f, x2 * x1, x2 * y1, x2};      /* float products, like the Mat_<float> A */
+        const float r1[9] = {0.f, 0.f, 0.f, -x1, -y1, -1.f, y2 * x1, y2 * y1, y2};
+        for (int k = 0; k < 9; k++) { R[2 * i][k] = r0[k]; R[2 * i + 1][k] = r1[k]; }
+    }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotations = 0;
+        for (int a = 0; a < 7; a++) {
+            for (int b = a + 1; b < 8; b++) {
+                double aa = 0, bb = 0, ab = 0;
+                for (int k = 0; k < 9; k++) { aa += R[a][k] * R[a][k]; bb += R[b][k] * R[b][k]; ab += R[a][k] * R[b][k]; }
+                if (ab == 0.0 || std::fabs(ab) <= 1e-15 * std::sqrt(aa * bb)) continue;
+                const double zeta = (bb - aa) / (2.0 * ab);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+                for (int k = 0; k < 9; k++) {
+                    const double ra = R[a][k], rb = R[b][k];
+                    R[a][k] = c * ra - sn * rb;
+                    R[b][k] = sn * ra + c * rb;
+                }
+                rotations++;
+            }
+        }
+        if (!rotations) break;
+    }
+    int last = 0;
+    double least = -1;
+    for (int i = 0; i < 8; i++) {
+        double nn = 0;
+        for (int k = 0; k < 9; k++) nn += R[i][k] * R[i][k];
+        if (least < 0 || nn < least) { least = nn; last = i; }
+    }
+    /* vt.row(7) is a unit vector in float32; H = H / H.at<float>(2,2) is a float division (dlt.cpp:48-50) */
+    const double norm = std::sqrt(least);
+    if (!(norm > 0)) return 0;
+    float v[9];
+    for (int k = 0; k < 9; k++) v[k] = (float)(R[last][k] / norm);
+    for (int k = 0; k < 9; k++) {
+        out[k] = v[k] / v[8];
+        if (!std::isfinite(out[k])) return 0;
+    }
+    return 1;
+}
+
+extern "C" int orc_solve_homography_dlt4p_thin(const float* points, const int* sample, float* model_out) {
+    return solve_homography4_thin_svd(points, sample, model_out);
+}
+
 extern "C" int orc_solve_minimal(int estimator, const float* points, const int* sample, float* models_out) {
     switch (estimator) {
         case ORC_EST_LINE2D: return solve_line(points, sample, models_out);

@@ -50,6 +50,9 @@ int orc_inv3x3(const float* m, float* out);
 
 /* ---- minimal solvers: returns number of models written to models_out (<= 3 models x 9 floats; line: 3 floats) ---- */
 int orc_solve_minimal(int estimator, const float* points, const int* sample, float* models_out);
+/* SURVEY.md Appendix B quirk 1 as a switch: the reference's DLt::DLT4p (dlt.cpp:7-53: raw coordinates, last row of a THIN SVD = the 8th
+ * singular vector, not the null vector). Returns the number of models (0/1). orc_config::ref_thin_svd runs a whole fit with it. */
+int orc_solve_homography_dlt4p_thin(const float* points, const int* sample, float* model_out);
 /* pieces exposed for unit tests */
 int orc_solve_cubic(const double c[4], double roots[3]);       /* c0 x^3 + c1 x^2 + c2 x + c3, cv::solveCubic order */
 int orc_fundamental_is_valid(const float* points, const float* F, const int* sample);
@@ -100,6 +103,7 @@ typedef struct {
     unsigned sample_table_rows;
     const int* knn_table;     /* neighbors==KNN: n x knn */
     int lo;                   /* LocOpt: 0 none, 1 InItLORsc, 2 InItFLORsc (model.hpp:13; inner_local_optimization.hpp) */
+    int ref_thin_svd;         /* Appendix B quirk 1: 1 = homography samples go through the reference's DLT4p (orc_solve_homography_dlt4p_thin) */
 } orc_config;
 
 typedef struct {

@@ -335,12 +335,16 @@ extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc
 
     int sample[8];
     float models[3 * 9];
+    auto solve = [&](const int* smp, float* mdl) {                    /* Appendix B quirk 1 as a switch */
+        if (cfg->ref_thin_svd && est == ORC_EST_HOMOGRAPHY) return orc_solve_homography_dlt4p_thin(points, smp, mdl);
+        return orc_solve_minimal(est, points, smp, mdl);
+    };
 
     if (cfg->batch <= 0) {
         /* ---------------- reference-sequential ---------------- */
         while (iters < max_iters) {
             draw(sample);
-            int nm = orc_solve_minimal(est, points, sample, models);
+            int nm = solve(sample, models);
             for (int i = 0; i < nm; i++) {
                 int cur_inl = 0; float cur_score = 0;
                 const float* mdl = models + 9 * i;
@@ -377,7 +381,7 @@ extern "C" int orc_ransac(const orc_config* cfg, const float* points, int n, orc
                 else
                     orc_sampler_generate(sampler, hyp, &samples[(size_t)j * m]);
                 hyp++;
-                nmodels[j] = orc_solve_minimal(est, points, &samples[(size_t)j * m], &rmodels[(size_t)j * S * 9]);
+                nmodels[j] = solve(&samples[(size_t)j * m], &rmodels[(size_t)j * S * 9]);
             }
             const SprtTest frozen = cfg->sprt ? sprt.hist[sprt.cur] : SprtTest();
             for (int j = 0; j < K; j++) {

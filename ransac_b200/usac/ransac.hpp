@@ -6,9 +6,9 @@
 //                    Sampler, Estimator, Quality, SPRT, TerminationCriteria / ProsacTerminationCriteria, LocalOptimization -
 //                    each call forwarding to the C ABI: the drop-in at plugin granularity. Without SPRT, run() with
 //                    Model::gpu_round_size = 1 is the same loop (and without PROSAC every round size is). With SPRT a round freezes
-//                    the test and starts model q of the round at pool offset cursor + 32 q (the oracle's batch = K form), while
+//                    the test and starts model q of the round at pool offset cursor + 32 q (rounds-of-K semantics), while
 //                    the sequential walk starts where the last one stopped: about one SPRT fit in ten ends differently even at
-//                    K = 1 (tools/stress_harness.py holds each form to its own oracle loop).
+//                    K = 1 (tools/stress_harness.py checks each form against its own CPU restatement).
 #pragma once
 #include <chrono>
 

@@ -404,3 +404,36 @@ def test_local_optimisation_lifts_minimal_models():
     base = O.ransac(pts, O.EST_FUNDAMENTAL, seed=3, max_iterations=2000)
     r = O.ransac(pts, O.EST_FUNDAMENTAL, seed=3, max_iterations=2000, lo=1)
     assert r["inliers"] > base["inliers"]
+
+
+def test_reference_dlt4p_switch_matches_opencv(golden_dir):
+    """SURVEY Appendix B quirk 1 as a documented switch: orc_solve_homography_dlt4p_thin restates the reference's OWN minimal
+    homography solver (dlt.cpp:7-53: raw pixel coordinates, float32 system, last row of the THIN SVD = the 8th singular vector).
+    Pinned against that code path on the real OpenCV: tests/golden/dlt4p_cv.npz holds cv2.SVDecomp's row for 256 samples
+    (make_dlt4p_golden.py). sigma_8 / sigma_1 ~ 1e-7, so agreement is to float32 conditioning: median 1e-5, worst case < 2 %.
+    The vector is NOT the null vector: the model misses its own four points by pixels, where the default solver (normalised DLT,
+    true null vector: what BASELINE.json names and the GPU computes) passes through them."""
+    d = np.load(os.path.join(golden_dir, "dlt4p_cv.npz"))
+    s = np.arange(4, dtype=np.int32)
+    rel, own_thin, own_null = [], [], []
+    for pts, H in zip(d["pts"], d["H"]):
+        o = O.solve_homography_dlt4p_thin(pts, s)
+        assert len(o) == 1
+        rel.append(np.abs(o[0] - H).max() / np.abs(H).max())
+        own_thin.append(O.errors(O.EST_HOMOGRAPHY, pts, o[0]).max())
+        m = O.solve_minimal(O.EST_HOMOGRAPHY, pts, s)
+        if len(m):
+            own_null.append(O.errors(O.EST_HOMOGRAPHY, pts, m[0]).max())
+    rel = np.array(rel)
+    assert np.median(rel) < 1e-4 and np.quantile(rel, 0.9) < 1e-3 and rel.max() < 2e-2
+    assert np.median(own_thin[:128]) > 0.5 and np.median(own_null[:128]) < 1e-2
+
+
+def test_reference_dlt4p_switch_in_the_whole_fit():
+    """orc_config::ref_thin_svd runs Ransac::run with the reference's solver: the termination criterion never fires (no sample model
+    reaches the inlier count of a correct one), while the default stops early with the full inlier set."""
+    pts, H, mask = gen.make(2)
+    a = O.ransac(pts, O.EST_HOMOGRAPHY, threshold=2.0, confidence=0.95, max_iterations=2000, seed=5, ref_thin_svd=True)
+    b = O.ransac(pts, O.EST_HOMOGRAPHY, threshold=2.0, confidence=0.95, max_iterations=2000, seed=5)
+    assert a["iterations"] == 2000 and a["inliers"] < 0.5 * mask.sum()
+    assert b["iterations"] < 1000 and b["inliers"] > 0.75 * mask.sum()

@@ -175,6 +175,31 @@ def test_reference_four_point_dlt_is_not_a_minimal_solver():
     assert a["iterations"] == 3000 and b["iterations"] < 1500
 
 
+def test_reference_four_point_dlt_against_opencv_and_the_oracle_switch(golden_dir):
+    """The same solver three ways (SURVEY Appendix B quirk 1): (i) the compiled reference's DLt::DLT4p on the stand-in SVD of
+    oracle/ref_shim (which, like cv::SVD, orthogonalises the ROWS of a wide matrix), (ii) the oracle's documented switch
+    orc_solve_homography_dlt4p_thin, (iii) the real OpenCV on the same float32 system (tests/golden/dlt4p_cv.npz). All three agree
+    to float32 conditioning (sigma_8 / sigma_1 ~ 1e-7), and a whole fit with the switch behaves like the compiled reference's
+    Ransac::run: every iteration spent, the same inlier set after the non-minimal refit."""
+    import os
+    d = np.load(os.path.join(golden_dir, "dlt4p_cv.npz"))
+    s = np.arange(4, dtype=np.int32)
+    ref_cv, ref_orc = [], []
+    for pts, H in zip(d["pts"], d["H"]):
+        r, o = R.solve_minimal(O.EST_HOMOGRAPHY, pts, s), O.solve_homography_dlt4p_thin(pts, s)
+        assert len(r) == 1 and len(o) == 1
+        ref_cv.append(np.abs(r[0] - H).max() / np.abs(H).max())
+        ref_orc.append(np.abs(r[0] - o[0]).max() / np.abs(H).max())
+    for rel in (np.array(ref_cv), np.array(ref_orc)):
+        assert np.median(rel) < 1e-4 and np.quantile(rel, 0.9) < 1e-3 and rel.max() < 2e-2
+    pts, H, mask = gen.make(2)
+    for seed in (1, 2):
+        a = R.ransac_run(O.EST_HOMOGRAPHY, pts, 2.0, conf=0.95, max_it=3000, seed=seed)
+        b = O.ransac(pts, O.EST_HOMOGRAPHY, rng=O.RNG_GLIBC, threshold=2.0, confidence=0.95, max_iterations=3000, seed=seed, ref_thin_svd=True)
+        fin = O.refit(O.EST_HOMOGRAPHY, pts, b["model"], b["inliers"], 2.0)
+        assert a["iterations"] == b["iterations"] == 3000 and a["inliers"] == fin["inliers"]
+
+
 def test_nonminimal_solvers_agree():
     """Normalised DLT / 8-point on >= 20 points (2N x 9 resp. N x 9 with at least 9 rows: the thin SVD's last row IS the null
     vector there): unit-norm models agree to 1e-4 (BASELINE.json's model tolerance); the oracle uses an eigen-solve of A'A."""
