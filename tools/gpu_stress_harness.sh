@@ -1,4 +1,6 @@
 #!/bin/bash
+# 1 GPU: the plug-in layer sweep with NAPSAC cases (rounds of 1 and of 8)
 mkdir -p gpurun_out
 make -s -C ransac_b200/usac
-timeout 900 python tools/stress_harness.py 60 1 > gpurun_out/stress_harness.txt 2>&1; echo "rc=$?"; tail -8 gpurun_out/stress_harness.txt | cut -c1-400
+timeout 400 python tools/stress_harness.py 40 3 1 napsac > gpurun_out/stress_harness_napsac_r1.txt 2>&1; echo "rc=$?"; tail -6 gpurun_out/stress_harness_napsac_r1.txt | cut -c1-600
+timeout 400 python tools/stress_harness.py 30 4 8 napsac > gpurun_out/stress_harness_napsac_r8.txt 2>&1; echo "rc=$?"; tail -6 gpurun_out/stress_harness_napsac_r8.txt | cut -c1-600

@@ -6,7 +6,7 @@ oracle's sequential loop (batch = 0: the reference's semantics); the fused run()
 SPRT the two are the same loop, with SPRT a round freezes the test and starts model q at pool offset cursor + 32 q (SURVEY hard part 3),
 which differs from the sequential walk (next model starts where the last one stopped) even for K = 1 - about one SPRT fit in ten ends
 with another iteration count or model.
-usage: stress_harness.py [cases=40] [seed=0] [round=1]"""
+usage: stress_harness.py [cases=40] [seed=0] [round=1] [napsac]"""
 import os
 import subprocess
 import sys
@@ -23,6 +23,7 @@ HARNESS = os.path.join(ROOT, "ransac_b200", "usac", "usac_harness")
 CASES = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 g = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 ROUND = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+NAPSAC = len(sys.argv) > 4 and sys.argv[4] == "napsac"          # homography cases also draw NAPSAC (grid / kNN) samplers
 NAMES = {1: "line2d", 2: "homography", 3: "fundamental", 4: "essential"}
 EST = {1: O.EST_LINE2D, 2: O.EST_HOMOGRAPHY, 3: O.EST_FUNDAMENTAL, 4: O.EST_ESSENTIAL}
 
@@ -53,11 +54,15 @@ with tempfile.TemporaryDirectory() as tmp:
         cfg = int(g.choice([1, 2, 2, 3, 4]))
         est = EST[cfg]
         n = int(g.integers(300, 2500))
-        pts = gen.make(cfg, seed_offset=7000 + case, n=n, inlier_ratio=float(g.choice([0.3, 0.5, 0.7])))[0]
-        n = len(pts)
+        ratio = float(g.choice([0.3, 0.5, 0.7]))
         thr = 8.0 if cfg == 1 else (2.5e-3 if cfg == 4 else 2.0)
         seed, max_it = int(g.integers(1, 500)), int(g.choice([100, 400]))
         sampler = "uniform" if cfg == 1 else str(g.choice(["uniform", "uniform", "prosac"]))
+        knn = 0
+        if NAPSAC and cfg == 2 and g.random() < 0.6:                     # NAPSAC over the cell grid (cell 50) or the k nearest neighbours
+            sampler, knn = "napsac", int(g.choice([0, 0, 5, 8]))
+        pts = gen.make(cfg, seed_offset=7000 + case, n=n, inlier_ratio=ratio, **({"clustered": True} if sampler == "napsac" else {}))[0]
+        n = len(pts)
         sprt = bool(g.random() < 0.5)
         lo = 0 if cfg == 1 else int(g.choice([0, 0, 1, 2]))
         path = os.path.join(tmp, "p.txt")
@@ -70,6 +75,8 @@ with tempfile.TemporaryDirectory() as tmp:
             cmd.append("--sprt")
         if lo:
             cmd += ["--lo", str(lo)]
+        if knn:
+            cmd += ["--knn", str(knn)]
         tag = f"case {case}: {' '.join(cmd[2:])} n {n}"
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         if r.returncode != 0:
@@ -79,8 +86,12 @@ with tempfile.TemporaryDirectory() as tmp:
         f, s = got["fused"], got["sequential"]
         wants = {}
         for name, batch in (("sequential", 0), ("fused", ROUND)):
-            ref = O.ransac(pts, est, sampler=O.SAMPLER_PROSAC if sampler == "prosac" else O.SAMPLER_UNIFORM, rng=O.RNG_PHILOX, threshold=thr,
-                           confidence=0.95, max_iterations=max_it, seed=seed, sprt=sprt, lo=lo, batch=batch)
+            kw = {"sampler": O.SAMPLER_PROSAC if sampler == "prosac" else O.SAMPLER_UNIFORM}
+            if sampler == "napsac":
+                kw = {"sampler": O.SAMPLER_NAPSAC, "neighbors": O.NEIGH_KNN, "knn_table": O.knn_build(pts, knn)} if knn else \
+                     {"sampler": O.SAMPLER_NAPSAC, "neighbors": O.NEIGH_GRID, "cell_size": 50}
+            ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=0.95, max_iterations=max_it, seed=seed, sprt=sprt, lo=lo,
+                           batch=batch, **kw)
             fin = O.refit(est, pts, ref["model"], ref["inliers"], thr)
             wants[name] = {"iterations": ref["iterations"], "inliers": fin["inliers"], "hash": fnv(fin["ids"][:fin["inliers"]]),
                            "model": np.asarray(fin["model"], np.float32).view(np.uint32)}
