@@ -325,6 +325,15 @@ __global__ void sample_kernel(const RoundArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // Minimal solvers: one thread per sample (Estimator::EstimateModel, estimator.hpp:19)
 // ---------------------------------------------------------------------------------------------------------------
+// How far the sequential loop `while (iters < max_iters)` (ransac.cpp:58) can still get: max_iters - and, while max_iters is the value
+// the standard criterion CAPS at (max_iterations: the initial bound, or a best model whose w^m is below 0.0005), the peak of the
+// termination table, because the next better model may answer an uncapped, larger bound (found by the parity sweep: max_iterations
+// 50, round size 32: the sequential loop went on to sample 61, the round had dropped samples 50..63 as out of reach).
+__device__ __forceinline__ unsigned samples_in_reach(const RoundArgs& a, const ProblemDesc& pd, const FitState& st) {
+    unsigned reach = st.max_iters;
+    if (a.term_tables && pd.term_off >= 0 && st.max_iters == a.max_iterations) reach = max(reach, a.term_tables[pd.term_off + (size_t)pd.n + 1]);
+    return reach;
+}
 template <int EST>
 __global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
     const int slot = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,11 +341,12 @@ __global__ void __launch_bounds__(64) solve_kernel(const RoundArgs a) {
     int* nm = a.nmodels + (size_t)slot * a.K + j;
     if (a.nranks > 1 && (j % a.nranks) != a.rank) { *nm = 0; return; }     // another rank's hypothesis
     const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
     if (a.limit_remaining) {
         const FitState& st = a.state[pid];
-        if (st.max_iters <= st.iters || (unsigned)j >= st.max_iters - st.iters) { *nm = 0; return; }
+        const unsigned reach = samples_in_reach(a, pd, st);
+        if (reach <= st.iters || (unsigned)j >= reach - st.iters) { *nm = 0; return; }
     }
-    const ProblemDesc pd = a.prob[pid];
     const float* pts = a.aos + (size_t)pd.aos_off * (EST == USAC_EST_LINE2D ? 2 : 4);
     int s[8];
     const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;
@@ -362,11 +372,12 @@ __global__ void __launch_bounds__(32 * E5_WARPS_PER_CTA, E5_MIN_CTAS) solve_kern
     int* nm = a.nmodels + (size_t)slot * a.K + j;
     if (a.nranks > 1 && (j % a.nranks) != a.rank) { if (lane == 0) *nm = 0; return; }
     const int pid = a.active[slot];
+    const ProblemDesc pd = a.prob[pid];
     if (a.limit_remaining) {
         const FitState& st = a.state[pid];
-        if (st.max_iters <= st.iters || (unsigned)j >= st.max_iters - st.iters) { if (lane == 0) *nm = 0; return; }
+        const unsigned reach = samples_in_reach(a, pd, st);
+        if (reach <= st.iters || (unsigned)j >= reach - st.iters) { if (lane == 0) *nm = 0; return; }
     }
-    const ProblemDesc pd = a.prob[pid];
     const float* pts = a.aos + (size_t)pd.aos_off * 4;
     int s[8];
     const int* src = a.samples + ((size_t)slot * a.K + j) * a.m;

@@ -18,6 +18,9 @@
 struct SprtModelResult { int good, tested_inl, tested_pts, full_inl; };
 // a walk handed from the thread-per-model head to the warp-per-model tail
 struct SprtCarry { int q, tp, tin, rejected; double lambda; unsigned start; int count_all; };
+#ifndef USAC_SPRT_LOGWALK
+#define USAC_SPRT_LOGWALK 1          // 1: the warp tail decides 64-point steps in the log domain (fixed point), exact chain only when too close to call
+#endif
 #ifndef USAC_SPRT_HEAD
 #define USAC_SPRT_HEAD 64            // points a model walks in the thread-per-model kernel (even)
 #endif
@@ -142,7 +145,96 @@ __device__ __forceinline__ SprtModelResult sprt_walk_warp(const float* __restric
         decide_pair<EST>(fm, rec, P, n, a, b, i0, i1, in0, in1);
         return (unsigned long long)__ballot_sync(0xffffffffu, in0) | ((unsigned long long)__ballot_sync(0xffffffffu, in1) << 32);
     };
+    // four 64-point steps at once: the 8 point loads of a lane are in flight together (one warp walks alone: without this every step
+    // waits for its own two loads, ~160 dependent global-memory latencies for N = 10 000)
+    auto decide256 = [&](int done, unsigned long long* mm) {
+        PoolPoint<EST> pa[4], pb[4];
+        int i0[4], i1[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const unsigned base = (unsigned)(((unsigned long long)cy.start + (unsigned long long)done + 64ull * b) % un);
+            i0[b] = (int)((base + (unsigned)lane) % un); i1[b] = (int)((base + 32u + (unsigned)lane) % un);
+            pa[b].load(P, i0[b]); pb[b].load(P, i1[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            bool in0, in1;
+            decide_pair<EST>(fm, rec, P, n, pa[b], pb[b], i0[b], i1[b], in0, in1);
+            mm[b] = (unsigned long long)__ballot_sync(0xffffffffu, in0) | ((unsigned long long)__ballot_sync(0xffffffffu, in1) << 32);
+        }
+    };
+#if USAC_SPRT_LOGWALK
+    // ---- the decision of a 64-point step WITHOUT the 64 dependent double multiplications (C3: a model that passes the test walks all
+    // N points; its N multiplications were 2/3 of the fit). While lambda is a normal double, the sequential product differs from
+    // the exact product r_in^i r_out^o lambda_0 by at most k 2^-53 relative after k steps, so log(lambda_k) = S_k +- err with
+    // S_k = log(lambda_0) + i_k log(r_in) + o_k log(r_out) kept in 64-bit FIXED POINT (2^-36; integer sums do not accumulate rounding:
+    // err <= 0.51 k units incl. the 1-ulp errors of log()). `margin` = 4 N + 1024 units. Per step:
+    //   * up = S + (positive parts of the step's terms) bounds every prefix of the step: up < log A - margin => no rejection in the
+    //     step, S moves by the step's total (warp-uniform integer work only);
+    //   * otherwise the lanes evaluate S_k for the 64 positions: the first k with S_k > log A + margin is THE rejecting point if no
+    //     earlier position lies within the margin of log A;
+    //   * once a prefix may fall below e^-600 (lambda about to leave the normal range: what a model that passes does after a few
+    //     thousand points) S becomes an UPPER BOUND of log(lambda): D' = max(D f (1 + 2^-53), e^-600) dominates the sequential value
+    //     (rounding and multiplication by a positive factor are monotone), and per step D_end <= max(S + total, -600 + positive
+    //     parts). The bound can only prove "no rejection".
+    // Anything else - a position inside the margin, the bound reaching log A, parameters outside the fixed-point range, a NaN - replays
+    // the walk with the exact chain below, from the carry. Checked against the sequential chain for every decision / tested_pts /
+    // tested_inl: tools/sprt_logwalk_sim.py (CPU model of exactly this logic) and the parity suite.
     if (good) {
+        const double Lin = log(r_in), Lout = log(r_out), LA = log(A), L0 = log(lambda);
+        const bool in_range = r_in > 0.0 && r_out > 0.0 && A > 0.0 && lambda > 1e-200 && lambda < 1e200 && fabs(Lin) < 64.0 && fabs(Lout) < 64.0 &&
+                              fabs(LA) < 64.0 && n <= (1 << 22);
+        if (in_range) {
+            const double sc = 68719476736.0;                                  // 2^36
+            const long long Lin_f = __double2ll_rn(Lin * sc), Lout_f = __double2ll_rn(Lout * sc), LA_f = __double2ll_rn(LA * sc);
+            const long long floor_f = __double2ll_rn(-600.0 * sc), margin = 4ll * n + 1024ll;
+            const long long LinP = max(Lin_f, 0ll), LinN = min(Lin_f, 0ll), LoutP = max(Lout_f, 0ll), LoutN = min(Lout_f, 0ll);
+            long long S = __double2ll_rn(L0 * sc);
+            bool bound_mode = false, replay = false, rejected = false;
+            int ftp = tp, ftin = tin;
+            unsigned long long mm[4];
+            int blk = 4;
+#pragma unroll 1
+            while (ftp < n) {
+                if (blk == 4) { decide256(ftp, mm); blk = 0; }                // blocks blk..3 of mm are the steps at ftp, ftp + 64, ...
+                const int cnt = min(64, n - ftp);
+                unsigned long long m = blk == 0 ? mm[0] : blk == 1 ? mm[1] : blk == 2 ? mm[2] : mm[3];
+                blk++;
+                if (cnt < 64) m &= (1ull << cnt) - 1ull;
+                const long long i = __popcll(m), o = cnt - i;
+                const long long up = S + i * LinP + o * LoutP, low = S + i * LinN + o * LoutN;
+                if (up < LA_f - margin) {                                     // no prefix of the step can reach log A
+                    if (low < floor_f) bound_mode = true;
+                    S = bound_mode ? max(S + i * Lin_f + o * Lout_f, floor_f + i * LinP + o * LoutP) : S + i * Lin_f + o * Lout_f;
+                    ftp += cnt; ftin += (int)i;
+                    continue;
+                }
+                if (bound_mode || low < floor_f) { replay = true; break; }    // an upper bound cannot place a rejection
+                unsigned long long hi = 0ull, band = 0ull;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = lane + 32 * h;
+                    const long long ik = __popcll(m & ((2ull << k) - 1ull)), ok = (k + 1) - ik;
+                    const long long Sk = S + ik * Lin_f + ok * Lout_f;
+                    const bool valid = k < cnt;
+                    const unsigned bh = __ballot_sync(0xffffffffu, valid && Sk > LA_f + margin);
+                    const unsigned bb = __ballot_sync(0xffffffffu, valid && Sk >= LA_f - margin && Sk <= LA_f + margin);
+                    hi |= (unsigned long long)bh << (32 * h); band |= (unsigned long long)bb << (32 * h);
+                }
+                if (!hi && !band) { S += i * Lin_f + o * Lout_f; ftp += cnt; ftin += (int)i; continue; }
+                const int first_hi = hi ? __ffsll((long long)hi) - 1 : 64, first_band = band ? __ffsll((long long)band) - 1 : 64;
+                if (first_band < first_hi) { replay = true; break; }          // too close to call in fixed point
+                ftin += __popcll(m & ((2ull << first_hi) - 1ull)); ftp += first_hi + 1; rejected = true;
+                break;
+            }
+            if (!replay) { tp = ftp; tin = ftin; good = !rejected; }
+            if (!replay && good) tp = n;                                      // (the loop below is skipped: tp == n)
+        }
+    }
+    if (good) {
+#else
+    if (good) {
+#endif
 #pragma unroll 1
         while (tp < n) {
             const int cnt = min(64, n - tp);
@@ -168,10 +260,13 @@ __device__ __forceinline__ SprtModelResult sprt_walk_warp(const float* __restric
         int done = tp, c = 0;
 #pragma unroll 1
         while (done < n) {
-            const int cnt = min(64, n - done);
-            const unsigned long long m = decide64(done);
-            c += __popcll(cnt == 64 ? m : (m & ((1ull << cnt) - 1ull)));
-            done += cnt;
+            unsigned long long mm[4];
+            decide256(done, mm);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int cnt = min(64, n - done);
+                if (cnt > 0) { c += __popcll(cnt == 64 ? mm[b] : (mm[b] & ((1ull << cnt) - 1ull))); done += cnt; }
+            }
         }
         res.full_inl = tin + c;
     }

@@ -979,19 +979,28 @@ extern "C" int usac_gpu_refit(usac_gpu_ctx* c, int problem, const float* model_i
 // function (prosac_sampler.hpp:62-114). Host libm on purpose: the bound is a function of the inlier count only, so a
 // table indexed by the count makes the device decision bit-identical to the host plugin's.
 // ------------------------------------------------------------------------------------------------------------------
+// Entry n + 1 is the table's PEAK. The bound is not monotone in the inlier count: below p = w^m < 0.0005 the criterion answers
+// max_iterations (standard_termination_criteria.hpp:57), the first count past that answers up to log(1 - conf) / log(1 - 0.0005)
+// (5990 at conf 0.95) - so with max_iterations below that figure a better model can RAISE the loop bound, and samples that look out
+// of reach at the start of a round are reached after all (solve_kernel's limit_remaining test reads the peak for that case).
 static void standard_termination_table(unsigned n, int m, float confidence, unsigned max_iterations, std::vector<unsigned>& out) {
-    out.resize((size_t)n + 1);
+    out.resize((size_t)n + 2);
     const float log_1_p = (float)logf(1 - confidence);
     auto fill = [&](unsigned lo, unsigned hi) {
         for (unsigned inl = lo; inl < hi; inl++) out[inl] = standard_termination_value(inl, n, m, log_1_p, max_iterations);
     };
     const unsigned total = n + 1;
     unsigned nthreads = total >= (1u << 16) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
-    if (nthreads <= 1) { fill(0, total); return; }
-    std::vector<std::thread> pool;                       // 1M-point problems: a million logf calls, spread over the host cores
-    const unsigned per = (total + nthreads - 1) / nthreads;
-    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(fill, std::min(total, t * per), std::min(total, (t + 1) * per));
-    for (auto& th : pool) th.join();
+    if (nthreads <= 1) fill(0, total);
+    else {
+        std::vector<std::thread> pool;                   // 1M-point problems: a million logf calls, spread over the host cores
+        const unsigned per = (total + nthreads - 1) / nthreads;
+        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(fill, std::min(total, t * per), std::min(total, (t + 1) * per));
+        for (auto& th : pool) th.join();
+    }
+    unsigned peak = 0;
+    for (unsigned inl = 0; inl < total; inl++) peak = std::max(peak, out[inl]);
+    out[total] = peak;
 }
 
 static void prosac_growth(unsigned n, unsigned m, std::vector<unsigned>& g) {

@@ -473,6 +473,27 @@ def assert_fit_equal_sprt(r, ref):
     assert r["score"] == ref["score"]                                 # under SPRT the score is the inlier count (sprt.hpp:240-241)
 
 
+@pytest.mark.parametrize("cfg,n,ratio,max_it,seed", [(2, 1501, 0.5, 20, 4), (2, 1501, 0.5, 50, 3), (3, 1201, 0.7, 20, 1), (3, 1201, 0.7, 50, 3),
+                                                     (4, 3013, 0.7, 20, 2), (4, 3013, 0.7, 50, 1), (2, 901, 0.7, 50, 15)])
+def test_fit_runs_past_max_iterations_like_the_reference(ctx, cfg, n, ratio, max_it, seed):
+    """The standard criterion answers max_iterations while w^m < 0.0005 and an UNCAPPED value (up to 5990 at confidence 0.95) from
+    the first count past that (standard_termination_criteria.hpp:52-62), so with a small max_iterations a better model RAISES the
+    bound of `while (iters < max_iters)` (ransac.cpp:58, :127) and the reference runs past max_iterations. Each of these fits does
+    (the oracle ends at 38 .. 121 iterations with the best sample beyond max_iterations): the round must not have dropped those
+    samples as out of reach. Every round size gives the sequential result. (Found by tools/stress_parity.py, seed 78.)"""
+    est = EST[gen.CONFIGS[cfg]["estimator"]]
+    thr, conf = gen.CONFIGS[cfg]["threshold"], gen.CONFIGS[cfg]["confidence"]
+    pts = gen.make(cfg, seed_offset=1686, n=n, inlier_ratio=ratio)[0]
+    ref = O.ransac(pts, est, rng=O.RNG_PHILOX, threshold=thr, confidence=conf, max_iterations=max_it, seed=seed)
+    assert ref["iterations"] > max_it + 5 and ref["best_hyp"] >= max_it
+    ctx.set_points(est, pts)
+    for K in (1, 7, 16, 32, 100, 512):
+        r = ctx.fit(thr, conf, max_it, seed=seed, round_size=K)[0]
+        for key in ("inliers", "iterations", "best_hyp", "best_model_idx"):
+            assert r[key] == ref[key], (K, key, r[key], ref[key])
+        assert np.array_equal(bits(r["model"]), bits(ref["model"])), K
+
+
 @pytest.mark.parametrize("cfg,K,max_it", [(1, 64, 2000), (2, 128, 10000), (2, 512, 10000), (3, 128, 1500)])
 def test_fit_sprt_matches_oracle(ctx, cfg, K, max_it):
     pts, gt, mask = gen.make(cfg) if cfg != 3 else gen.make(cfg, n=4000)
