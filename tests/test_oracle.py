@@ -437,3 +437,15 @@ def test_reference_dlt4p_switch_in_the_whole_fit():
     b = O.ransac(pts, O.EST_HOMOGRAPHY, threshold=2.0, confidence=0.95, max_iterations=2000, seed=5)
     assert a["iterations"] == 2000 and a["inliers"] < 0.5 * mask.sum()
     assert b["iterations"] < 1000 and b["inliers"] > 0.75 * mask.sum()
+
+
+def test_sprt_logwalk_model_agrees_with_the_sequential_chain():
+    """The log-domain decision rule of the SPRT tail kernel (sprt.cuh, USAC_SPRT_LOGWALK), restated step for step on the CPU, against
+    the sequential chain of double multiplications of sprt.hpp:205-234: every walk the rule decides gives the chain's decision,
+    tested points and tested inliers (tools/sprt_logwalk_sim.py exits non-zero on any difference)."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sprt_logwalk_sim.py")
+    r = subprocess.run([sys.executable, tool, "11", "500"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches 0" in r.stdout
