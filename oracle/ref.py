@@ -184,6 +184,18 @@ def knn(points, k):
     return out
 
 
+def shim_svd(A, depth64=False, flags=0):
+    """cv::SVD::compute of the stand-in OpenCV (oracle/ref_shim/cvshim.hpp) -> (w, u, vt) as float64 arrays"""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    r, c = A.shape
+    w, u, vt, dims = np.zeros(max(r, c)), np.zeros(max(r, c) ** 2), np.zeros(max(r, c) ** 2), np.zeros(5, np.int32)
+    dp = C.POINTER(C.c_double)
+    fn = lib().ref_shim_svd
+    fn.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.POINTER(C.c_int)]
+    fn(A.ctypes.data_as(dp), r, c, int(depth64), int(flags), w.ctypes.data_as(dp), u.ctypes.data_as(dp), vt.ctypes.data_as(dp), _i(dims))
+    return w[:dims[0]].copy(), u[:dims[1] * dims[2]].reshape(dims[1], dims[2]).copy(), vt[:dims[3] * dims[4]].reshape(dims[3], dims[4]).copy()
+
+
 def rpoly(coeffs_high_first):
     c = np.ascontiguousarray(coeffs_high_first, dtype=np.float64)
     deg = len(c) - 1

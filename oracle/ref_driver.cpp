@@ -262,4 +262,24 @@ int ref_ransac_run(int est, int sampler, int neighbors, int sprt, int lo, const 
     return 0;
 }
 
+// ---- the stand-in cv::SVD itself (oracle/ref_shim/cvshim.hpp), so that it can be held against the real OpenCV on the matrices the
+// reference feeds it (tests/golden/svd_cv.npz): A is rows x cols in double, converted to float32 when !depth64; flags as cv::SVD
+// (4 = FULL_UV). dims = {len(w), u.rows, u.cols, vt.rows, vt.cols}.
+int ref_shim_svd(const double* A, int rows, int cols, int depth64, int flags, double* w, double* u, double* vt, int* dims) {
+    cv::Mat M(rows, cols, depth64 ? CV_64F : CV_32F);
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < cols; c++) {
+            if (depth64) M.at<double>(r, c) = A[(size_t)r * cols + c];
+            else M.at<float>(r, c) = (float)A[(size_t)r * cols + c];
+        }
+    cv::Mat W, U, Vt;
+    cv::SVD::compute(M, W, U, Vt, flags);
+    auto get = [&](const cv::Mat& m, int r, int c) { return depth64 ? m.at<double>(r, c) : (double)m.at<float>(r, c); };
+    dims[0] = W.rows * W.cols; dims[1] = U.rows; dims[2] = U.cols; dims[3] = Vt.rows; dims[4] = Vt.cols;
+    for (int i = 0; i < dims[0]; i++) w[i] = W.rows > 1 ? get(W, i, 0) : get(W, 0, i);
+    for (int r = 0; r < U.rows; r++) for (int c = 0; c < U.cols; c++) u[(size_t)r * U.cols + c] = get(U, r, c);
+    for (int r = 0; r < Vt.rows; r++) for (int c = 0; c < Vt.cols; c++) vt[(size_t)r * Vt.cols + c] = get(Vt, r, c);
+    return 0;
+}
+
 }   // extern "C"
