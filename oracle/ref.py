@@ -196,6 +196,37 @@ def shim_svd(A, depth64=False, flags=0):
     return w[:dims[0]].copy(), u[:dims[1] * dims[2]].reshape(dims[1], dims[2]).copy(), vt[:dims[3] * dims[4]].reshape(dims[3], dims[4]).copy()
 
 
+def shim_eigen(A, depth64=False):
+    """cv::eigen of the stand-in OpenCV on a symmetric matrix -> (eigenvalues descending, eigenvectors as rows)"""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    ev, vec = np.zeros(n), np.zeros((n, n))
+    dp = C.POINTER(C.c_double)
+    fn = lib().ref_shim_eigen
+    fn.argtypes = [dp, C.c_int, C.c_int, dp, dp]
+    ok = fn(A.ctypes.data_as(dp), n, int(depth64), ev.ctypes.data_as(dp), vec.ctypes.data_as(dp))
+    return (ev, vec) if ok else None
+
+
+def shim_cubic(coeffs4):
+    c = np.ascontiguousarray(coeffs4, dtype=np.float64)
+    r = np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    fn = lib().ref_shim_cubic
+    fn.argtypes = [dp, dp]
+    n = fn(c.ctypes.data_as(dp), r.ctypes.data_as(dp))
+    return n, r
+
+
+def shim_inv3(m):
+    a = np.ascontiguousarray(m, dtype=np.float32).reshape(9)
+    out = np.zeros(9, np.float32)
+    fn = lib().ref_shim_inv3
+    fn.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    fn(_f(a), _f(out))
+    return out.reshape(3, 3)
+
+
 def rpoly(coeffs_high_first):
     c = np.ascontiguousarray(coeffs_high_first, dtype=np.float64)
     deg = len(c) - 1

@@ -282,4 +282,34 @@ int ref_shim_svd(const double* A, int rows, int cols, int depth64, int flags, do
     return 0;
 }
 
+// ---- the other stand-in numerical routines the path calls: cv::eigen (line2d_estimator.hpp:93), cv::solveCubic (seven_points.cpp:131),
+// cv::invert / Mat::inv of a float 3 x 3 (homography_estimator.hpp:35) - held against cv2 fixtures in tests/test_ref_build.py
+int ref_shim_eigen(const double* A, int n, int depth64, double* evals, double* evecs) {
+    cv::Mat M(n, n, depth64 ? CV_64F : CV_32F);
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) { if (depth64) M.at<double>(r, c) = A[r * n + c]; else M.at<float>(r, c) = (float)A[r * n + c]; }
+    cv::Mat D, V;
+    if (!cv::eigen(M, D, V)) return 0;
+    for (int i = 0; i < n; i++) {
+        evals[i] = depth64 ? D.at<double>(i) : (double)D.at<float>(i);
+        for (int c = 0; c < n; c++) evecs[i * n + c] = depth64 ? V.at<double>(i, c) : (double)V.at<float>(i, c);
+    }
+    return 1;
+}
+int ref_shim_cubic(const double* coeffs4, double* roots3) {
+    cv::Mat_<double> c(1, 4), r(1, 3);
+    for (int i = 0; i < 4; i++) c(0, i) = coeffs4[i];
+    for (int i = 0; i < 3; i++) r(0, i) = 0;
+    const int n = cv::solveCubic(c, r);
+    for (int i = 0; i < 3; i++) roots3[i] = r(0, i);
+    return n;
+}
+int ref_shim_inv3(const float* in9, float* out9) {
+    cv::Mat_<float> m(3, 3);
+    std::memcpy(m.data, in9, 36);
+    cv::Mat inv = m.inv();
+    for (int i = 0; i < 9; i++) out9[i] = inv.at<float>(i);
+    return 0;
+}
+
 }   // extern "C"

@@ -727,7 +727,9 @@ inline int solveCubic(const Mat& coeffs, Mat& roots) {
         a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
         const double Q = (a1 * a1 - 3 * a2) * (1. / 9), R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
         const double Qcubed = Q * Q * Q;
-        double d = Qcubed - R * R;
+        // OpenCV >= 4.5 expands Qcubed - R R so that the common terms a1^6 / 729 and a1^4 a2 / 81 cancel before rounding (mathfuncs.cpp);
+        // with the plain difference one of the 512 cubics of tests/golden/cv_primitives.npz gets another root COUNT than cv2's
+        double d = (a1 * a1 * (a2 * a2 - 4 * a1 * a3) + 2 * a2 * (9 * a1 * a3 - 2 * a2 * a2) - 27 * a3 * a3) * (1. / 108);
         if (d > 0) {
             const double theta = std::acos(R / std::sqrt(Qcubed)), sqrtQ = std::sqrt(Q);
             const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);

@@ -11,6 +11,8 @@ results go through a singular value decomposition.
   kind 5   4 x 4 float64            five_points.cpp:327        last row of vt (triangulation)
   kind 6   3 x 3 float64            five_points.cpp:341        singular values of an essential matrix
 
+Also eig_cv.npz: cv2.eigen on 64 symmetric 2 x 2 float32 scatter matrices (line2d_estimator.hpp:86-93).
+
 Stored per case: the matrix (float64 copy of the values in its own depth), kind, depth, flags, cv2's w and vt (zero padded to 9 x 9).
 Run in the build container: python tests/golden/make_svd_golden.py"""
 import os
@@ -90,3 +92,19 @@ for kind, dt, fl, A in cases:
 np.savez_compressed(os.path.join(OUT, "svd_cv.npz"), kind=np.array(kinds), depth=np.array(depths), flags=np.array(flags), shape=np.array(shapes),
                     A=np.stack(mats), w=np.stack(ws), vt=np.stack(vts), cv_version=cv2.__version__)
 print("wrote svd_cv.npz:", len(cases), "decompositions, OpenCV", cv2.__version__)
+
+# cv::eigen on the symmetric float32 matrices of the path: the 2 x 2 scatter matrix of the non-minimal line fit (line2d_estimator.hpp:86-93)
+eig_A, eig_vals, eig_vecs = [], [], []
+for t in range(64):
+    n_pts = int(g.choice([2, 5, 50, 500]))
+    ang = g.uniform(0, np.pi)
+    tt = g.uniform(-500, 500, n_pts)
+    xy = np.c_[500 + tt * np.cos(ang), 500 + tt * np.sin(ang)] + g.normal(0, 3.0, (n_pts, 2))
+    xy = xy.astype(np.float32)
+    m = xy.mean(0)
+    cov = ((xy - m).T @ (xy - m)).astype(np.float32)
+    cov[1, 0] = cov[0, 1]
+    ok, vals, vecs = cv2.eigen(cov)
+    eig_A.append(cov); eig_vals.append(vals.ravel()); eig_vecs.append(vecs)
+np.savez_compressed(os.path.join(OUT, "eig_cv.npz"), A=np.stack(eig_A), vals=np.stack(eig_vals), vecs=np.stack(eig_vecs), cv_version=cv2.__version__)
+print("wrote eig_cv.npz:", len(eig_A), "2 x 2 float32 eigen-decompositions")

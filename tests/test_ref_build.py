@@ -288,3 +288,29 @@ def test_stand_in_svd_against_opencv(golden_dir):
             assert np.median(errs) < 1e-5 and errs.max() < 2e-2
         else:
             assert errs.max() < (1e-10 if kind in (1, 5, 6) else 1e-4), (kind, errs.max())
+
+
+def test_stand_in_eigen_cubic_inverse_against_opencv(golden_dir):
+    """The other stand-in routines on the path, against cv2 fixtures: cv::eigen on the 2 x 2 float32 scatter matrix of the non-minimal
+    line fit (eig_cv.npz: values and vectors to float32 rounding), cv::solveCubic of the 7-point solver (cv_primitives.npz: the same
+    root COUNT and ORDER for all 512 cubics - which needs OpenCV's expanded discriminant - and the same values to 1e-9 except where
+    the trigonometric formula itself is ill-conditioned, <= 1e-5), Mat::inv of a float 3 x 3 (bit-identical, singular -> zeros)."""
+    import os
+    d = np.load(os.path.join(golden_dir, "eig_cv.npz"))
+    for A, vals, vecs in zip(d["A"], d["vals"], d["vecs"]):
+        e, v = R.shim_eigen(A, False)
+        assert np.abs(e - vals).max() <= 4e-7 * np.abs(vals).max()
+        for i in range(2):
+            assert min(np.abs(v[i] - vecs[i]).max(), np.abs(v[i] + vecs[i]).max()) < 1e-6
+    c = np.load(os.path.join(golden_dir, "cv_primitives.npz"))
+    loose = 0
+    for co, ref, n in zip(c["cubic_in"], c["cubic_out"], c["cubic_n"]):
+        k, r = R.shim_cubic(co)
+        assert k == n, co
+        for a, b in zip(r[:k], ref[:n]):
+            err = abs(a - b) / max(1.0, abs(b))
+            assert err < 1e-5, (co, a, b)
+            loose += err > 1e-9
+    assert loose <= 8
+    for m, ref in zip(c["inv_in"], c["inv_out"]):
+        assert np.array_equal(R.shim_inv3(m).view(np.uint32), ref.view(np.uint32))
