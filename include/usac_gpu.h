@@ -92,7 +92,10 @@ typedef struct {
     usac_sampler_cfg sampler;
     float threshold;             /* model.hpp:17 */
     float confidence;            /* model.hpp:18 desired_prob */
-    unsigned max_iterations;     /* model.hpp:22 */
+    unsigned max_iterations;     /* model.hpp:22. The initial bound of `while (iters < max_iters)` (ransac.cpp:58) and the value the standard
+                                  * criterion answers while w^m < 0.0005 - NOT a hard cap: as in the reference, a better model may answer a larger,
+                                  * uncapped bound (up to 5990 at confidence 0.95) and the fit then runs past max_iterations
+                                  * (standard_termination_criteria.hpp:52-62); usac_fit_result::iterations reports what was done */
     int sprt;                    /* model.hpp:38 */
     int round_size;              /* K: samples per round and problem; 0 = automatic */
     const int* sample_table;     /* rng == USAC_RNG_TABLE: rows of m indices, used by problem 0 */
