@@ -25,3 +25,17 @@ def test_randomised_parity_sweep_fallback_paths():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_parity.py"), "60", "11"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=900, env=env)
     assert r.returncode == 0 and ", 0 mismatches" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cases,seed,round_size", [(12, 3, 1), (8, 4, 8)])
+def test_randomised_sweep_through_the_plugin_layer(cases, seed, round_size):
+    """tools/stress_harness.py: random estimator / sampler (uniform, PROSAC, NAPSAC over the grid or the k nearest neighbours) / SPRT /
+    LO through ransac_b200/usac/usac_harness --both. The fused Ransac::run() must equal the oracle's rounds of K, the one-hypothesis-at-
+    a-time loop over the plug-in classes the oracle's sequential loop (= the compiled reference's semantics), both after the refit:
+    iterations, inliers, inlier list, model bits. (By hand: 140 runs, profiles/r2_stress_harness.txt.)"""
+    harness_dir = os.path.join(ROOT, "ransac_b200", "usac")
+    subprocess.check_call(["make", "-s", "-C", harness_dir])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_harness.py"), str(cases), str(seed), str(round_size), "napsac"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and ", 0 mismatches" in r.stdout, r.stdout[-4000:]
