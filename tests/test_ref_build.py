@@ -314,3 +314,18 @@ def test_stand_in_eigen_cubic_inverse_against_opencv(golden_dir):
     assert loose <= 8
     for m, ref in zip(c["inv_in"], c["inv_out"]):
         assert np.array_equal(R.shim_inv3(m).view(np.uint32), ref.view(np.uint32))
+
+
+def test_reference_runs_past_max_iterations():
+    """`max_iterations` is the INITIAL bound of `while (iters < max_iters)` (ransac.cpp:58), not a cap: the standard criterion answers
+    it only while w^m < 0.0005 and an uncapped value otherwise (standard_termination_criteria.hpp:52-62), so the compiled reference's
+    Ransac::run ends line fits with max_iterations 3 / 5 / 10 after 15 - 46 iterations - and so does the oracle, identically. (The GPU
+    side of this: test_fit_runs_past_max_iterations_like_the_reference.)"""
+    pts = gen.make(1)[0]
+    for conf in (0.99, 0.999999):
+        for max_it in (3, 5, 10):
+            for seed in (1, 4):
+                a = R.ransac_run(O.EST_LINE2D, pts, 8.0, conf=conf, max_it=max_it, seed=seed)
+                b = O.ransac(pts, O.EST_LINE2D, rng=O.RNG_GLIBC, threshold=8.0, confidence=conf, max_iterations=max_it, seed=seed)
+                assert a["iterations"] == b["iterations"] > max_it
+                assert a["inliers"] == O.refit(O.EST_LINE2D, pts, b["model"], b["inliers"], 8.0)["inliers"]
