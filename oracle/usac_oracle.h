@@ -6,12 +6,21 @@
  * bench.py's cpu_baseline / --impl reference legs may load it. The product (ransac_b200/) never links, imports or
  * falls back to it.
  *
- * Parity status: the homography and Sampson scoring functions are pinned by the 46 known-answer vectors recovered
- * from the reference's shipped datasets/results (tests/golden/scoring_kat.npz). Everything else (line/essential
- * scoring, solvers, samplers, SPRT, termination) is "parity unpinned" by the reference's own artefacts - the
- * reference cannot be compiled here (needs OpenCV-contrib/Eigen/nanoflann) - and is anchored on (a) identities
- * (solver output annihilates its sample, det F = 0 ...), (b) OpenCV primitives called through Python cv2 4.13
- * (tests/golden/make_cv_golden.py) and (c) the glibc random() stream of this container's libc.
+ * Parity status (DESIGN.md section 3 has the table):
+ *  - pinned by the reference's own artefacts: the homography and Sampson scoring functions reproduce the 46 known-answer vectors
+ *    recovered from the reference's shipped datasets/results (tests/golden/scoring_kat.npz);
+ *  - pinned by THE REFERENCE ITSELF, compiled here: oracle/_ref/libusac_ref.so is the reference's own usac/ sources built where they
+ *    lie (oracle/Makefile.ref; OpenCV / Eigen / nanoflann answered by the stand-ins of oracle/ref_shim/, whose SVD, eigen, solveCubic
+ *    and 3x3 inverse are themselves held against the real OpenCV: tests/golden/svd_cv.npz, eig_cv.npz, cv_primitives.npz).
+ *    tests/test_ref_build.py: all four GetError metrics and Quality::getNumberInliers, the uniform sampler's glibc stream, the PROSAC
+ *    schedule, standard and PROSAC termination, SPRT (decisions, counts, pool cursor, test history, iteration bound), the
+ *    neighbourhood structures and the line solver are BIT-IDENTICAL / index-identical to the compiled reference; Ransac::run as a
+ *    whole for line fits (also past max_iterations); the non-minimal, 7-point and 5-point solvers agree to float32 conditioning;
+ *  - the reference's quirks are kept, or are switches: orc_config::ref_thin_svd = its own 4-point DLT4p,
+ *    pinned against the real OpenCV (tests/golden/dlt4p_cv.npz) and the compiled reference;
+ *  - still "parity unpinned": what the reference computes THROUGH an OpenCV numerical routine whose low-order bits cannot be
+ *    reproduced here - the basis cv::SVD picks inside a null space (hence the root ORDER of the five-point solver and the float32
+ *    low bits of 7-point models). Those rows are capped at "partial" in DESIGN.md.
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  */
