@@ -8,8 +8,12 @@
  * per root the null vector of M(z) -> x, y -> E (:181-204), and the cheirality vote over the five points for the four
  * (R, t) decompositions (:206-252); one E (or none) is returned, cast to float (:28).
  *
- * "Parity unpinned": the reference cannot be built here, and it leans on cv::SVD and the Jenkins-Traub rpoly code. Where
- * the result is basis/ordering dependent this file fixes a deterministic choice, shared with the CUDA solver:
+ * Parity: "partial". The reference's own solver is compiled in oracle/_ref (five_points.cpp + rpoly.cpp + mblock.hpp on the
+ * stand-in cv::SVD, which agrees with the real OpenCV's null SPACE to 4e-14): tests/test_ref_build.py shows that the ONE matrix it
+ * returns is a member of this file's candidate set and cheirality-valid here (53 of 55 samples), and that rpoly's real roots are
+ * this file's roots (1e-6). What cannot be pinned is WHICH candidate comes first: that depends on the basis cv::SVD picks inside
+ * the null space and on Jenkins-Traub's visiting order ("parity unpinned" for the root order). Where the
+ * result is basis/ordering dependent this file fixes a deterministic choice, shared with the CUDA solver:
  *   - null spaces by Gauss-Jordan with partial pivoting (orc_null_space) instead of SVD rows (any basis spans the same E's);
  *   - polynomial coefficients by Newton divided differences instead of inverting the Vandermonde matrix;
  *   - real roots by derivative bracketing + bisection, visited in order of ascending |z| (Jenkins-Traub finds zeros in
